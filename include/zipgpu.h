@@ -1,0 +1,153 @@
+/*
+ * include/zipgpu.h -- C ABI of libzipgpu: the B200 (sm_100a) drop-in for the *commit* path of zinc's Zip PCS.
+ *
+ * The reference (NethermindEth/zinc, pure Rust) has no FFI seam; the seam this library is shaped for is the
+ * generic Rust API itself (citations relative to /root/reference):
+ *
+ *   MultilinearZip::commit            src/zip/pcs/commit.rs:50-87     -> zipgpu_commit / zipgpu_commit_device / zipgpu_commit_resident
+ *   MultilinearZip::commit_no_merkle  src/zip/pcs/commit.rs:104-119   -> zipgpu_encode_rows / zipgpu_encode_rows_device
+ *   MultilinearZip::batch_commit      src/zip/pcs/commit.rs:134-142   -> zipgpu_batch_commit
+ *   MultilinearZip::encode_rows       src/zip/pcs/commit.rs:158-183   -> zipgpu_encode_rows
+ *   RaaCode::{new,encode_inner}       src/zip/code_raa.rs:35-105      -> zipgpu_code_create (+ zipgpu_perm_from_seed)
+ *   MerkleTree::new                   src/zip/pcs/utils.rs:74-118     -> zipgpu_merkle_rows / zipgpu_merkle_rows_device
+ *   MerkleProof::create_proof,
+ *   ColumnOpening::open_at_column     src/zip/pcs/utils.rs:163-176,221-233, open_z.rs:124-143 -> zipgpu_data_open_columns
+ *
+ * Conventions
+ *   - Integers are the in-memory layout of `[Int<n>]`: n little-endian u64 limbs per value, least significant
+ *     limb first (field/int.rs:23-25,230-232).  `evals` is row-major: row i = evals[i*row_len .. (i+1)*row_len).
+ *   - `rows` (u-hat) is num_rows*cw values of out_limbs limbs, row-major (structs.rs:33-38).
+ *   - `layers` is, per row, (2<<depth)-2 BLAKE3 digests of 32 bytes laid out as MerkleTree::layers after the
+ *     root is popped (pcs/utils.rs:77-85): [leaf hashes (cw) | level depth-1 (cw/2) | ... | level 1 (2)];
+ *     rows are concatenated.  `roots` is num_rows*32 bytes (structs.rs:40-45).
+ *   - The two RAA permutations are inputs: perm[i] = index the shuffled slice takes element i from, i.e. the
+ *     array obtained by applying `shuffle_seeded(&mut v, seed)` (zip/utils.rs:139-142) to v = [0,1,..,cw).
+ *     A Rust host passes exactly that; zipgpu_perm_from_seed is a restatement of rand 0.9.2 for hosts
+ *     without the crate (parity with the real crate unpinned).
+ *   - Every function returns 0 on success or a negative zipgpu_status; it never aborts or unwinds.
+ *     zipgpu_last_error() gives a thread-local message for the last failure.
+ *   - `*_device` entry points take device pointers and enqueue on `stream` (a cudaStream_t passed as void*,
+ *     NULL = the context's own stream) without synchronising.  The others take HOST pointers, perform the
+ *     host<->device copies themselves (pipelined with the kernels) and return when the outputs are valid.
+ *   - A context is bound to one GPU.  Multi-GPU = one context (and one process/thread) per GPU, each working on a
+ *     contiguous row range (commit) or on a subset of the polynomials (batch_commit); see INTEGRATION.md.
+ */
+#ifndef ZIPGPU_H
+#define ZIPGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zipgpu_ctx zipgpu_ctx;
+typedef struct zipgpu_code zipgpu_code;
+typedef struct zipgpu_data zipgpu_data;
+
+typedef enum {
+    ZIPGPU_OK = 0,
+    ZIPGPU_ERR_INVALID = -1,     /* bad argument / shape (maps to Error::InvalidPcsParam or the reference's asserts) */
+    ZIPGPU_ERR_CUDA = -2,        /* CUDA runtime failure */
+    ZIPGPU_ERR_NOMEM = -3,       /* device or pinned-host allocation failed */
+    ZIPGPU_ERR_UNSUPPORTED = -4, /* shape outside what the kernels implement */
+    ZIPGPU_ERR_NO_DEVICE = -5,   /* no CUDA device / wrong architecture */
+    ZIPGPU_ERR_WIDTH = -6        /* code_raa.rs:68-72: out type too narrow for the codeword entries */
+} zipgpu_status;
+
+/* ---- library / context ------------------------------------------------------------------------------- */
+const char *zipgpu_version(void);
+const char *zipgpu_last_error(void);
+int zipgpu_device_count(int *count);
+
+int zipgpu_ctx_create(int device, zipgpu_ctx **out);
+void zipgpu_ctx_destroy(zipgpu_ctx *ctx);
+int zipgpu_ctx_device(const zipgpu_ctx *ctx);
+int zipgpu_ctx_sync(zipgpu_ctx *ctx);
+/* number of zipgpu kernels launched by this context so far (bench.py's gpu_launches) */
+uint64_t zipgpu_ctx_launch_count(const zipgpu_ctx *ctx);
+
+/* pinned host memory for the host-pointer entry points (pageable pointers also work, through a staging copy) */
+int zipgpu_host_alloc(size_t bytes, void **out);
+int zipgpu_host_free(void *p);
+int zipgpu_host_register(void *p, size_t bytes);
+int zipgpu_host_unregister(void *p);
+
+/* ---- code (RaaCode, per-pp state) -------------------------------------------------------------------- */
+/* shuffle_seeded(&mut [0..n), seed) restated (zip/utils.rs:139-142; rand 0.9.2).  Host-side, no GPU needed. */
+int zipgpu_perm_from_seed(uint64_t seed, uint32_t n, uint32_t *perm_out);
+/* RaaCode::new geometry (code_raa.rs:42-43), MultilinearZip::setup (structs.rs:79-90). Host-side. */
+size_t zipgpu_raa_row_len(size_t poly_size);
+size_t zipgpu_num_rows(size_t poly_size, size_t row_len);
+/* bits a codeword entry needs (code_raa.rs:53-67) */
+int zipgpu_raa_codeword_width_bits(int in_limbs, size_t poly_size, size_t repetition_factor);
+
+/* Uploads the permutations once per pp.  perm1/perm2: cw = row_len*repetition_factor entries each, validated
+ * to be permutations of [0,cw).  in_limbs/out_limbs: limbs of ZT::N and ZT::K (1 and 4 for INT_LIMBS=1).
+ * ZIPGPU_ERR_WIDTH if 64*out_limbs < 64*in_limbs + 2*ceil(log2(cw)) (the reference's width assert can then
+ * not hold for any poly_size with this cw). */
+int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t repetition_factor, int in_limbs, int out_limbs,
+                       const uint32_t *perm1, const uint32_t *perm2, zipgpu_code **out);
+void zipgpu_code_destroy(zipgpu_code *code);
+size_t zipgpu_code_row_len(const zipgpu_code *code);
+size_t zipgpu_code_codeword_len(const zipgpu_code *code);
+/* merkle depth = codeword_len.next_power_of_two().ilog2()  (commit.rs:67) */
+int zipgpu_code_merkle_depth(const zipgpu_code *code);
+
+/* ---- encode_rows / commit_no_merkle (commit.rs:104-119,158-183) -------------------------------------- */
+int zipgpu_encode_rows(zipgpu_code *code, size_t num_rows, const uint64_t *evals, uint64_t *rows_out);
+int zipgpu_encode_rows_device(zipgpu_code *code, size_t num_rows, const uint64_t *d_evals, uint64_t *d_rows_out,
+                              void *stream);
+
+/* ---- MerkleTree::new batched over rows (pcs/utils.rs:74-118) ----------------------------------------- */
+/* leaves: num_rows * (1<<depth) values of leaf_limbs limbs.  layers_out nullable.  roots_out: num_rows*32. */
+int zipgpu_merkle_rows(zipgpu_ctx *ctx, size_t num_rows, int depth, int leaf_limbs, const uint64_t *leaves,
+                       uint8_t *layers_out, uint8_t *roots_out);
+int zipgpu_merkle_rows_device(zipgpu_ctx *ctx, size_t num_rows, int depth, int leaf_limbs, const uint64_t *d_leaves,
+                              uint8_t *d_layers_out, uint8_t *d_roots_out, void *stream);
+
+/* ---- commit (commit.rs:50-87) ------------------------------------------------------------------------ */
+/* host buffers; rows_out / layers_out nullable (then they are not copied back; see zipgpu_commit_resident) */
+int zipgpu_commit(zipgpu_code *code, size_t num_rows, const uint64_t *evals, uint64_t *rows_out, uint8_t *layers_out,
+                  uint8_t *roots_out);
+/* device buffers; d_rows_out / d_layers_out nullable (internal scratch is used) */
+int zipgpu_commit_device(zipgpu_code *code, size_t num_rows, const uint64_t *d_evals, uint64_t *d_rows_out,
+                         uint8_t *d_layers_out, uint8_t *d_roots_out, void *stream);
+/* batch_commit (commit.rs:134-142): num_polys polynomials sharing one pp; evals[p] -> outputs[p] (arrays of
+ * host pointers; rows_out / layers_out may be NULL, or hold NULL entries) */
+int zipgpu_batch_commit(zipgpu_code *code, size_t num_polys, size_t num_rows, const uint64_t *const *evals,
+                        uint64_t *const *rows_out, uint8_t *const *layers_out, uint8_t *const *roots_out);
+
+/* ---- device-resident prover data (MultilinearZipData, structs.rs:33-38) ------------------------------ */
+/* host evals in, host roots out; rows + layers stay on the GPU behind *handle for the opening phase */
+int zipgpu_commit_resident(zipgpu_code *code, size_t num_rows, const uint64_t *evals, uint8_t *roots_out,
+                           zipgpu_data **handle);
+void zipgpu_data_free(zipgpu_data *data);
+size_t zipgpu_data_num_rows(const zipgpu_data *data);
+const uint64_t *zipgpu_data_rows_device(const zipgpu_data *data);
+const uint8_t *zipgpu_data_layers_device(const zipgpu_data *data);
+const uint8_t *zipgpu_data_roots_device(const zipgpu_data *data);
+/* copy a row range of `rows` / `layers` back to the host */
+int zipgpu_data_read_rows(const zipgpu_data *data, size_t row_begin, size_t row_count, uint64_t *rows_out);
+int zipgpu_data_read_layers(const zipgpu_data *data, size_t row_begin, size_t row_count, uint8_t *layers_out);
+/* Column openings (open_z.rs:124-143 + pcs/utils.rs:163-176,221-233): for each requested column j, the
+ * num_rows column entries rows[i*cw + j] (out_limbs limbs each) and, per row, the Merkle path of `depth`
+ * digests in create_proof order (sibling at the leaf level first).
+ *   col_values_out: num_cols * num_rows * out_limbs u64;  paths_out: num_cols * num_rows * depth * 32 bytes */
+int zipgpu_data_open_columns(const zipgpu_data *data, size_t num_cols, const uint32_t *columns,
+                             uint64_t *col_values_out, uint8_t *paths_out);
+
+/* ---- measurement helpers (used by bench.py; no reference counterpart) -------------------------------- */
+/* When enabled, every commit/encode/merkle call records CUDA events around its kernels on the launch stream. */
+int zipgpu_profile_enable(zipgpu_ctx *ctx, int on);
+/* Sums since the last reset, milliseconds of device time: encoder kernel, hash kernels; and call count. */
+int zipgpu_profile_read(zipgpu_ctx *ctx, double *encode_ms, double *hash_ms, uint64_t *calls, int reset);
+/* Dependency-free INT32 micro-benchmark: runs `iters` rounds of `kind` ops per thread on the whole GPU and
+ * returns achieved warp-level lane-ops/s.  kind 0 = LOP3/SHF/IADD3 (alu pipe), 1 = alu + IMAD mix. */
+int zipgpu_microbench_int32(zipgpu_ctx *ctx, int kind, int iters, double *lane_ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZIPGPU_H */

@@ -1,0 +1,25 @@
+"""zinc_b200 -- B200 (sm_100a) implementation of the commit path of zinc's Zip polynomial commitment.
+
+Only what the path needs: csrc/ (CUDA kernels + the C ABI of include/zipgpu.h, built into libzipgpu.so),
+and the host-side mirror of the reference's commit API (zip.py, transcript.py) over that C ABI.
+"""
+from .transcript import KeccakTranscript, MockTranscript  # noqa: F401
+from .zip import (  # noqa: F401
+    Context,
+    DefaultLinearCodeSpec,
+    DenseMultilinearExtension,
+    Error,
+    InvalidPcsParam,
+    MerkleProof,
+    MerkleTree,
+    MultilinearZip,
+    MultilinearZipCommitment,
+    MultilinearZipData,
+    MultilinearZipParams,
+    RaaCode,
+    RandomFieldZipTypes,
+    ResidentZipData,
+    ZipTypes,
+    default_context,
+    shuffle_seeded_indices,
+)

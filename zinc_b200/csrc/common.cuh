@@ -1,0 +1,59 @@
+// zinc_b200/csrc/common.cuh -- shared helpers for the sm_100a kernels of libzipgpu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace zipgpu {
+
+constexpr int kWarp = 32;
+
+// streaming (read-once) 16-byte global load / store: keep L1 for the tables that are reused
+__device__ __forceinline__ uint4 ld_stream_v4(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_v4(uint4 *p, const uint4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+
+// ---- multi-limb (W x u32, little-endian) wrap-around add: one carry chain per call ---------------------
+template <int W>
+__device__ __forceinline__ void add_limbs(uint32_t (&a)[W], const uint32_t (&b)[W]);
+
+template <>
+__device__ __forceinline__ void add_limbs<2>(uint32_t (&a)[2], const uint32_t (&b)[2]) {
+    asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(a[0]), "+r"(a[1]) : "r"(b[0]), "r"(b[1]));
+}
+template <>
+__device__ __forceinline__ void add_limbs<3>(uint32_t (&a)[3], const uint32_t (&b)[3]) {
+    asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, %5;"
+        : "+r"(a[0]), "+r"(a[1]), "+r"(a[2])
+        : "r"(b[0]), "r"(b[1]), "r"(b[2]));
+}
+template <>
+__device__ __forceinline__ void add_limbs<4>(uint32_t (&a)[4], const uint32_t (&b)[4]) {
+    asm("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %5;\n\taddc.cc.u32 %2, %2, %6;\n\taddc.u32 %3, %3, %7;"
+        : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3])
+        : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]));
+}
+template <>
+__device__ __forceinline__ void add_limbs<5>(uint32_t (&a)[5], const uint32_t (&b)[5]) {
+    asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, %7;\n\taddc.cc.u32 %3, %3, %8;\n\t"
+        "addc.u32 %4, %4, %9;"
+        : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4])
+        : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]));
+}
+template <>
+__device__ __forceinline__ void add_limbs<6>(uint32_t (&a)[6], const uint32_t (&b)[6]) {
+    asm("add.cc.u32 %0, %0, %6;\n\taddc.cc.u32 %1, %1, %7;\n\taddc.cc.u32 %2, %2, %8;\n\taddc.cc.u32 %3, %3, %9;\n\t"
+        "addc.cc.u32 %4, %4, %10;\n\taddc.u32 %5, %5, %11;"
+        : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5])
+        : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]));
+}
+
+}  // namespace zipgpu

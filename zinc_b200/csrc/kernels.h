@@ -1,0 +1,56 @@
+// zinc_b200/csrc/kernels.h -- host-visible launchers of the sm_100a kernels (internal to libzipgpu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace zipgpu {
+
+// ---- K1: RAA encoder (raa_encode.cu) ----
+struct EncodeArgs {
+    const uint32_t *evals;   // [num_rows][row_len][2*in_limbs]
+    uint32_t *rows_out;      // [num_rows][cw][out32]
+    const uint32_t *perm1;   // device, zero-padded to encode_perm_padded_len(cw)
+    const uint32_t *perm2;
+    uint32_t num_rows, row_len, cw, out32;
+    int in_limbs;
+    int num_sms;
+    cudaStream_t stream;
+};
+size_t encode_perm_padded_len(uint32_t cw);
+int encode_compute_limbs(int in_limbs, uint32_t cw);
+bool encode_supported(int in_limbs, uint32_t cw);
+cudaError_t launch_raa_encode(const EncodeArgs &a);
+
+// ---- K2/K3: BLAKE3 leaves + per-row Merkle levels (merkle.cu) ----
+struct MerkleArgs {
+    const uint32_t *leaves;  // [num_rows][1<<depth][leaf32]
+    uint8_t *layers;         // [num_rows][(2<<depth)-2][32]  (may be internal scratch)
+    uint8_t *roots;          // [num_rows][32]
+    uint32_t num_rows;
+    int depth;
+    int leaf32;
+    cudaStream_t stream;
+};
+bool merkle_supported(int leaf32);
+// returns the number of kernel launches through *launches
+cudaError_t launch_merkle_rows(const MerkleArgs &a, int *launches);
+
+// ---- K4: column openings (open_columns.cu) ----
+struct OpenArgs {
+    const uint32_t *rows;    // [num_rows][cw][out32]
+    const uint8_t *layers;   // [num_rows][(2<<depth)-2][32]
+    const uint32_t *columns; // device [num_cols]
+    uint32_t *col_values;    // [num_cols][num_rows][out32]
+    uint8_t *paths;          // [num_cols][num_rows][depth][32]
+    uint32_t num_rows, cw, out32, num_cols;
+    int depth;
+    cudaStream_t stream;
+};
+cudaError_t launch_open_columns(const OpenArgs &a);
+
+// ---- INT32 micro-benchmark (microbench.cu) ----
+cudaError_t launch_microbench_int32(int kind, int iters, int num_sms, cudaStream_t stream, uint32_t *d_sink,
+                                    double *lane_ops);
+
+}  // namespace zipgpu

@@ -1,0 +1,177 @@
+// zinc_b200/csrc/merkle.cu -- K2/K3: BLAKE3 leaf hashing and per-row Merkle levels for sm_100a.
+//
+// Replaces MerkleTree::new batched over all rows of a commit (zip/pcs/utils.rs:74-118, called once per row,
+// serially, from commit.rs:71-74).  The layers buffer reproduces `MerkleTree::layers` exactly:
+//   per row [leaf hashes (cw) | level depth-1 (cw/2) | ... | level 1 (2)], the root goes to roots[row].
+//
+// Design: the work is pure INT32 ALU (one compression per hash), so the kernels are organised to keep every
+// lane busy rather than around memory.  Each thread reduces 2^H *consecutive* children to one node with a
+// binary-counter stack held in registers (no shuffles, no shared memory, no idle lanes inside the subtree),
+// writing every intermediate level to `layers` on the way.  Level 0..3 (15/16 of all compressions) run in
+// the first pass; each further pass consumes 3 levels (the last one up to 4), batched over ALL rows so the
+// narrow top of the trees still fills the GPU (4096 rows x 1 node at nv=24).
+#include "blake3_dev.cuh"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace zipgpu {
+
+namespace {
+
+struct TreeGeom {
+    uint32_t cw;        // leaves per row = 1 << depth
+    uint32_t depth;
+    size_t row_stride;  // digests per row in layers = 2*cw - 2
+};
+
+// address of node `idx` of level `level` (0 = leaf hashes, depth = root) of row `row`
+__device__ __forceinline__ uint4 *node_ptr(uint8_t *layers, uint8_t *roots, const TreeGeom &g, uint32_t row,
+                                           uint32_t level, uint32_t idx) {
+    if (level == g.depth) return reinterpret_cast<uint4 *>(roots + (size_t)row * 32);
+    const size_t off = 2 * (size_t)g.cw - ((2 * (size_t)g.cw) >> level);
+    return reinterpret_cast<uint4 *>(layers + ((size_t)row * g.row_stride + off + idx) * 32);
+}
+
+__device__ __forceinline__ void store_digest(uint4 *p, const uint32_t (&d)[8]) {
+    p[0] = make_uint4(d[0], d[1], d[2], d[3]);
+    p[1] = make_uint4(d[4], d[5], d[6], d[7]);
+}
+__device__ __forceinline__ void load_digest(const uint4 *p, uint32_t (&d)[8]) {
+    const uint4 a = p[0], b = p[1];
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
+    d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+
+template <int LEAF32>
+__device__ __forceinline__ void load_leaf(const uint32_t *p, uint32_t (&x)[LEAF32]) {
+    if constexpr (LEAF32 % 4 == 0) {
+        const uint4 *p4 = reinterpret_cast<const uint4 *>(p);
+#pragma unroll
+        for (int i = 0; i < LEAF32 / 4; i++) {
+            const uint4 a = ld_stream_v4(p4 + i);
+            x[4 * i] = a.x; x[4 * i + 1] = a.y; x[4 * i + 2] = a.z; x[4 * i + 3] = a.w;
+        }
+    } else {
+        const uint2 *p2 = reinterpret_cast<const uint2 *>(p);
+#pragma unroll
+        for (int i = 0; i < LEAF32 / 2; i++) {
+            const uint2 a = __ldg(p2 + i);
+            x[2 * i] = a.x; x[2 * i + 1] = a.y;
+        }
+    }
+}
+
+// LEAF32 > 0: inputs are raw leaves (LEAF32 u32 words each), level_in must be 0 and level-0 digests are produced.
+// LEAF32 == 0: inputs are the digests of level `level_in`, already in `layers`.
+template <int LEAF32, int H>
+__global__ void __launch_bounds__(128)
+    merkle_subtree_kernel(const uint32_t *__restrict__ leaves, uint8_t *layers, uint8_t *roots, uint32_t num_rows,
+                          TreeGeom g, uint32_t level_in) {
+    const uint32_t chunks_per_row = (g.cw >> level_in) >> H;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)num_rows * chunks_per_row) return;
+    const uint32_t row = (uint32_t)(gid / chunks_per_row);
+    const uint32_t c = (uint32_t)(gid % chunks_per_row);
+
+    uint32_t stack[(H > 0) ? H : 1][8];
+#pragma unroll 1
+    for (uint32_t i = 0; i < (1u << H); i++) {
+        const uint32_t idx = (c << H) | i;  // index within level_in
+        uint32_t d[8];
+        if constexpr (LEAF32 > 0) {
+            uint32_t x[LEAF32];
+            load_leaf<LEAF32>(leaves + ((size_t)row * g.cw + idx) * LEAF32, x);
+            b3::hash_leaf<LEAF32>(x, d);
+            store_digest(node_ptr(layers, roots, g, row, 0, idx), d);
+        } else {
+            load_digest(node_ptr(layers, roots, g, row, level_in, idx), d);
+        }
+        bool parked = false;
+#pragma unroll
+        for (int l = 0; l < H; l++) {
+            if (!parked) {
+                if ((i >> l) & 1u) {
+                    uint32_t o[8];
+                    b3::hash_node(stack[l], d, o);
+#pragma unroll
+                    for (int w = 0; w < 8; w++) d[w] = o[w];
+                    store_digest(node_ptr(layers, roots, g, row, level_in + l + 1, idx >> (l + 1)), d);
+                } else {
+#pragma unroll
+                    for (int w = 0; w < 8; w++) stack[l][w] = d[w];
+                    parked = true;
+                }
+            }
+        }
+    }
+}
+
+template <int LEAF32, int H>
+cudaError_t launch_pass(const MerkleArgs &a, const TreeGeom &g, uint32_t level_in) {
+    const size_t threads = (size_t)a.num_rows * ((g.cw >> level_in) >> H);
+    const uint32_t block = 128;
+    const size_t grid = (threads + block - 1) / block;
+    if (grid == 0) return cudaSuccess;
+    if (grid > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    merkle_subtree_kernel<LEAF32, H><<<(uint32_t)grid, block, 0, a.stream>>>(a.leaves, a.layers, a.roots, a.num_rows,
+                                                                           g, level_in);
+    return cudaGetLastError();
+}
+
+template <int LEAF32>
+cudaError_t launch_leaf_pass(const MerkleArgs &a, const TreeGeom &g, int h) {
+    switch (h) {
+        case 0: return launch_pass<LEAF32, 0>(a, g, 0);
+        case 1: return launch_pass<LEAF32, 1>(a, g, 0);
+        case 2: return launch_pass<LEAF32, 2>(a, g, 0);
+        default: return launch_pass<LEAF32, 3>(a, g, 0);
+    }
+}
+
+cudaError_t launch_node_pass(const MerkleArgs &a, const TreeGeom &g, uint32_t level_in, int h) {
+    switch (h) {
+        case 1: return launch_pass<0, 1>(a, g, level_in);
+        case 2: return launch_pass<0, 2>(a, g, level_in);
+        case 3: return launch_pass<0, 3>(a, g, level_in);
+        default: return launch_pass<0, 4>(a, g, level_in);
+    }
+}
+
+}  // namespace
+
+bool merkle_supported(int leaf32) {
+    return leaf32 == 2 || leaf32 == 4 || leaf32 == 6 || leaf32 == 8 || leaf32 == 16;
+}
+
+cudaError_t launch_merkle_rows(const MerkleArgs &a, int *launches) {
+    TreeGeom g;
+    g.depth = (uint32_t)a.depth;
+    g.cw = 1u << a.depth;
+    g.row_stride = 2 * (size_t)g.cw - 2;
+    int n = 0;
+    int h = a.depth < 3 ? a.depth : 3;
+    cudaError_t err;
+    switch (a.leaf32) {
+        case 2: err = launch_leaf_pass<2>(a, g, h); break;
+        case 4: err = launch_leaf_pass<4>(a, g, h); break;
+        case 6: err = launch_leaf_pass<6>(a, g, h); break;
+        case 8: err = launch_leaf_pass<8>(a, g, h); break;
+        case 16: err = launch_leaf_pass<16>(a, g, h); break;
+        default: return cudaErrorInvalidValue;
+    }
+    if (err != cudaSuccess) return err;
+    n++;
+    int level = h, remaining = a.depth - h;
+    while (remaining > 0) {
+        h = remaining <= 4 ? remaining : 3;
+        err = launch_node_pass(a, g, (uint32_t)level, h);
+        if (err != cudaSuccess) return err;
+        n++;
+        level += h;
+        remaining -= h;
+    }
+    if (launches) *launches = n;
+    return cudaSuccess;
+}
+
+}  // namespace zipgpu

@@ -1,0 +1,806 @@
+// zinc_b200/csrc/zipgpu.cu -- C ABI of libzipgpu (include/zipgpu.h): contexts, per-pp code state, the
+// host<->device pipeline around the kernels, device-resident prover data.
+//
+// Host-pointer entry points split the rows into chunks and run  H2D(chunk k+1) || kernels(chunk k) || D2H(chunk k-1)
+// on three streams, so that the PCIe copies of a commit hide behind the hashing.  All device memory comes from the
+// stream-ordered pool (cudaMallocAsync) whose release threshold is lifted, so steady-state calls allocate nothing.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/zipgpu.h"
+#include "kernels.h"
+
+namespace zipgpu {
+void perm_from_seed(uint64_t seed, uint32_t n, uint32_t *perm);
+}
+
+using namespace zipgpu;
+
+// ------------------------------------------------------------------------------------------------------
+// state
+// ------------------------------------------------------------------------------------------------------
+struct ProfRec {
+    cudaEvent_t e0, e1, e2;  // before encode, between, after hash
+    bool has_enc, has_hash;
+};
+
+struct zipgpu_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;  // kernels
+    cudaStream_t h2d = nullptr;
+    cudaStream_t d2h = nullptr;
+    std::vector<cudaEvent_t> ring;  // timing-disabled events for cross-stream ordering
+    size_t ring_pos = 0;
+    std::atomic<uint64_t> launches{0};
+    bool profile = false;
+    std::vector<ProfRec> prof_pending;
+    std::vector<ProfRec> prof_free;
+    double enc_ms = 0, hash_ms = 0;
+    uint64_t prof_calls = 0;
+    uint32_t *d_sink = nullptr;
+    std::mutex mu;
+};
+
+struct zipgpu_code {
+    zipgpu_ctx *ctx;
+    size_t row_len, rep, cw;
+    int in_limbs, out_limbs;
+    int depth;  // -1 when cw is not a power of two (encode only)
+    uint32_t *d_perm1, *d_perm2;
+};
+
+struct zipgpu_data {
+    zipgpu_ctx *ctx;
+    size_t num_rows, cw;
+    int out_limbs, depth;
+    uint64_t *d_rows;
+    uint8_t *d_layers;
+    uint8_t *d_roots;
+};
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char *what) {
+    g_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return e == cudaErrorMemoryAllocation ? ZIPGPU_ERR_NOMEM : ZIPGPU_ERR_CUDA;
+}
+#define CU(call)                                           \
+    do {                                                   \
+        cudaError_t e__ = (call);                          \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+static bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
+static int ilog2(size_t x) {
+    int l = 0;
+    while (x >>= 1) l++;
+    return l;
+}
+static size_t layers_per_row(int depth) { return ((size_t)2 << depth) - 2; }
+
+static cudaEvent_t next_event(zipgpu_ctx *c) {
+    cudaEvent_t e = c->ring[c->ring_pos];
+    c->ring_pos = (c->ring_pos + 1) % c->ring.size();
+    return e;
+}
+// make `waiter` wait for everything enqueued so far on `src`
+static cudaError_t chain(zipgpu_ctx *c, cudaStream_t src, cudaStream_t waiter) {
+    if (src == waiter) return cudaSuccess;
+    cudaEvent_t e = next_event(c);
+    cudaError_t err = cudaEventRecord(e, src);
+    if (err != cudaSuccess) return err;
+    return cudaStreamWaitEvent(waiter, e, 0);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// library / context
+// ------------------------------------------------------------------------------------------------------
+extern "C" const char *zipgpu_version(void) { return "zipgpu 0.1 (sm_100a)"; }
+extern "C" const char *zipgpu_last_error(void) { return g_err.c_str(); }
+
+extern "C" int zipgpu_device_count(int *count) {
+    if (!count) return fail(ZIPGPU_ERR_INVALID, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        cudaGetLastError();
+        return fail(ZIPGPU_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *count = n;
+    return ZIPGPU_OK;
+}
+
+extern "C" int zipgpu_ctx_create(int device, zipgpu_ctx **out) {
+    if (!out) return fail(ZIPGPU_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(ZIPGPU_ERR_NO_DEVICE, "no CUDA device visible: libzipgpu has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(ZIPGPU_ERR_INVALID, "device index out of range");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        return fail(ZIPGPU_ERR_NO_DEVICE, std::string("libzipgpu is built for sm_100a only; device is ") + prop.name +
+                                              " (sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    }
+    zipgpu_ctx *c = new (std::nothrow) zipgpu_ctx();
+    if (!c) return fail(ZIPGPU_ERR_NOMEM, "host allocation failed");
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete c;
+        return cuda_fail(e, "cudaStreamCreate");
+    }
+    c->ring.resize(256);
+    for (auto &ev : c->ring) {
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) {
+            delete c;
+            return cuda_fail(e, "cudaEventCreate");
+        }
+    }
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    if ((e = cudaMalloc(&c->d_sink, 256)) != cudaSuccess) {
+        delete c;
+        return cuda_fail(e, "cudaMalloc");
+    }
+    *out = c;
+    return ZIPGPU_OK;
+}
+
+extern "C" void zipgpu_ctx_destroy(zipgpu_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &r : c->prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); cudaEventDestroy(r.e2); }
+    for (auto &r : c->prof_free) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); cudaEventDestroy(r.e2); }
+    for (auto &ev : c->ring) cudaEventDestroy(ev);
+    if (c->d_sink) cudaFree(c->d_sink);
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->h2d);
+    cudaStreamDestroy(c->d2h);
+    delete c;
+}
+
+extern "C" int zipgpu_ctx_device(const zipgpu_ctx *c) { return c ? c->device : -1; }
+extern "C" uint64_t zipgpu_ctx_launch_count(const zipgpu_ctx *c) { return c ? c->launches.load() : 0; }
+
+extern "C" int zipgpu_ctx_sync(zipgpu_ctx *c) {
+    if (!c) return fail(ZIPGPU_ERR_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->h2d));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->d2h));
+    return ZIPGPU_OK;
+}
+
+extern "C" int zipgpu_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(ZIPGPU_ERR_INVALID, "out is NULL");
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
+    return ZIPGPU_OK;
+}
+extern "C" int zipgpu_host_free(void *p) {
+    CU(cudaFreeHost(p));
+    return ZIPGPU_OK;
+}
+extern "C" int zipgpu_host_register(void *p, size_t bytes) {
+    CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    return ZIPGPU_OK;
+}
+extern "C" int zipgpu_host_unregister(void *p) {
+    CU(cudaHostUnregister(p));
+    return ZIPGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// code geometry (host only)
+// ------------------------------------------------------------------------------------------------------
+extern "C" int zipgpu_perm_from_seed(uint64_t seed, uint32_t n, uint32_t *perm_out) {
+    if (!perm_out && n) return fail(ZIPGPU_ERR_INVALID, "perm_out is NULL");
+    perm_from_seed(seed, n, perm_out);
+    return ZIPGPU_OK;
+}
+
+static uint64_t isqrt64(uint64_t x) {
+    uint64_t r = 0;
+    for (uint64_t bit = 1ull << 31; bit; bit >>= 1) {
+        const uint64_t t = r | bit;
+        if (t * t <= x) r = t;
+    }
+    return r;
+}
+static size_t next_pow2(size_t x) {
+    size_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+// code_raa.rs:42-43
+extern "C" size_t zipgpu_raa_row_len(size_t poly_size) {
+    if (poly_size == 0) return 0;
+    const int num_vars = ilog2(poly_size);
+    return next_pow2((size_t)isqrt64(1ull << num_vars));
+}
+// pcs/structs.rs:79-90
+extern "C" size_t zipgpu_num_rows(size_t poly_size, size_t row_len) {
+    if (poly_size == 0 || row_len == 0) return 0;
+    const int num_vars = ilog2(poly_size);
+    return next_pow2(((size_t)1 << num_vars) / row_len);
+}
+// code_raa.rs:53-67
+extern "C" int zipgpu_raa_codeword_width_bits(int in_limbs, size_t poly_size, size_t rep) {
+    const int num_vars = poly_size ? ilog2(poly_size) : 0;
+    const int nv_even = (num_vars % 2 == 0) ? num_vars : num_vars + 1;
+    return 64 * in_limbs + nv_even + 2 * ilog2(next_pow2(rep ? rep : 1));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// code (per-pp state)
+// ------------------------------------------------------------------------------------------------------
+static bool is_permutation(const uint32_t *p, size_t n) {
+    std::vector<uint8_t> seen(n, 0);
+    for (size_t i = 0; i < n; i++) {
+        if (p[i] >= n || seen[p[i]]) return false;
+        seen[p[i]] = 1;
+    }
+    return true;
+}
+
+extern "C" int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t rep, int in_limbs, int out_limbs,
+                                  const uint32_t *perm1, const uint32_t *perm2, zipgpu_code **out) {
+    if (!out) return fail(ZIPGPU_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!ctx || !perm1 || !perm2) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (row_len == 0 || rep == 0) return fail(ZIPGPU_ERR_INVALID, "row_len and repetition_factor must be positive");
+    if (in_limbs < 1 || out_limbs < in_limbs) return fail(ZIPGPU_ERR_INVALID, "need 1 <= in_limbs <= out_limbs");
+    const size_t cw = row_len * rep;
+    if (cw > (1u << 24)) return fail(ZIPGPU_ERR_UNSUPPORTED, "codeword longer than 2^24");
+    // the narrowest width the reference's assert (code_raa.rs:53-72) can accept for this codeword length
+    const int need_bits = 64 * in_limbs + 2 * ilog2(next_pow2(cw));
+    if (64 * out_limbs < need_bits)
+        return fail(ZIPGPU_ERR_WIDTH, "Cannot fit " + std::to_string(need_bits) + "-bit wide codeword entries in " +
+                                          std::to_string(64 * out_limbs) + " bits integers");
+    if (!is_permutation(perm1, cw) || !is_permutation(perm2, cw))
+        return fail(ZIPGPU_ERR_INVALID, "perm1/perm2 must be permutations of [0, codeword_len)");
+    if (!encode_supported(in_limbs, (uint32_t)cw))
+        return fail(ZIPGPU_ERR_UNSUPPORTED, "no encoder kernel for in_limbs=" + std::to_string(in_limbs) +
+                                                " codeword_len=" + std::to_string(cw) +
+                                                " (the codeword must fit one SM's shared memory)");
+    CU(cudaSetDevice(ctx->device));
+    zipgpu_code *c = new (std::nothrow) zipgpu_code();
+    if (!c) return fail(ZIPGPU_ERR_NOMEM, "host allocation failed");
+    c->ctx = ctx;
+    c->row_len = row_len;
+    c->rep = rep;
+    c->cw = cw;
+    c->in_limbs = in_limbs;
+    c->out_limbs = out_limbs;
+    c->depth = is_pow2(cw) ? ilog2(cw) : -1;
+    const size_t padded = encode_perm_padded_len((uint32_t)cw);
+    cudaError_t e;
+    if ((e = cudaMalloc(&c->d_perm1, padded * 4)) != cudaSuccess || (e = cudaMalloc(&c->d_perm2, padded * 4)) != cudaSuccess) {
+        delete c;
+        return cuda_fail(e, "cudaMalloc(perm)");
+    }
+    std::vector<uint32_t> tmp(padded, 0);
+    std::memcpy(tmp.data(), perm1, cw * 4);
+    CU(cudaMemcpy(c->d_perm1, tmp.data(), padded * 4, cudaMemcpyHostToDevice));
+    std::memcpy(tmp.data(), perm2, cw * 4);
+    CU(cudaMemcpy(c->d_perm2, tmp.data(), padded * 4, cudaMemcpyHostToDevice));
+    *out = c;
+    return ZIPGPU_OK;
+}
+
+extern "C" void zipgpu_code_destroy(zipgpu_code *c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(c->d_perm1);
+    cudaFree(c->d_perm2);
+    delete c;
+}
+extern "C" size_t zipgpu_code_row_len(const zipgpu_code *c) { return c ? c->row_len : 0; }
+extern "C" size_t zipgpu_code_codeword_len(const zipgpu_code *c) { return c ? c->cw : 0; }
+extern "C" int zipgpu_code_merkle_depth(const zipgpu_code *c) { return c ? ilog2(next_pow2(c->cw)) : -1; }
+
+// ------------------------------------------------------------------------------------------------------
+// profiling records
+// ------------------------------------------------------------------------------------------------------
+static bool prof_begin(zipgpu_ctx *c, ProfRec *r) {
+    if (!c->profile) return false;
+    if (!c->prof_free.empty()) {
+        *r = c->prof_free.back();
+        c->prof_free.pop_back();
+    } else {
+        if (cudaEventCreate(&r->e0) != cudaSuccess || cudaEventCreate(&r->e1) != cudaSuccess ||
+            cudaEventCreate(&r->e2) != cudaSuccess)
+            return false;
+    }
+    r->has_enc = r->has_hash = false;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// device-level building blocks
+// ------------------------------------------------------------------------------------------------------
+static int check_align16(const void *p, const char *name) {
+    if (((uintptr_t)p & 15) != 0) return fail(ZIPGPU_ERR_INVALID, std::string(name) + " must be 16-byte aligned");
+    return ZIPGPU_OK;
+}
+
+static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_evals, uint64_t *d_rows, cudaStream_t s) {
+    if (num_rows == 0) return ZIPGPU_OK;
+    if (num_rows > 0xffffffffull) return fail(ZIPGPU_ERR_UNSUPPORTED, "too many rows");
+    int rc;
+    if ((rc = check_align16(d_evals, "evals")) || (rc = check_align16(d_rows, "rows_out"))) return rc;
+    EncodeArgs a;
+    a.evals = reinterpret_cast<const uint32_t *>(d_evals);
+    a.rows_out = reinterpret_cast<uint32_t *>(d_rows);
+    a.perm1 = code->d_perm1;
+    a.perm2 = code->d_perm2;
+    a.num_rows = (uint32_t)num_rows;
+    a.row_len = (uint32_t)code->row_len;
+    a.cw = (uint32_t)code->cw;
+    a.out32 = (uint32_t)code->out_limbs * 2;
+    a.in_limbs = code->in_limbs;
+    a.num_sms = code->ctx->num_sms;
+    a.stream = s;
+    cudaError_t e = launch_raa_encode(a);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_raa_encode");
+    code->ctx->launches++;
+    return ZIPGPU_OK;
+}
+
+static int merkle_dev(zipgpu_ctx *ctx, size_t num_rows, int depth, int leaf_limbs, const uint64_t *d_leaves,
+                      uint8_t *d_layers, uint8_t *d_roots, cudaStream_t s) {
+    if (num_rows == 0) return ZIPGPU_OK;
+    if (num_rows > 0xffffffffull) return fail(ZIPGPU_ERR_UNSUPPORTED, "too many rows");
+    if (depth < 0 || depth > 30) return fail(ZIPGPU_ERR_INVALID, "depth out of range");
+    if (!merkle_supported(leaf_limbs * 2))
+        return fail(ZIPGPU_ERR_UNSUPPORTED, "leaf_limbs must be one of 1,2,3,4,8");
+    MerkleArgs a;
+    a.leaves = reinterpret_cast<const uint32_t *>(d_leaves);
+    a.layers = d_layers;
+    a.roots = d_roots;
+    a.num_rows = (uint32_t)num_rows;
+    a.depth = depth;
+    a.leaf32 = leaf_limbs * 2;
+    a.stream = s;
+    int n = 0;
+    cudaError_t e = launch_merkle_rows(a, &n);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_merkle_rows");
+    ctx->launches += (uint64_t)n;
+    return ZIPGPU_OK;
+}
+
+// encode + merkle of a row range on stream s, with optional profiling events
+static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_evals, uint64_t *d_rows, uint8_t *d_layers,
+                      uint8_t *d_roots, cudaStream_t s) {
+    zipgpu_ctx *ctx = code->ctx;
+    ProfRec r;
+    const bool prof = prof_begin(ctx, &r);
+    if (prof) cudaEventRecord(r.e0, s);
+    int rc = encode_dev(code, num_rows, d_evals, d_rows, s);
+    if (rc) return rc;
+    if (prof) {
+        cudaEventRecord(r.e1, s);
+        r.has_enc = true;
+    }
+    if (d_roots) {
+        rc = merkle_dev(ctx, num_rows, code->depth, code->out_limbs, d_rows, d_layers, d_roots, s);
+        if (rc) return rc;
+        if (prof) {
+            cudaEventRecord(r.e2, s);
+            r.has_hash = true;
+        }
+    }
+    if (prof) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->prof_pending.push_back(r);
+    }
+    return ZIPGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// encode_rows
+// ------------------------------------------------------------------------------------------------------
+extern "C" int zipgpu_encode_rows_device(zipgpu_code *code, size_t num_rows, const uint64_t *d_evals,
+                                         uint64_t *d_rows_out, void *stream) {
+    if (!code || (num_rows && (!d_evals || !d_rows_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(code->ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : code->ctx->stream;
+    return commit_dev(code, num_rows, d_evals, d_rows_out, nullptr, nullptr, s);
+}
+
+static size_t pick_chunk_rows(size_t num_rows, size_t bytes_per_row_in, int num_sms) {
+    // ~16 MiB of input per chunk, at least two CTAs per SM worth of rows, at most 32 chunks
+    size_t rows = std::max<size_t>((16u << 20) / std::max<size_t>(bytes_per_row_in, 1), (size_t)num_sms * 2);
+    rows = std::max(rows, (num_rows + 31) / 32);
+    return std::min(rows, std::max<size_t>(num_rows, 1));
+}
+
+// the pipelined host path shared by encode_rows / commit / commit_resident / batch_commit.  Does not synchronise.
+struct HostJob {
+    const uint64_t *evals;
+    uint64_t *rows_out;   // host, nullable
+    uint8_t *layers_out;  // host, nullable
+    uint8_t *roots_out;   // host, nullable (encode only)
+    bool want_roots;
+    zipgpu_data **keep;   // nullable
+};
+
+static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) {
+    zipgpu_ctx *ctx = code->ctx;
+    const size_t in_row_bytes = code->row_len * code->in_limbs * 8;
+    const size_t out_row_bytes = code->cw * code->out_limbs * 8;
+    const bool merkle = job.want_roots;
+    if (merkle && code->depth < 0)
+        return fail(ZIPGPU_ERR_INVALID, "leaves.len().is_power_of_two(): codeword_len is not a power of two");
+    const size_t lay_row_bytes = merkle ? layers_per_row(code->depth) * 32 : 0;
+    if (job.keep) *job.keep = nullptr;
+    if (num_rows == 0) return ZIPGPU_OK;
+
+    uint64_t *d_evals = nullptr, *d_rows = nullptr;
+    uint8_t *d_layers = nullptr, *d_roots = nullptr;
+    cudaStream_t s = ctx->stream;
+    CU(cudaMallocAsync(&d_evals, num_rows * in_row_bytes, s));
+    CU(cudaMallocAsync(&d_rows, num_rows * out_row_bytes, s));
+    if (merkle) {
+        CU(cudaMallocAsync(&d_layers, std::max<size_t>(num_rows * lay_row_bytes, 32), s));
+        CU(cudaMallocAsync(&d_roots, num_rows * 32, s));
+    }
+    cudaError_t e;
+    if ((e = chain(ctx, s, ctx->h2d)) != cudaSuccess) return cuda_fail(e, "chain");
+    if ((e = chain(ctx, s, ctx->d2h)) != cudaSuccess) return cuda_fail(e, "chain");
+
+    const size_t chunk = pick_chunk_rows(num_rows, in_row_bytes, ctx->num_sms);
+    for (size_t r0 = 0; r0 < num_rows; r0 += chunk) {
+        const size_t n = std::min(chunk, num_rows - r0);
+        CU(cudaMemcpyAsync((uint8_t *)d_evals + r0 * in_row_bytes, (const uint8_t *)job.evals + r0 * in_row_bytes,
+                           n * in_row_bytes, cudaMemcpyHostToDevice, ctx->h2d));
+        if ((e = chain(ctx, ctx->h2d, s)) != cudaSuccess) return cuda_fail(e, "chain");
+        int rc = commit_dev(code, n, (const uint64_t *)((uint8_t *)d_evals + r0 * in_row_bytes),
+                            (uint64_t *)((uint8_t *)d_rows + r0 * out_row_bytes),
+                            merkle ? d_layers + r0 * lay_row_bytes : nullptr, merkle ? d_roots + r0 * 32 : nullptr, s);
+        if (rc) return rc;
+        if (job.rows_out || job.layers_out) {
+            if ((e = chain(ctx, s, ctx->d2h)) != cudaSuccess) return cuda_fail(e, "chain");
+            if (job.rows_out)
+                CU(cudaMemcpyAsync((uint8_t *)job.rows_out + r0 * out_row_bytes, (uint8_t *)d_rows + r0 * out_row_bytes,
+                                   n * out_row_bytes, cudaMemcpyDeviceToHost, ctx->d2h));
+            if (job.layers_out && lay_row_bytes)
+                CU(cudaMemcpyAsync(job.layers_out + r0 * lay_row_bytes, d_layers + r0 * lay_row_bytes,
+                                   n * lay_row_bytes, cudaMemcpyDeviceToHost, ctx->d2h));
+        }
+    }
+    if (merkle && job.roots_out) {
+        if ((e = chain(ctx, s, ctx->d2h)) != cudaSuccess) return cuda_fail(e, "chain");
+        CU(cudaMemcpyAsync(job.roots_out, d_roots, num_rows * 32, cudaMemcpyDeviceToHost, ctx->d2h));
+    }
+    // join the copy streams back into the kernel stream so the frees are ordered after every use
+    if ((e = chain(ctx, ctx->d2h, s)) != cudaSuccess) return cuda_fail(e, "chain");
+    if ((e = chain(ctx, ctx->h2d, s)) != cudaSuccess) return cuda_fail(e, "chain");
+    CU(cudaFreeAsync(d_evals, s));
+    if (job.keep) {
+        zipgpu_data *d = new (std::nothrow) zipgpu_data();
+        if (!d) return fail(ZIPGPU_ERR_NOMEM, "host allocation failed");
+        d->ctx = ctx;
+        d->num_rows = num_rows;
+        d->cw = code->cw;
+        d->out_limbs = code->out_limbs;
+        d->depth = code->depth;
+        d->d_rows = d_rows;
+        d->d_layers = d_layers;
+        d->d_roots = d_roots;
+        *job.keep = d;
+    } else {
+        CU(cudaFreeAsync(d_rows, s));
+        if (d_layers) CU(cudaFreeAsync(d_layers, s));
+        if (d_roots) CU(cudaFreeAsync(d_roots, s));
+    }
+    return ZIPGPU_OK;
+}
+
+extern "C" int zipgpu_encode_rows(zipgpu_code *code, size_t num_rows, const uint64_t *evals, uint64_t *rows_out) {
+    if (!code || (num_rows && (!evals || !rows_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(code->ctx->device));
+    HostJob job{evals, rows_out, nullptr, nullptr, false, nullptr};
+    int rc = run_host_job(code, num_rows, job);
+    int rc2 = zipgpu_ctx_sync(code->ctx);
+    return rc ? rc : rc2;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// merkle_rows
+// ------------------------------------------------------------------------------------------------------
+extern "C" int zipgpu_merkle_rows_device(zipgpu_ctx *ctx, size_t num_rows, int depth, int leaf_limbs,
+                                         const uint64_t *d_leaves, uint8_t *d_layers_out, uint8_t *d_roots_out,
+                                         void *stream) {
+    if (!ctx || (num_rows && (!d_leaves || !d_roots_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    int rc;
+    if ((rc = check_align16(d_leaves, "leaves")) || (rc = check_align16(d_roots_out, "roots_out")) ||
+        (rc = check_align16(d_layers_out, "layers_out")))
+        return rc;
+    uint8_t *scratch = nullptr;
+    if (!d_layers_out && depth > 0) {
+        CU(cudaMallocAsync(&scratch, num_rows * layers_per_row(depth) * 32, s));
+        d_layers_out = scratch;
+    }
+    ProfRec r;
+    const bool prof = prof_begin(ctx, &r);
+    if (prof) cudaEventRecord(r.e1, s);
+    rc = merkle_dev(ctx, num_rows, depth, leaf_limbs, d_leaves, d_layers_out, d_roots_out, s);
+    if (prof && rc == 0) {
+        cudaEventRecord(r.e2, s);
+        r.has_hash = true;
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->prof_pending.push_back(r);
+    }
+    if (scratch) CU(cudaFreeAsync(scratch, s));
+    return rc;
+}
+
+extern "C" int zipgpu_merkle_rows(zipgpu_ctx *ctx, size_t num_rows, int depth, int leaf_limbs, const uint64_t *leaves,
+                                  uint8_t *layers_out, uint8_t *roots_out) {
+    if (!ctx || (num_rows && (!leaves || !roots_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (depth < 0 || depth > 30) return fail(ZIPGPU_ERR_INVALID, "depth out of range");
+    if (num_rows == 0) return ZIPGPU_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t nleaves = num_rows << depth;
+    const size_t leaf_bytes = nleaves * leaf_limbs * 8;
+    const size_t lay_bytes = num_rows * layers_per_row(depth) * 32;
+    uint64_t *d_leaves = nullptr;
+    uint8_t *d_layers = nullptr, *d_roots = nullptr;
+    CU(cudaMallocAsync(&d_leaves, leaf_bytes, s));
+    CU(cudaMallocAsync(&d_layers, std::max<size_t>(lay_bytes, 32), s));
+    CU(cudaMallocAsync(&d_roots, num_rows * 32, s));
+    CU(cudaMemcpyAsync(d_leaves, leaves, leaf_bytes, cudaMemcpyHostToDevice, s));
+    int rc = zipgpu_merkle_rows_device(ctx, num_rows, depth, leaf_limbs, d_leaves, d_layers, d_roots, s);
+    if (rc == 0) {
+        if (layers_out && lay_bytes) CU(cudaMemcpyAsync(layers_out, d_layers, lay_bytes, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(roots_out, d_roots, num_rows * 32, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaFreeAsync(d_leaves, s));
+    CU(cudaFreeAsync(d_layers, s));
+    CU(cudaFreeAsync(d_roots, s));
+    CU(cudaStreamSynchronize(s));
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// commit
+// ------------------------------------------------------------------------------------------------------
+extern "C" int zipgpu_commit_device(zipgpu_code *code, size_t num_rows, const uint64_t *d_evals, uint64_t *d_rows_out,
+                                    uint8_t *d_layers_out, uint8_t *d_roots_out, void *stream) {
+    if (!code || (num_rows && (!d_evals || !d_roots_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (code->depth < 0)
+        return fail(ZIPGPU_ERR_INVALID, "leaves.len().is_power_of_two(): codeword_len is not a power of two");
+    if (num_rows == 0) return ZIPGPU_OK;
+    CU(cudaSetDevice(code->ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : code->ctx->stream;
+    int rc;
+    if ((rc = check_align16(d_roots_out, "roots_out")) || (rc = check_align16(d_layers_out, "layers_out"))) return rc;
+    uint64_t *rows_scratch = nullptr;
+    uint8_t *layers_scratch = nullptr;
+    if (!d_rows_out) {
+        CU(cudaMallocAsync(&rows_scratch, num_rows * code->cw * code->out_limbs * 8, s));
+        d_rows_out = rows_scratch;
+    }
+    if (!d_layers_out && code->depth > 0) {
+        CU(cudaMallocAsync(&layers_scratch, num_rows * layers_per_row(code->depth) * 32, s));
+        d_layers_out = layers_scratch;
+    }
+    rc = commit_dev(code, num_rows, d_evals, d_rows_out, d_layers_out, d_roots_out, s);
+    if (rows_scratch) CU(cudaFreeAsync(rows_scratch, s));
+    if (layers_scratch) CU(cudaFreeAsync(layers_scratch, s));
+    return rc;
+}
+
+extern "C" int zipgpu_commit(zipgpu_code *code, size_t num_rows, const uint64_t *evals, uint64_t *rows_out,
+                             uint8_t *layers_out, uint8_t *roots_out) {
+    if (!code || (num_rows && (!evals || !roots_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(code->ctx->device));
+    HostJob job{evals, rows_out, layers_out, roots_out, true, nullptr};
+    int rc = run_host_job(code, num_rows, job);
+    int rc2 = zipgpu_ctx_sync(code->ctx);
+    return rc ? rc : rc2;
+}
+
+extern "C" int zipgpu_batch_commit(zipgpu_code *code, size_t num_polys, size_t num_rows, const uint64_t *const *evals,
+                                   uint64_t *const *rows_out, uint8_t *const *layers_out, uint8_t *const *roots_out) {
+    if (!code || (num_polys && (!evals || !roots_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(code->ctx->device));
+    int rc = ZIPGPU_OK;
+    for (size_t p = 0; p < num_polys && rc == 0; p++) {
+        if (num_rows && (!evals[p] || !roots_out[p])) {
+            rc = fail(ZIPGPU_ERR_INVALID, "NULL polynomial or roots pointer in batch");
+            break;
+        }
+        HostJob job{evals[p], rows_out ? rows_out[p] : nullptr, layers_out ? layers_out[p] : nullptr, roots_out[p], true,
+                    nullptr};
+        rc = run_host_job(code, num_rows, job);  // no sync: poly p+1's H2D overlaps poly p's kernels
+    }
+    int rc2 = zipgpu_ctx_sync(code->ctx);
+    return rc ? rc : rc2;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// device-resident prover data
+// ------------------------------------------------------------------------------------------------------
+extern "C" int zipgpu_commit_resident(zipgpu_code *code, size_t num_rows, const uint64_t *evals, uint8_t *roots_out,
+                                      zipgpu_data **handle) {
+    if (!code || !handle || (num_rows && (!evals || !roots_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(code->ctx->device));
+    HostJob job{evals, nullptr, nullptr, roots_out, true, handle};
+    int rc = run_host_job(code, num_rows, job);
+    int rc2 = zipgpu_ctx_sync(code->ctx);
+    return rc ? rc : rc2;
+}
+
+extern "C" void zipgpu_data_free(zipgpu_data *d) {
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    cudaStream_t s = d->ctx->stream;
+    if (d->d_rows) cudaFreeAsync(d->d_rows, s);
+    if (d->d_layers) cudaFreeAsync(d->d_layers, s);
+    if (d->d_roots) cudaFreeAsync(d->d_roots, s);
+    delete d;
+}
+extern "C" size_t zipgpu_data_num_rows(const zipgpu_data *d) { return d ? d->num_rows : 0; }
+extern "C" const uint64_t *zipgpu_data_rows_device(const zipgpu_data *d) { return d ? d->d_rows : nullptr; }
+extern "C" const uint8_t *zipgpu_data_layers_device(const zipgpu_data *d) { return d ? d->d_layers : nullptr; }
+extern "C" const uint8_t *zipgpu_data_roots_device(const zipgpu_data *d) { return d ? d->d_roots : nullptr; }
+
+extern "C" int zipgpu_data_read_rows(const zipgpu_data *d, size_t row_begin, size_t row_count, uint64_t *rows_out) {
+    if (!d || (row_count && !rows_out)) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (row_begin + row_count > d->num_rows) return fail(ZIPGPU_ERR_INVALID, "row range out of bounds");
+    CU(cudaSetDevice(d->ctx->device));
+    const size_t rb = d->cw * d->out_limbs * 8;
+    CU(cudaMemcpyAsync(rows_out, (const uint8_t *)d->d_rows + row_begin * rb, row_count * rb, cudaMemcpyDeviceToHost,
+                       d->ctx->stream));
+    CU(cudaStreamSynchronize(d->ctx->stream));
+    return ZIPGPU_OK;
+}
+extern "C" int zipgpu_data_read_layers(const zipgpu_data *d, size_t row_begin, size_t row_count, uint8_t *layers_out) {
+    if (!d || (row_count && !layers_out)) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (row_begin + row_count > d->num_rows) return fail(ZIPGPU_ERR_INVALID, "row range out of bounds");
+    CU(cudaSetDevice(d->ctx->device));
+    const size_t lb = layers_per_row(d->depth) * 32;
+    if (lb * row_count) {
+        CU(cudaMemcpyAsync(layers_out, d->d_layers + row_begin * lb, row_count * lb, cudaMemcpyDeviceToHost,
+                           d->ctx->stream));
+        CU(cudaStreamSynchronize(d->ctx->stream));
+    }
+    return ZIPGPU_OK;
+}
+
+extern "C" int zipgpu_data_open_columns(const zipgpu_data *d, size_t num_cols, const uint32_t *columns,
+                                        uint64_t *col_values_out, uint8_t *paths_out) {
+    if (!d || (num_cols && (!columns || !col_values_out || (!paths_out && d->depth > 0))))
+        return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (num_cols == 0) return ZIPGPU_OK;
+    for (size_t i = 0; i < num_cols; i++)
+        if (columns[i] >= d->cw) return fail(ZIPGPU_ERR_INVALID, "column index out of range");
+    zipgpu_ctx *ctx = d->ctx;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t val_bytes = num_cols * d->num_rows * d->out_limbs * 8;
+    const size_t path_bytes = num_cols * d->num_rows * (size_t)d->depth * 32;
+    uint32_t *d_cols = nullptr, *d_vals = nullptr;
+    uint8_t *d_paths = nullptr;
+    CU(cudaMallocAsync(&d_cols, num_cols * 4, s));
+    CU(cudaMallocAsync(&d_vals, val_bytes, s));
+    CU(cudaMallocAsync(&d_paths, std::max<size_t>(path_bytes, 32), s));
+    CU(cudaMemcpyAsync(d_cols, columns, num_cols * 4, cudaMemcpyHostToDevice, s));
+    OpenArgs a;
+    a.rows = reinterpret_cast<const uint32_t *>(d->d_rows);
+    a.layers = d->d_layers;
+    a.columns = d_cols;
+    a.col_values = d_vals;
+    a.paths = d_paths;
+    a.num_rows = (uint32_t)d->num_rows;
+    a.cw = (uint32_t)d->cw;
+    a.out32 = (uint32_t)d->out_limbs * 2;
+    a.num_cols = (uint32_t)num_cols;
+    a.depth = d->depth;
+    a.stream = s;
+    cudaError_t e = launch_open_columns(a);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_open_columns");
+    ctx->launches++;
+    CU(cudaMemcpyAsync(col_values_out, d_vals, val_bytes, cudaMemcpyDeviceToHost, s));
+    if (path_bytes) CU(cudaMemcpyAsync(paths_out, d_paths, path_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaFreeAsync(d_cols, s));
+    CU(cudaFreeAsync(d_vals, s));
+    CU(cudaFreeAsync(d_paths, s));
+    CU(cudaStreamSynchronize(s));
+    return ZIPGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// measurement helpers
+// ------------------------------------------------------------------------------------------------------
+extern "C" int zipgpu_profile_enable(zipgpu_ctx *c, int on) {
+    if (!c) return fail(ZIPGPU_ERR_INVALID, "ctx is NULL");
+    c->profile = on != 0;
+    return ZIPGPU_OK;
+}
+
+extern "C" int zipgpu_profile_read(zipgpu_ctx *c, double *encode_ms, double *hash_ms, uint64_t *calls, int reset) {
+    if (!c) return fail(ZIPGPU_ERR_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (auto &r : c->prof_pending) {
+        float ms = 0;
+        if (r.has_enc) {
+            CU(cudaEventSynchronize(r.e1));
+            CU(cudaEventElapsedTime(&ms, r.e0, r.e1));
+            c->enc_ms += ms;
+        }
+        if (r.has_hash) {
+            CU(cudaEventSynchronize(r.e2));
+            CU(cudaEventElapsedTime(&ms, r.e1, r.e2));
+            c->hash_ms += ms;
+        }
+        c->prof_calls++;
+        c->prof_free.push_back(r);
+    }
+    c->prof_pending.clear();
+    if (encode_ms) *encode_ms = c->enc_ms;
+    if (hash_ms) *hash_ms = c->hash_ms;
+    if (calls) *calls = c->prof_calls;
+    if (reset) {
+        c->enc_ms = c->hash_ms = 0;
+        c->prof_calls = 0;
+    }
+    return ZIPGPU_OK;
+}
+
+extern "C" int zipgpu_microbench_int32(zipgpu_ctx *c, int kind, int iters, double *lane_ops_per_s) {
+    if (!c || !lane_ops_per_s) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (kind < 0 || kind > 1 || iters < 1) return fail(ZIPGPU_ERR_INVALID, "bad kind/iters");
+    CU(cudaSetDevice(c->device));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    double ops = 0;
+    cudaError_t e = launch_microbench_int32(kind, iters, c->num_sms, c->stream, c->d_sink, &ops);  // warm-up
+    if (e != cudaSuccess) return cuda_fail(e, "microbench");
+    CU(cudaEventRecord(e0, c->stream));
+    e = launch_microbench_int32(kind, iters, c->num_sms, c->stream, c->d_sink, &ops);
+    if (e != cudaSuccess) return cuda_fail(e, "microbench");
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    c->launches += 2;
+    *lane_ops_per_s = ops / (ms * 1e-3);
+    return ZIPGPU_OK;
+}
