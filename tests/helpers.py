@@ -9,9 +9,14 @@ I64_MIN = -(1 << 63)
 
 
 def shape_for(nv: int):
-    """row_len / num_rows / cw for a 2^nv MLE (code_raa.rs:42-43, structs.rs:82, rep = 2)"""
-    row_len = 1 << ((nv + 1) // 2)
-    num_rows = 1 << (nv // 2)
+    """row_len / num_rows / cw for a 2^nv MLE: row_len = isqrt(2^nv).next_power_of_two() (code_raa.rs:42-43),
+    num_rows = (2^nv / row_len).next_power_of_two() (structs.rs:82), cw = 2 * row_len (rep = 2)"""
+    import math
+
+    r = math.isqrt(1 << nv)
+    row_len = 1 << (r - 1).bit_length() if r > 1 else 1
+    q = (1 << nv) // row_len
+    num_rows = 1 << (q - 1).bit_length() if q > 1 else 1
     return row_len, num_rows, 2 * row_len
 
 

@@ -12,7 +12,7 @@ def make_code(nv, seeds, oracle):
 
     row_len, num_rows, cw = shape_for(nv)
     p1, p2 = oracle.perm_from_seed(cw, seeds[0]), oracle.perm_from_seed(cw, seeds[1])
-    code = RaaCode.with_permutations(ZipTypes(1), row_len, 2, p1, p2)
+    code = RaaCode.with_permutations(ZipTypes(), row_len, 2, p1, p2)
     return code, row_len, num_rows, cw, p1, p2
 
 

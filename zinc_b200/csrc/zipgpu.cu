@@ -2,13 +2,15 @@
 // host<->device pipeline around the kernels, device-resident prover data.
 //
 // Host-pointer entry points split the rows into chunks and run  H2D(chunk k+1) || kernels(chunk k) || D2H(chunk k-1)
-// on three streams, so that the PCIe copies of a commit hide behind the hashing.  All device memory comes from the
-// stream-ordered pool (cudaMallocAsync) whose release threshold is lifted, so steady-state calls allocate nothing.
+// on three streams, so that the PCIe copies of a commit hide behind the hashing.  Device buffers are recycled by a
+// per-context cache (dev_alloc/dev_free), so steady-state calls never reach cudaMalloc.
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -32,7 +34,18 @@ struct ProfRec {
     bool has_enc, has_hash;
 };
 
+// Device buffers are recycled through a small per-context cache (a freed buffer carries the event after which
+// it may be reused on another stream), so steady-state calls never reach cudaMalloc/cudaFree.
+struct CachedBuf {
+    void *p;
+    size_t bytes;
+    cudaEvent_t ready;
+};
+
 struct zipgpu_ctx {
+    std::vector<CachedBuf> cache_free;
+    std::vector<CachedBuf> cache_live;
+    std::mutex cache_mu;
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;  // kernels
@@ -105,6 +118,56 @@ static cudaError_t chain(zipgpu_ctx *c, cudaStream_t src, cudaStream_t waiter) {
     return cudaStreamWaitEvent(waiter, e, 0);
 }
 
+static cudaError_t dev_alloc(zipgpu_ctx *c, void **out, size_t bytes, cudaStream_t s) {
+    bytes = std::max<size_t>((bytes + 511) & ~(size_t)511, 512);
+    std::lock_guard<std::mutex> lk(c->cache_mu);
+    size_t best = (size_t)-1;
+    for (size_t i = 0; i < c->cache_free.size(); i++) {
+        const size_t b = c->cache_free[i].bytes;
+        if (b >= bytes && b <= bytes + bytes / 4 && (best == (size_t)-1 || b < c->cache_free[best].bytes)) best = i;
+    }
+    CachedBuf buf;
+    if (best != (size_t)-1) {
+        buf = c->cache_free[best];
+        c->cache_free.erase(c->cache_free.begin() + best);
+        cudaError_t e = cudaStreamWaitEvent(s, buf.ready, 0);
+        if (e != cudaSuccess) return e;
+    } else {
+        cudaError_t e = cudaMalloc(&buf.p, bytes);
+        if (e == cudaErrorMemoryAllocation) {  // drop the cache and retry once
+            cudaGetLastError();
+            cudaDeviceSynchronize();
+            for (auto &f : c->cache_free) { cudaFree(f.p); cudaEventDestroy(f.ready); }
+            c->cache_free.clear();
+            e = cudaMalloc(&buf.p, bytes);
+        }
+        if (e != cudaSuccess) return e;
+        buf.bytes = bytes;
+        e = cudaEventCreateWithFlags(&buf.ready, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    c->cache_live.push_back(buf);
+    *out = buf.p;
+    return cudaSuccess;
+}
+// the buffer may be handed out again once everything enqueued on `s` so far has completed
+static cudaError_t dev_free(zipgpu_ctx *c, void *p, cudaStream_t s) {
+    if (!p) return cudaSuccess;
+    std::lock_guard<std::mutex> lk(c->cache_mu);
+    for (size_t i = 0; i < c->cache_live.size(); i++) {
+        if (c->cache_live[i].p == p) {
+            CachedBuf buf = c->cache_live[i];
+            c->cache_live.erase(c->cache_live.begin() + i);
+            cudaError_t e = cudaEventRecord(buf.ready, s);
+            c->cache_free.push_back(buf);
+            return e;
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+#define DEV_ALLOC(ctx, ptr, bytes, s) CU(dev_alloc((ctx), (void **)(ptr), (bytes), (s)))
+#define DEV_FREE(ctx, ptr, s) CU(dev_free((ctx), (ptr), (s)))
+
 // ------------------------------------------------------------------------------------------------------
 // library / context
 // ------------------------------------------------------------------------------------------------------
@@ -158,11 +221,6 @@ extern "C" int zipgpu_ctx_create(int device, zipgpu_ctx **out) {
             return cuda_fail(e, "cudaEventCreate");
         }
     }
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
     if ((e = cudaMalloc(&c->d_sink, 256)) != cudaSuccess) {
         delete c;
         return cuda_fail(e, "cudaMalloc");
@@ -178,6 +236,8 @@ extern "C" void zipgpu_ctx_destroy(zipgpu_ctx *c) {
     for (auto &r : c->prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); cudaEventDestroy(r.e2); }
     for (auto &r : c->prof_free) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); cudaEventDestroy(r.e2); }
     for (auto &ev : c->ring) cudaEventDestroy(ev);
+    for (auto &b : c->cache_free) { cudaFree(b.p); cudaEventDestroy(b.ready); }
+    for (auto &b : c->cache_live) { cudaFree(b.p); cudaEventDestroy(b.ready); }
     if (c->d_sink) cudaFree(c->d_sink);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->h2d);
@@ -436,6 +496,10 @@ extern "C" int zipgpu_encode_rows_device(zipgpu_code *code, size_t num_rows, con
 }
 
 static size_t pick_chunk_rows(size_t num_rows, size_t bytes_per_row_in, int num_sms) {
+    if (const char *env = getenv("ZIPGPU_CHUNK_ROWS")) {  // tuning knob for experiments
+        const long v = atol(env);
+        if (v > 0) return std::min<size_t>((size_t)v, std::max<size_t>(num_rows, 1));
+    }
     // ~16 MiB of input per chunk, at least two CTAs per SM worth of rows, at most 32 chunks
     size_t rows = std::max<size_t>((16u << 20) / std::max<size_t>(bytes_per_row_in, 1), (size_t)num_sms * 2);
     rows = std::max(rows, (num_rows + 31) / 32);
@@ -466,13 +530,17 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
     uint64_t *d_evals = nullptr, *d_rows = nullptr;
     uint8_t *d_layers = nullptr, *d_roots = nullptr;
     cudaStream_t s = ctx->stream;
-    CU(cudaMallocAsync(&d_evals, num_rows * in_row_bytes, s));
-    CU(cudaMallocAsync(&d_rows, num_rows * out_row_bytes, s));
+    static const bool trace = getenv("ZIPGPU_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    DEV_ALLOC(ctx, &d_evals, num_rows * in_row_bytes, s);
+    DEV_ALLOC(ctx, &d_rows, num_rows * out_row_bytes, s);
     if (merkle) {
-        CU(cudaMallocAsync(&d_layers, std::max<size_t>(num_rows * lay_row_bytes, 32), s));
-        CU(cudaMallocAsync(&d_roots, num_rows * 32, s));
+        DEV_ALLOC(ctx, &d_layers, std::max<size_t>(num_rows * lay_row_bytes, 32), s);
+        DEV_ALLOC(ctx, &d_roots, num_rows * 32, s);
     }
     cudaError_t e;
+    const double t_alloc = now();
     if ((e = chain(ctx, s, ctx->h2d)) != cudaSuccess) return cuda_fail(e, "chain");
     if ((e = chain(ctx, s, ctx->d2h)) != cudaSuccess) return cuda_fail(e, "chain");
 
@@ -503,7 +571,9 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
     // join the copy streams back into the kernel stream so the frees are ordered after every use
     if ((e = chain(ctx, ctx->d2h, s)) != cudaSuccess) return cuda_fail(e, "chain");
     if ((e = chain(ctx, ctx->h2d, s)) != cudaSuccess) return cuda_fail(e, "chain");
-    CU(cudaFreeAsync(d_evals, s));
+    const double t_enq = now();
+    DEV_FREE(ctx, d_evals, s);
+    if (trace) fprintf(stderr, "[zipgpu] host job: alloc %.3f ms, enqueue %.3f ms\n", t_alloc - t_begin, t_enq - t_alloc);
     if (job.keep) {
         zipgpu_data *d = new (std::nothrow) zipgpu_data();
         if (!d) return fail(ZIPGPU_ERR_NOMEM, "host allocation failed");
@@ -517,9 +587,9 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
         d->d_roots = d_roots;
         *job.keep = d;
     } else {
-        CU(cudaFreeAsync(d_rows, s));
-        if (d_layers) CU(cudaFreeAsync(d_layers, s));
-        if (d_roots) CU(cudaFreeAsync(d_roots, s));
+        DEV_FREE(ctx, d_rows, s);
+        if (d_layers) DEV_FREE(ctx, d_layers, s);
+        if (d_roots) DEV_FREE(ctx, d_roots, s);
     }
     return ZIPGPU_OK;
 }
@@ -548,7 +618,7 @@ extern "C" int zipgpu_merkle_rows_device(zipgpu_ctx *ctx, size_t num_rows, int d
         return rc;
     uint8_t *scratch = nullptr;
     if (!d_layers_out && depth > 0) {
-        CU(cudaMallocAsync(&scratch, num_rows * layers_per_row(depth) * 32, s));
+        DEV_ALLOC(ctx, &scratch, num_rows * layers_per_row(depth) * 32, s);
         d_layers_out = scratch;
     }
     ProfRec r;
@@ -561,7 +631,7 @@ extern "C" int zipgpu_merkle_rows_device(zipgpu_ctx *ctx, size_t num_rows, int d
         std::lock_guard<std::mutex> lk(ctx->mu);
         ctx->prof_pending.push_back(r);
     }
-    if (scratch) CU(cudaFreeAsync(scratch, s));
+    if (scratch) DEV_FREE(ctx, scratch, s);
     return rc;
 }
 
@@ -577,18 +647,18 @@ extern "C" int zipgpu_merkle_rows(zipgpu_ctx *ctx, size_t num_rows, int depth, i
     const size_t lay_bytes = num_rows * layers_per_row(depth) * 32;
     uint64_t *d_leaves = nullptr;
     uint8_t *d_layers = nullptr, *d_roots = nullptr;
-    CU(cudaMallocAsync(&d_leaves, leaf_bytes, s));
-    CU(cudaMallocAsync(&d_layers, std::max<size_t>(lay_bytes, 32), s));
-    CU(cudaMallocAsync(&d_roots, num_rows * 32, s));
+    DEV_ALLOC(ctx, &d_leaves, leaf_bytes, s);
+    DEV_ALLOC(ctx, &d_layers, std::max<size_t>(lay_bytes, 32), s);
+    DEV_ALLOC(ctx, &d_roots, num_rows * 32, s);
     CU(cudaMemcpyAsync(d_leaves, leaves, leaf_bytes, cudaMemcpyHostToDevice, s));
     int rc = zipgpu_merkle_rows_device(ctx, num_rows, depth, leaf_limbs, d_leaves, d_layers, d_roots, s);
     if (rc == 0) {
         if (layers_out && lay_bytes) CU(cudaMemcpyAsync(layers_out, d_layers, lay_bytes, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(roots_out, d_roots, num_rows * 32, cudaMemcpyDeviceToHost, s));
     }
-    CU(cudaFreeAsync(d_leaves, s));
-    CU(cudaFreeAsync(d_layers, s));
-    CU(cudaFreeAsync(d_roots, s));
+    DEV_FREE(ctx, d_leaves, s);
+    DEV_FREE(ctx, d_layers, s);
+    DEV_FREE(ctx, d_roots, s);
     CU(cudaStreamSynchronize(s));
     return rc;
 }
@@ -602,23 +672,24 @@ extern "C" int zipgpu_commit_device(zipgpu_code *code, size_t num_rows, const ui
     if (code->depth < 0)
         return fail(ZIPGPU_ERR_INVALID, "leaves.len().is_power_of_two(): codeword_len is not a power of two");
     if (num_rows == 0) return ZIPGPU_OK;
-    CU(cudaSetDevice(code->ctx->device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : code->ctx->stream;
+    zipgpu_ctx *ctx = code->ctx;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     int rc;
     if ((rc = check_align16(d_roots_out, "roots_out")) || (rc = check_align16(d_layers_out, "layers_out"))) return rc;
     uint64_t *rows_scratch = nullptr;
     uint8_t *layers_scratch = nullptr;
     if (!d_rows_out) {
-        CU(cudaMallocAsync(&rows_scratch, num_rows * code->cw * code->out_limbs * 8, s));
+        DEV_ALLOC(ctx, &rows_scratch, num_rows * code->cw * code->out_limbs * 8, s);
         d_rows_out = rows_scratch;
     }
     if (!d_layers_out && code->depth > 0) {
-        CU(cudaMallocAsync(&layers_scratch, num_rows * layers_per_row(code->depth) * 32, s));
+        DEV_ALLOC(ctx, &layers_scratch, num_rows * layers_per_row(code->depth) * 32, s);
         d_layers_out = layers_scratch;
     }
     rc = commit_dev(code, num_rows, d_evals, d_rows_out, d_layers_out, d_roots_out, s);
-    if (rows_scratch) CU(cudaFreeAsync(rows_scratch, s));
-    if (layers_scratch) CU(cudaFreeAsync(layers_scratch, s));
+    if (rows_scratch) DEV_FREE(ctx, rows_scratch, s);
+    if (layers_scratch) DEV_FREE(ctx, layers_scratch, s);
     return rc;
 }
 
@@ -667,9 +738,9 @@ extern "C" void zipgpu_data_free(zipgpu_data *d) {
     if (!d) return;
     cudaSetDevice(d->ctx->device);
     cudaStream_t s = d->ctx->stream;
-    if (d->d_rows) cudaFreeAsync(d->d_rows, s);
-    if (d->d_layers) cudaFreeAsync(d->d_layers, s);
-    if (d->d_roots) cudaFreeAsync(d->d_roots, s);
+    dev_free(d->ctx, d->d_rows, s);
+    dev_free(d->ctx, d->d_layers, s);
+    dev_free(d->ctx, d->d_roots, s);
     delete d;
 }
 extern "C" size_t zipgpu_data_num_rows(const zipgpu_data *d) { return d ? d->num_rows : 0; }
@@ -714,9 +785,9 @@ extern "C" int zipgpu_data_open_columns(const zipgpu_data *d, size_t num_cols, c
     const size_t path_bytes = num_cols * d->num_rows * (size_t)d->depth * 32;
     uint32_t *d_cols = nullptr, *d_vals = nullptr;
     uint8_t *d_paths = nullptr;
-    CU(cudaMallocAsync(&d_cols, num_cols * 4, s));
-    CU(cudaMallocAsync(&d_vals, val_bytes, s));
-    CU(cudaMallocAsync(&d_paths, std::max<size_t>(path_bytes, 32), s));
+    DEV_ALLOC(ctx, &d_cols, num_cols * 4, s);
+    DEV_ALLOC(ctx, &d_vals, val_bytes, s);
+    DEV_ALLOC(ctx, &d_paths, std::max<size_t>(path_bytes, 32), s);
     CU(cudaMemcpyAsync(d_cols, columns, num_cols * 4, cudaMemcpyHostToDevice, s));
     OpenArgs a;
     a.rows = reinterpret_cast<const uint32_t *>(d->d_rows);
@@ -735,9 +806,9 @@ extern "C" int zipgpu_data_open_columns(const zipgpu_data *d, size_t num_cols, c
     ctx->launches++;
     CU(cudaMemcpyAsync(col_values_out, d_vals, val_bytes, cudaMemcpyDeviceToHost, s));
     if (path_bytes) CU(cudaMemcpyAsync(paths_out, d_paths, path_bytes, cudaMemcpyDeviceToHost, s));
-    CU(cudaFreeAsync(d_cols, s));
-    CU(cudaFreeAsync(d_vals, s));
-    CU(cudaFreeAsync(d_paths, s));
+    DEV_FREE(ctx, d_cols, s);
+    DEV_FREE(ctx, d_vals, s);
+    DEV_FREE(ctx, d_paths, s);
     CU(cudaStreamSynchronize(s));
     return ZIPGPU_OK;
 }

@@ -78,29 +78,17 @@ def default_context() -> Context:
 # ----------------------------------------------------------------------------------------------------------
 @dataclass(frozen=True)
 class ZipTypes:
-    """traits/types.rs:202-217 + field/int.rs:276-289: N = Int<n>, L = Int<2n>, K = Int<4n>, M = Int<8n>."""
+    """traits/types.rs:202-217: limb counts of the four integer types of a Zip instantiation."""
 
-    int_limbs: int = 1
-
-    @property
-    def N(self) -> int:
-        return self.int_limbs
-
-    @property
-    def L(self) -> int:
-        return 2 * self.int_limbs
-
-    @property
-    def K(self) -> int:
-        return 4 * self.int_limbs
-
-    @property
-    def M(self) -> int:
-        return 8 * self.int_limbs
+    N: int = 1
+    L: int = 2
+    K: int = 4
+    M: int = 8
 
 
 def RandomFieldZipTypes(int_limbs: int = 1) -> ZipTypes:
-    return ZipTypes(int_limbs)
+    """field/int.rs:276-289: N = Int<n>, L = Int<2n>, K = Int<4n>, M = Int<8n>."""
+    return ZipTypes(int_limbs, 2 * int_limbs, 4 * int_limbs, 8 * int_limbs)
 
 
 def as_limbs(values, limbs: int) -> np.ndarray:
@@ -196,7 +184,7 @@ class RaaCode:
         self._native: dict[tuple[int, int, int], C.c_void_p] = {}
 
     @staticmethod
-    def new(spec, poly_size: int, transcript, zt: ZipTypes = ZipTypes(1)) -> "RaaCode":
+    def new(spec, poly_size: int, transcript, zt: ZipTypes = ZipTypes()) -> "RaaCode":
         """code_raa.rs:35-86"""
         num_vars = poly_size.bit_length() - 1  # ilog2
         row_len = int(nat.lib().zipgpu_raa_row_len(1 << num_vars))
