@@ -21,6 +21,27 @@ __device__ __forceinline__ void st_stream_v4(uint4 *p, const uint4 &v) {
                  : "memory");
 }
 
+// 32-byte global accesses (sm_100: LDG/STG.E.ENL2.256): one full sector per lane, so a 32-byte digest or Int<4>
+// never reaches L2 as two partial-sector writes
+struct __align__(32) u32x8 {
+    uint32_t w[8];
+};
+__device__ __forceinline__ void st_global_v8(void *p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const void *p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void ld_stream_v8(const void *p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
+
 // ---- multi-limb (W x u32, little-endian) wrap-around add: one carry chain per call ---------------------
 template <int W>
 __device__ __forceinline__ void add_limbs(uint32_t (&a)[W], const uint32_t (&b)[W]);

@@ -32,19 +32,20 @@ __device__ __forceinline__ uint4 *node_ptr(uint8_t *layers, uint8_t *roots, cons
     return reinterpret_cast<uint4 *>(layers + ((size_t)row * g.row_stride + off + idx) * 32);
 }
 
-__device__ __forceinline__ void store_digest(uint4 *p, const uint32_t (&d)[8]) {
-    p[0] = make_uint4(d[0], d[1], d[2], d[3]);
-    p[1] = make_uint4(d[4], d[5], d[6], d[7]);
-}
-__device__ __forceinline__ void load_digest(const uint4 *p, uint32_t (&d)[8]) {
-    const uint4 a = p[0], b = p[1];
-    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
-    d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
-}
+__device__ __forceinline__ void store_digest(uint4 *p, const uint32_t (&d)[8]) { st_global_v8(p, d); }
+__device__ __forceinline__ void load_digest(const uint4 *p, uint32_t (&d)[8]) { ld_global_v8(p, d); }
 
 template <int LEAF32>
 __device__ __forceinline__ void load_leaf(const uint32_t *p, uint32_t (&x)[LEAF32]) {
-    if constexpr (LEAF32 % 4 == 0) {
+    if constexpr (LEAF32 % 8 == 0) {
+#pragma unroll
+        for (int i = 0; i < LEAF32 / 8; i++) {
+            uint32_t a[8];
+            ld_stream_v8(p + 8 * i, a);
+#pragma unroll
+            for (int j = 0; j < 8; j++) x[8 * i + j] = a[j];
+        }
+    } else if constexpr (LEAF32 % 4 == 0) {
         const uint4 *p4 = reinterpret_cast<const uint4 *>(p);
 #pragma unroll
         for (int i = 0; i < LEAF32 / 4; i++) {
@@ -66,7 +67,7 @@ __device__ __forceinline__ void load_leaf(const uint32_t *p, uint32_t (&x)[LEAF3
 template <int LEAF32, int H>
 __global__ void __launch_bounds__(128)
     merkle_subtree_kernel(const uint32_t *__restrict__ leaves, uint8_t *layers, uint8_t *roots, uint32_t num_rows,
-                          TreeGeom g, uint32_t level_in) {
+                          TreeGeom g, uint32_t level_in, uint32_t one) {
     const uint32_t chunks_per_row = (g.cw >> level_in) >> H;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)num_rows * chunks_per_row) return;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(128)
         if constexpr (LEAF32 > 0) {
             uint32_t x[LEAF32];
             load_leaf<LEAF32>(leaves + ((size_t)row * g.cw + idx) * LEAF32, x);
-            b3::hash_leaf<LEAF32>(x, d);
+            b3::hash_leaf<LEAF32>(x, d, one);
             store_digest(node_ptr(layers, roots, g, row, 0, idx), d);
         } else {
             load_digest(node_ptr(layers, roots, g, row, level_in, idx), d);
@@ -91,10 +92,15 @@ __global__ void __launch_bounds__(128)
         for (int l = 0; l < H; l++) {
             if (!parked) {
                 if ((i >> l) & 1u) {
-                    uint32_t o[8];
-                    b3::hash_node(stack[l], d, o);
+                    b3::Digest lft, rgt;
 #pragma unroll
-                    for (int w = 0; w < 8; w++) d[w] = o[w];
+                    for (int w = 0; w < 8; w++) {
+                        lft.w[w] = stack[l][w];
+                        rgt.w[w] = d[w];
+                    }
+                    const b3::Digest o = b3::hash_node_call(lft, rgt, one);
+#pragma unroll
+                    for (int w = 0; w < 8; w++) d[w] = o.w[w];
                     store_digest(node_ptr(layers, roots, g, row, level_in + l + 1, idx >> (l + 1)), d);
                 } else {
 #pragma unroll
@@ -114,7 +120,7 @@ cudaError_t launch_pass(const MerkleArgs &a, const TreeGeom &g, uint32_t level_i
     if (grid == 0) return cudaSuccess;
     if (grid > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     merkle_subtree_kernel<LEAF32, H><<<(uint32_t)grid, block, 0, a.stream>>>(a.leaves, a.layers, a.roots, a.num_rows,
-                                                                           g, level_in);
+                                                                           g, level_in, 1u);
     return cudaGetLastError();
 }
 

@@ -34,16 +34,18 @@ __device__ __forceinline__ uint32_t slot_of(uint32_t t, uint32_t k, uint32_t T) 
     return k * T + (t ^ ((k << Swz<E>::SH) & 31u));
 }
 
-// inclusive scan of W-limb values across the CTA; on return v[k] holds the inclusive prefix over the logical
-// order i = t*E + k.  aux: 2 * 32 * W words of shared memory.
+// Scan of W-limb values across the CTA in the logical order i = t*E + k.  On return v[k] holds the inclusive scan
+// WITHIN the thread and pre[] the sum of everything owned by lower threads; the caller adds pre to each v[k] at
+// the point where it consumes it (keeps the live register set small).  aux: 2 * 32 * W words of shared memory.
 template <int W, int E>
-__device__ __forceinline__ void block_scan(uint32_t (&v)[E][W], uint32_t *aux, uint32_t t, uint32_t nwarps) {
+__device__ __forceinline__ void block_scan(uint32_t (&v)[E][W], uint32_t (&pre)[W], uint32_t *aux, uint32_t t,
+                                           uint32_t nwarps) {
     const uint32_t lane = t & 31u, warp = t >> 5;
 #pragma unroll
     for (int k = 1; k < E; k++) add_limbs<W>(v[k], v[k - 1]);
-    uint32_t tot[W], inc[W];
+    uint32_t inc[W];
 #pragma unroll
-    for (int w = 0; w < W; w++) inc[w] = tot[w] = v[E - 1][w];
+    for (int w = 0; w < W; w++) inc[w] = v[E - 1][w];
     // warp inclusive scan of thread totals
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -76,8 +78,7 @@ __device__ __forceinline__ void block_scan(uint32_t (&v)[E][W], uint32_t *aux, u
         }
     }
     __syncthreads();
-    // exclusive prefix of this thread = warp prefix + (inclusive - own total)
-    uint32_t pre[W];
+    // exclusive prefix of this thread = warp prefix + inclusive scan of the lower lanes of the warp
 #pragma unroll
     for (int w = 0; w < W; w++) {
         uint32_t e = __shfl_up_sync(0xffffffffu, inc[w], 1);
@@ -87,15 +88,25 @@ __device__ __forceinline__ void block_scan(uint32_t (&v)[E][W], uint32_t *aux, u
 #pragma unroll
     for (int w = 0; w < W; w++) wp[w] = aux[32 * W + warp * W + w];
     add_limbs<W>(pre, wp);
-#pragma unroll
-    for (int k = 0; k < E; k++) add_limbs<W>(v[k], pre);
-    (void)tot;
+}
+
+// Pre-translated permutation tables (built once per pp by build_encode_tables, below):
+//   tab1[i'] = word offset into the staged input row of the element that codeword position i gathers in pass 1
+//              ( (perm1[i] mod row_len) * IN32 )
+//   tab2[i'] = shared-memory slot of the s1 entry that codeword position i gathers in pass 2 ( slot(perm2[i]) )
+// stored "lane-major": position i = t*E + k lives at i' = (k / G) * (T * G) + t * G + (k % G) with G = min(E, 4), so
+// the G entries a thread needs for one group are one 16-byte load and consecutive lanes read consecutive
+// addresses (512 B per warp request, L2-resident: the tables are shared by every row).
+template <int E>
+__device__ __forceinline__ uint32_t tab_index(uint32_t t, uint32_t k, uint32_t T) {
+    constexpr uint32_t G = E < 4 ? E : 4;
+    return (k / G) * (T * G) + t * G + (k % G);
 }
 
 template <int IN32, int W, int E, bool CACHE_PERM, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
     raa_encode_kernel(const uint32_t *__restrict__ evals, uint32_t *__restrict__ rows_out,
-                      const uint32_t *__restrict__ perm1, const uint32_t *__restrict__ perm2, uint32_t num_rows,
+                      const uint32_t *__restrict__ tab1, const uint32_t *__restrict__ tab2, uint32_t num_rows,
                       uint32_t row_len, uint32_t cw, uint32_t out32) {
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t T = blockDim.x, t = threadIdx.x;
@@ -105,24 +116,36 @@ __global__ void __launch_bounds__(MAXT, MINB)
     uint32_t *aux = smem + (size_t)W * P;
     const uint32_t nwarps = T >> 5;
     const uint32_t in_words = row_len * IN32;
+    constexpr int G = E < 4 ? E : 4;
 
-    // CACHE_PERM: the permutations, translated to shared-memory offsets/slots, stay in registers for every row
-    // this CTA processes.  Otherwise (E = 16: 64-register budget) they are re-read from L2 in each phase.
-    uint32_t src1[CACHE_PERM ? E : 1], slot2[CACHE_PERM ? E : 1];
-    if (CACHE_PERM) {
+    // table entries of this thread, group g = entries k in [g*G, g*G+G)
+    auto load_group = [&](const uint32_t *tab, int g, uint32_t (&q)[G]) {
+        const uint32_t *p = tab + (size_t)g * (T * G) + t * G;
+        if constexpr (G == 4) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+            q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+        } else {
 #pragma unroll
-        for (int k = 0; k < E; k++) {
-            const uint32_t i = t * E + k;  // device tables are zero-padded to P entries
-            const uint32_t p1 = __ldg(perm1 + i), p2 = __ldg(perm2 + i);
-            src1[CACHE_PERM ? k : 0] = (p1 % row_len) * IN32;
-            slot2[CACHE_PERM ? k : 0] = slot_of<E>(p2 / E, p2 % E, T);
+            for (int j = 0; j < G; j++) q[j] = __ldg(p + j);
+        }
+    };
+
+    // CACHE_PERM (E <= 8): both tables stay in registers for every row this persistent CTA processes.
+    // Otherwise (E = 16 runs at a 64-register budget) the entries are re-read from L2 in each pass.
+    uint32_t src1[CACHE_PERM ? E : 1], slot2[CACHE_PERM ? E : 1];
+    if constexpr (CACHE_PERM) {
+#pragma unroll
+        for (int g = 0; g < E / G; g++) {
+            uint32_t q1[G], q2[G];
+            load_group(tab1, g, q1);
+            load_group(tab2, g, q2);
+#pragma unroll
+            for (int j = 0; j < G; j++) {
+                src1[CACHE_PERM ? g * G + j : 0] = q1[j];
+                slot2[CACHE_PERM ? g * G + j : 0] = q2[j];
+            }
         }
     }
-    // fetch perm[t*E + k] for the non-cached variant (E % 4 == 0 there): one 16-byte load per 4 entries
-    auto perm_at = [&](const uint32_t *perm, int k, uint4 &q) -> uint32_t {
-        if ((k & 3) == 0) q = __ldg(reinterpret_cast<const uint4 *>(perm + t * E + k));
-        return (k & 3) == 0 ? q.x : (k & 3) == 1 ? q.y : (k & 3) == 2 ? q.z : q.w;
-    };
 
     for (uint32_t row = blockIdx.x; row < num_rows; row += gridDim.x) {
         // ---- 1. stage the input row (coalesced, read-once) ----
@@ -138,33 +161,39 @@ __global__ void __launch_bounds__(MAXT, MINB)
 
         // ---- 2. y1 = widen(row[perm1[i] mod row_len]) ----
         uint32_t v[E][W];
-        uint4 pq = make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int k = 0; k < E; k++) {
-            const bool valid = (t * E + k) < cw;
-            const uint32_t so = CACHE_PERM ? src1[CACHE_PERM ? k : 0] : (perm_at(perm1, k, pq) % row_len) * IN32;
-            if (IN32 == 2) {
-                const uint2 x = *reinterpret_cast<const uint2 *>(stage + so);
-                v[k][0] = x.x;
-                v[k][1] = x.y;
-            } else {
+        for (int g = 0; g < E / G; g++) {
+            uint32_t q[G];
+            if constexpr (!CACHE_PERM) load_group(tab1, g, q);
 #pragma unroll
-                for (int w = 0; w < IN32; w++) v[k][w] = stage[so + w];
-            }
-            const uint32_t sign = (uint32_t)((int32_t)v[k][IN32 - 1] >> 31);
+            for (int j = 0; j < G; j++) {
+                const int k = g * G + j;
+                const uint32_t so = CACHE_PERM ? src1[CACHE_PERM ? k : 0] : q[j];
+                if (IN32 == 2) {
+                    const uint2 x = *reinterpret_cast<const uint2 *>(stage + so);
+                    v[k][0] = x.x;
+                    v[k][1] = x.y;
+                } else {
 #pragma unroll
-            for (int w = IN32; w < W; w++) v[k][w] = sign;
-            if (!valid) {
+                    for (int w = 0; w < IN32; w++) v[k][w] = stage[so + w];
+                }
+                const uint32_t sign = (uint32_t)((int32_t)v[k][IN32 - 1] >> 31);
 #pragma unroll
-                for (int w = 0; w < W; w++) v[k][w] = 0u;
+                for (int w = IN32; w < W; w++) v[k][w] = sign;
+                if ((t * E + k) >= cw) {  // padding positions (cw not a multiple of 32*E) contribute nothing
+#pragma unroll
+                    for (int w = 0; w < W; w++) v[k][w] = 0u;
+                }
             }
         }
-        __syncthreads();  // stage is dead from here on
 
         // ---- 3. s1 = prefix sum(y1), parked in the swizzled planes ----
-        block_scan<W, E>(v, aux, t, nwarps);
+        // (the barriers inside block_scan also order every thread's stage reads before the plane writes)
+        uint32_t pre[W];
+        block_scan<W, E>(v, pre, aux, t, nwarps);
 #pragma unroll
         for (int k = 0; k < E; k++) {
+            add_limbs<W>(v[k], pre);
             const uint32_t s = slot_of<E>(t, k, T);
 #pragma unroll
             for (int w = 0; w < W; w++) planes[w * P + s] = v[k][w];
@@ -173,63 +202,63 @@ __global__ void __launch_bounds__(MAXT, MINB)
 
         // ---- 4. y2 = s1[perm2[i]] ----
 #pragma unroll
-        for (int k = 0; k < E; k++) {
-            const bool valid = (t * E + k) < cw;
-            uint32_t sl;
-            if (CACHE_PERM) {
-                sl = slot2[CACHE_PERM ? k : 0];
-            } else {
-                const uint32_t p2 = perm_at(perm2, k, pq);
-                sl = slot_of<E>(p2 / E, p2 % E, T);
-            }
+        for (int g = 0; g < E / G; g++) {
+            uint32_t q[G];
+            if constexpr (!CACHE_PERM) load_group(tab2, g, q);
 #pragma unroll
-            for (int w = 0; w < W; w++) v[k][w] = valid ? planes[w * P + sl] : 0u;
+            for (int j = 0; j < G; j++) {
+                const int k = g * G + j;
+                const uint32_t sl = CACHE_PERM ? slot2[CACHE_PERM ? k : 0] : q[j];
+                const bool valid = (t * E + k) < cw;
+#pragma unroll
+                for (int w = 0; w < W; w++) v[k][w] = valid ? planes[w * P + sl] : 0u;
+            }
         }
-        __syncthreads();
 
         // ---- 5. s2 = prefix sum(y2) ----
-        block_scan<W, E>(v, aux, t, nwarps);
+        // (its barriers order every thread's plane reads before the next row's stage writes)
+        block_scan<W, E>(v, pre, aux, t, nwarps);
+
+        // ---- 6. write-out straight from registers, sign-extended to out32 words.  Each lane owns E consecutive
+        //         codeword entries; a 32-byte Int<4> leaves as ONE 256-bit store = one full L2 sector. ----
+        uint32_t *dst = rows_out + ((size_t)row * cw + (size_t)t * E) * out32;
 #pragma unroll
         for (int k = 0; k < E; k++) {
-            const uint32_t s = slot_of<E>(t, k, T);
+            add_limbs<W>(v[k], pre);
+            if ((t * E + k) < cw) {
+                const uint32_t sign = (uint32_t)((int32_t)v[k][W - 1] >> 31);
+                uint32_t *d = dst + (size_t)k * out32;
+                if ((out32 & 7u) == 0) {
+                    constexpr int QV = (W + 7) / 8;  // 32-byte vectors that still carry value words
 #pragma unroll
-            for (int w = 0; w < W; w++) planes[w * P + s] = v[k][w];
-        }
-        __syncthreads();
-
-        // ---- 6. coalesced write-out with sign extension to out32 words ----
-        uint32_t *dst_row = rows_out + (size_t)row * cw * out32;
+                    for (int qv = 0; qv < QV; qv++) {
+                        uint32_t o[8];
 #pragma unroll
-        for (int it = 0; it < E; it++) {
-            const uint32_t i = it * T + t;
-            if (i < cw) {
-                const uint32_t s = slot_of<E>(i / E, i % E, T);
-                uint32_t val[W];
-#pragma unroll
-                for (int w = 0; w < W; w++) val[w] = planes[w * P + s];
-                const uint32_t sign = (uint32_t)((int32_t)val[W - 1] >> 31);
-                uint32_t *dst = dst_row + (size_t)i * out32;
-                if ((out32 & 3u) == 0) {
-                    constexpr int QV = (W + 3) / 4;  // 16-byte vectors that still carry value words
+                        for (int j = 0; j < 8; j++) o[j] = (8 * qv + j < W) ? v[k][(8 * qv + j < W) ? 8 * qv + j : 0] : sign;
+                        st_global_v8(d + 8 * qv, o);
+                    }
+                    const uint32_t sg[8] = {sign, sign, sign, sign, sign, sign, sign, sign};
+                    for (uint32_t q = 8 * QV; q < out32; q += 8) st_global_v8(d + q, sg);
+                } else if ((out32 & 3u) == 0) {
+                    constexpr int QV = (W + 3) / 4;
 #pragma unroll
                     for (int qv = 0; qv < QV; qv++) {
                         uint4 o;
-                        o.x = (4 * qv + 0 < W) ? val[(4 * qv + 0 < W) ? 4 * qv + 0 : 0] : sign;
-                        o.y = (4 * qv + 1 < W) ? val[(4 * qv + 1 < W) ? 4 * qv + 1 : 0] : sign;
-                        o.z = (4 * qv + 2 < W) ? val[(4 * qv + 2 < W) ? 4 * qv + 2 : 0] : sign;
-                        o.w = (4 * qv + 3 < W) ? val[(4 * qv + 3 < W) ? 4 * qv + 3 : 0] : sign;
-                        st_stream_v4(reinterpret_cast<uint4 *>(dst + 4 * qv), o);
+                        o.x = (4 * qv + 0 < W) ? v[k][(4 * qv + 0 < W) ? 4 * qv + 0 : 0] : sign;
+                        o.y = (4 * qv + 1 < W) ? v[k][(4 * qv + 1 < W) ? 4 * qv + 1 : 0] : sign;
+                        o.z = (4 * qv + 2 < W) ? v[k][(4 * qv + 2 < W) ? 4 * qv + 2 : 0] : sign;
+                        o.w = (4 * qv + 3 < W) ? v[k][(4 * qv + 3 < W) ? 4 * qv + 3 : 0] : sign;
+                        st_stream_v4(reinterpret_cast<uint4 *>(d + 4 * qv), o);
                     }
                     const uint4 sg = make_uint4(sign, sign, sign, sign);
-                    for (uint32_t q = 4 * QV; q < out32; q += 4) st_stream_v4(reinterpret_cast<uint4 *>(dst + q), sg);
+                    for (uint32_t q = 4 * QV; q < out32; q += 4) st_stream_v4(reinterpret_cast<uint4 *>(d + q), sg);
                 } else {
 #pragma unroll
-                    for (int w = 0; w < W; w++) dst[w] = val[w];
-                    for (uint32_t q = W; q < out32; q++) dst[q] = sign;
+                    for (int w = 0; w < W; w++) d[w] = v[k][w];
+                    for (uint32_t q = W; q < out32; q++) d[q] = sign;
                 }
             }
         }
-        __syncthreads();  // planes are reused as the next row's stage
     }
 }
 
@@ -268,7 +297,7 @@ cudaError_t launch_one(const EncodeArgs &a, int T, size_t smem, int grid_cap_per
     if (grid_cap_per_sm > 0 && occ > grid_cap_per_sm) occ = grid_cap_per_sm;
     uint32_t grid = (uint32_t)a.num_sms * (uint32_t)occ;
     if (grid > a.num_rows) grid = a.num_rows;
-    kern<<<grid, T, smem, a.stream>>>(a.evals, a.rows_out, a.perm1, a.perm2, a.num_rows, a.row_len, a.cw, a.out32);
+    kern<<<grid, T, smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.num_rows, a.row_len, a.cw, a.out32);
     return cudaGetLastError();
 }
 
@@ -294,6 +323,29 @@ cudaError_t launch_w(const EncodeArgs &a) {
 size_t encode_perm_padded_len(uint32_t cw) {
     const EncodeCfg c = pick_cfg(cw);
     return (size_t)c.T * c.E;
+}
+
+// host side, once per pp: translate the two gather permutations into the kernel's table layout
+void build_encode_tables(const uint32_t *perm1, const uint32_t *perm2, uint32_t row_len, uint32_t cw, int in_limbs,
+                         uint32_t *tab1, uint32_t *tab2) {
+    const EncodeCfg c = pick_cfg(cw);
+    const uint32_t E = (uint32_t)c.E, T = (uint32_t)c.T, G = E < 4 ? E : 4;
+    const uint32_t sh = E >= 32 ? 0 : (E == 16 ? 1 : E == 8 ? 2 : E == 4 ? 3 : E == 2 ? 4 : 5);
+    const uint32_t in32 = (uint32_t)in_limbs * 2;
+    for (uint32_t t = 0; t < T; t++) {
+        for (uint32_t k = 0; k < E; k++) {
+            const uint32_t i = t * E + k;
+            const size_t at = (size_t)(k / G) * (T * G) + (size_t)t * G + (k % G);
+            if (i < cw) {
+                const uint32_t p2 = perm2[i], t2 = p2 / E, k2 = p2 % E;
+                tab1[at] = (perm1[i] % row_len) * in32;
+                tab2[at] = k2 * T + (t2 ^ ((k2 << sh) & 31u));
+            } else {
+                tab1[at] = 0;
+                tab2[at] = 0;
+            }
+        }
+    }
 }
 
 int encode_compute_limbs(int in_limbs, uint32_t cw) {

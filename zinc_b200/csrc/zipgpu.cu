@@ -365,11 +365,11 @@ extern "C" int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t rep, i
         delete c;
         return cuda_fail(e, "cudaMalloc(perm)");
     }
-    std::vector<uint32_t> tmp(padded, 0);
-    std::memcpy(tmp.data(), perm1, cw * 4);
-    CU(cudaMemcpy(c->d_perm1, tmp.data(), padded * 4, cudaMemcpyHostToDevice));
-    std::memcpy(tmp.data(), perm2, cw * 4);
-    CU(cudaMemcpy(c->d_perm2, tmp.data(), padded * 4, cudaMemcpyHostToDevice));
+    // the kernel consumes pre-translated, lane-major tables (raa_encode.cu), not the raw permutations
+    std::vector<uint32_t> t1(padded, 0), t2(padded, 0);
+    build_encode_tables(perm1, perm2, (uint32_t)row_len, (uint32_t)cw, in_limbs, t1.data(), t2.data());
+    CU(cudaMemcpy(c->d_perm1, t1.data(), padded * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_perm2, t2.data(), padded * 4, cudaMemcpyHostToDevice));
     *out = c;
     return ZIPGPU_OK;
 }
@@ -406,8 +406,8 @@ static bool prof_begin(zipgpu_ctx *c, ProfRec *r) {
 // ------------------------------------------------------------------------------------------------------
 // device-level building blocks
 // ------------------------------------------------------------------------------------------------------
-static int check_align16(const void *p, const char *name) {
-    if (((uintptr_t)p & 15) != 0) return fail(ZIPGPU_ERR_INVALID, std::string(name) + " must be 16-byte aligned");
+static int check_align16(const void *p, const char *name) {  // 32 bytes: rows, digests move as 256-bit accesses
+    if (((uintptr_t)p & 31) != 0) return fail(ZIPGPU_ERR_INVALID, std::string(name) + " must be 32-byte aligned");
     return ZIPGPU_OK;
 }
 
@@ -419,8 +419,8 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     EncodeArgs a;
     a.evals = reinterpret_cast<const uint32_t *>(d_evals);
     a.rows_out = reinterpret_cast<uint32_t *>(d_rows);
-    a.perm1 = code->d_perm1;
-    a.perm2 = code->d_perm2;
+    a.tab1 = code->d_perm1;
+    a.tab2 = code->d_perm2;
     a.num_rows = (uint32_t)num_rows;
     a.row_len = (uint32_t)code->row_len;
     a.cw = (uint32_t)code->cw;
