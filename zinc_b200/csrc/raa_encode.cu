@@ -18,7 +18,8 @@
 //     slot(t,k) = k*T + (t ^ (k << log2(32/E))) which is bank-conflict free both for the owner-thread
 //     writes (fixed k, consecutive t) and for the coalesced read-out (consecutive i = t*E + k).  The perm2
 //     gather is the only randomly-banked access.
-//   * Output is written with 16-byte stores, consecutive lanes -> consecutive 32-byte Int<4> values.
+//   * Output goes back through the planes so that consecutive lanes store consecutive 32-byte Int<4> values with
+//     one 256-bit store each (a scattered store costs the L1 data pipe one wavefront per 32-byte sector).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -215,26 +216,38 @@ __global__ void __launch_bounds__(MAXT, MINB)
             }
         }
 
-        // ---- 5. s2 = prefix sum(y2) ----
-        // (its barriers order every thread's plane reads before the next row's stage writes)
+        // ---- 5. s2 = prefix sum(y2), parked in the planes again (same conflict-free layout) ----
         block_scan<W, E>(v, pre, aux, t, nwarps);
-
-        // ---- 6. write-out straight from registers, sign-extended to out32 words.  Each lane owns E consecutive
-        //         codeword entries; a 32-byte Int<4> leaves as ONE 256-bit store = one full L2 sector. ----
-        uint32_t *dst = rows_out + ((size_t)row * cw + (size_t)t * E) * out32;
 #pragma unroll
         for (int k = 0; k < E; k++) {
             add_limbs<W>(v[k], pre);
-            if ((t * E + k) < cw) {
-                const uint32_t sign = (uint32_t)((int32_t)v[k][W - 1] >> 31);
-                uint32_t *d = dst + (size_t)k * out32;
+            const uint32_t s = slot_of<E>(t, k, T);
+#pragma unroll
+            for (int w = 0; w < W; w++) planes[w * P + s] = v[k][w];
+        }
+        __syncthreads();
+
+        // ---- 6. coalesced write-out with sign extension to out32 words: consecutive lanes read consecutive
+        //         codeword entries back (conflict-free by the XOR swizzle) and each 32-byte Int<4> leaves as ONE
+        //         256-bit store, so a warp request covers 1 KiB of contiguous output (8 full 128-byte lines). ----
+        uint32_t *dst_row = rows_out + (size_t)row * cw * out32;
+#pragma unroll
+        for (int it = 0; it < E; it++) {
+            const uint32_t i = it * T + t;
+            if (i < cw) {
+                const uint32_t s = slot_of<E>(i / E, i % E, T);
+                uint32_t val[W];
+#pragma unroll
+                for (int w = 0; w < W; w++) val[w] = planes[w * P + s];
+                const uint32_t sign = (uint32_t)((int32_t)val[W - 1] >> 31);
+                uint32_t *d = dst_row + (size_t)i * out32;
                 if ((out32 & 7u) == 0) {
                     constexpr int QV = (W + 7) / 8;  // 32-byte vectors that still carry value words
 #pragma unroll
                     for (int qv = 0; qv < QV; qv++) {
                         uint32_t o[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) o[j] = (8 * qv + j < W) ? v[k][(8 * qv + j < W) ? 8 * qv + j : 0] : sign;
+                        for (int j = 0; j < 8; j++) o[j] = (8 * qv + j < W) ? val[(8 * qv + j < W) ? 8 * qv + j : 0] : sign;
                         st_global_v8(d + 8 * qv, o);
                     }
                     const uint32_t sg[8] = {sign, sign, sign, sign, sign, sign, sign, sign};
@@ -244,21 +257,22 @@ __global__ void __launch_bounds__(MAXT, MINB)
 #pragma unroll
                     for (int qv = 0; qv < QV; qv++) {
                         uint4 o;
-                        o.x = (4 * qv + 0 < W) ? v[k][(4 * qv + 0 < W) ? 4 * qv + 0 : 0] : sign;
-                        o.y = (4 * qv + 1 < W) ? v[k][(4 * qv + 1 < W) ? 4 * qv + 1 : 0] : sign;
-                        o.z = (4 * qv + 2 < W) ? v[k][(4 * qv + 2 < W) ? 4 * qv + 2 : 0] : sign;
-                        o.w = (4 * qv + 3 < W) ? v[k][(4 * qv + 3 < W) ? 4 * qv + 3 : 0] : sign;
+                        o.x = (4 * qv + 0 < W) ? val[(4 * qv + 0 < W) ? 4 * qv + 0 : 0] : sign;
+                        o.y = (4 * qv + 1 < W) ? val[(4 * qv + 1 < W) ? 4 * qv + 1 : 0] : sign;
+                        o.z = (4 * qv + 2 < W) ? val[(4 * qv + 2 < W) ? 4 * qv + 2 : 0] : sign;
+                        o.w = (4 * qv + 3 < W) ? val[(4 * qv + 3 < W) ? 4 * qv + 3 : 0] : sign;
                         st_stream_v4(reinterpret_cast<uint4 *>(d + 4 * qv), o);
                     }
                     const uint4 sg = make_uint4(sign, sign, sign, sign);
                     for (uint32_t q = 4 * QV; q < out32; q += 4) st_stream_v4(reinterpret_cast<uint4 *>(d + q), sg);
                 } else {
 #pragma unroll
-                    for (int w = 0; w < W; w++) d[w] = v[k][w];
+                    for (int w = 0; w < W; w++) d[w] = val[w];
                     for (uint32_t q = W; q < out32; q++) d[q] = sign;
                 }
             }
         }
+        __syncthreads();  // the planes are reused as the next row's stage
     }
 }
 
