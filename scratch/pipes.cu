@@ -71,6 +71,26 @@ __global__ void __launch_bounds__(256) k(uint32_t *sink, int iters, uint32_t see
                     asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i]));
                     asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(b[i]) : "r"(one), "r"(a[i]));
                 }
+                if (KIND == 18) {  // IMAD.WIDE.U32 imm
+                    asm volatile("{ .reg .b64 t; mul.wide.u32 t, %0, 0x2000000; mov.b64 {%0,%1}, t; }" : "+r"(a[i]), "=r"(b[i]));
+                }
+                if (KIND == 19) {  // IMAD.WIDE.U32 reg
+                    asm volatile("{ .reg .b64 t; mul.wide.u32 t, %0, %2; mov.b64 {%0,%1}, t; }" : "+r"(a[i]), "=r"(b[i]) : "r"(one));
+                }
+                if (KIND == 20) {  // IMAD.HI.U32 reg
+                    asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(one), "r"(b[i]));
+                }
+                if (KIND == 21) {  // LEA.HI (shift+add on alu)
+                    asm volatile("{ .reg .b32 t; shf.l.wrap.b32 t, %0, %0, 25; add.u32 %0, t, %1; }" : "+r"(a[i]) : "r"(b[i]));
+                }
+                if (KIND == 22) {  // 1 alu : 2 imad-imm
+                    asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i]));
+                    asm volatile("mad.lo.u32 %0, %0, 3, %1;" : "+r"(b[i]) : "r"(a[i]));
+                    asm volatile("mad.lo.u32 %0, %0, 5, %1;" : "+r"(b[i]) : "r"(one));
+                }
+                if (KIND == 23) {  // imad-imm only
+                    asm volatile("mad.lo.u32 %0, %0, 3, %1;" : "+r"(a[i]) : "r"(b[i]));
+                }
                 if (KIND == 12) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(one)); }
                 if (KIND == 13) { asm volatile("vadd.u32.u32.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i])); }
                 if (KIND == 14) {
@@ -86,10 +106,10 @@ __global__ void __launch_bounds__(256) k(uint32_t *sink, int iters, uint32_t see
     if (s == 0x12345u) sink[0] = s;
 }
 
-static const double OPS[] = {1, 1, 1, 1, 1, 1, 2, 6, 6, 4, 3, 2, 1, 1, 2, 7, 7, 7};
+static const double OPS[] = {1, 1, 1, 1, 1, 1, 2, 6, 6, 4, 3, 2, 1, 1, 2, 7, 7, 7, 1, 1, 1, 1, 3, 1};
 static const char *NAME[] = {"add.u32", "xor (LOP3)", "shf", "prmt", "mad.lo reg-mult", "mad.lo x1", "add3 (2 adds)",
                              "halfG plain (6 ops)", "halfG c+d via mad (6 ops)", "3alu:1imad", "2alu:1imad", "1alu:1imad",
-                             "lop3 3-in", "vadd", "add.u64 (2 ops)", "halfG all-IMAD (4alu+3fma)", "halfG a+b IMAD,+m IADD (5+2)", "4alu+3fma independent"};
+                             "lop3 3-in", "vadd", "add.u64 (2 ops)", "halfG all-IMAD (4alu+3fma)", "halfG a+b IMAD,+m IADD (5+2)", "4alu+3fma independent", "IMAD.WIDE imm", "IMAD.WIDE reg", "IMAD.HI reg", "shf+add (LEA.HI?)", "1alu:2imad-imm", "imad-imm x3"};
 
 template <int KIND> void run(uint32_t *sink, int sms) {
     const int iters = 400, grid = sms * 8;
@@ -111,5 +131,6 @@ int main() {
     run<0>(sink, sms); run<1>(sink, sms); run<2>(sink, sms); run<3>(sink, sms); run<4>(sink, sms); run<5>(sink, sms);
     run<6>(sink, sms); run<7>(sink, sms); run<8>(sink, sms); run<9>(sink, sms); run<10>(sink, sms); run<11>(sink, sms);
     run<12>(sink, sms); run<15>(sink, sms); run<16>(sink, sms); run<17>(sink, sms);
+    run<18>(sink, sms); run<19>(sink, sms); run<20>(sink, sms); run<21>(sink, sms); run<22>(sink, sms); run<23>(sink, sms);
     return 0;
 }

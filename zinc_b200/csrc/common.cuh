@@ -21,6 +21,13 @@ __device__ __forceinline__ void st_stream_v4(uint4 *p, const uint4 &v) {
                  : "memory");
 }
 
+// asynchronous bulk prefetch of [p, p+bytes) into L2 (sm_90+: one instruction, no registers, no completion to wait for).
+// p and bytes must be multiples of 16.
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+    if ((bytes & 15u) == 0 && bytes != 0)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // 32-byte global accesses (sm_100: LDG/STG.E.ENL2.256): one full sector per lane, so a 32-byte digest or Int<4>
 // never reaches L2 as two partial-sector writes
 struct __align__(32) u32x8 {

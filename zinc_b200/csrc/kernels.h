@@ -10,8 +10,9 @@ namespace zipgpu {
 struct EncodeArgs {
     const uint32_t *evals;   // [num_rows][row_len][2*in_limbs]
     uint32_t *rows_out;      // [num_rows][cw][out32]
-    const uint32_t *tab1;    // device tables from build_encode_tables, encode_perm_padded_len(cw) entries each
-    const uint32_t *tab2;
+    const uint16_t *tab1;    // device tables from build_encode_tables, encode_perm_padded_len(cw) entries each
+    const uint16_t *tab2;
+    const uint8_t *colw;
     uint32_t num_rows, row_len, cw, out32;
     int in_limbs;
     int num_sms;
@@ -19,9 +20,9 @@ struct EncodeArgs {
 };
 size_t encode_perm_padded_len(uint32_t cw);
 void build_encode_tables(const uint32_t *perm1, const uint32_t *perm2, uint32_t row_len, uint32_t cw, int in_limbs,
-                         uint32_t *tab1, uint32_t *tab2);
+                         uint16_t *tab1, uint16_t *tab2, uint8_t *colw);
 int encode_compute_limbs(int in_limbs, uint32_t cw);
-bool encode_supported(int in_limbs, uint32_t cw);
+bool encode_supported(int in_limbs, uint32_t cw, uint32_t row_len);
 cudaError_t launch_raa_encode(const EncodeArgs &a);
 
 // ---- K2/K3: BLAKE3 leaves + per-row Merkle levels (merkle.cu) ----

@@ -6,20 +6,24 @@
 //
 // Design (B200-first, not a translation of the Rust loops):
 //   * One CTA owns one row at a time and keeps the whole codeword on chip: the only HBM traffic is the
-//     compulsory 8 B read + 64 B written per evaluation (INT_LIMBS=1).  The CTA is persistent over rows so
-//     the two permutations (identical for every row of a pp) are loaded ONCE into registers, already
-//     translated to shared-memory slots.
+//     compulsory 8 B read + 64 B written per evaluation (INT_LIMBS=1).  The CTA is persistent over rows; the
+//     next row's evaluations are fetched into registers while the current row is being written out, so the
+//     DRAM latency of the input hides behind the output stores.
 //   * repeat o perm1 folds into a gather from the staged input row: y1[i] = widen(row[perm1[i] mod row_len]).
 //   * Values are held in W 32-bit limbs (W=3, 96 bit, is exact for Int<1> inputs up to cw = 2^16 because
 //     |s2| < 2^63 * cw^2); the stored Int<K> is the sign extension, produced on the way out.
 //   * Each thread owns E consecutive codeword positions: a serial carry-chain scan in registers, a
 //     warp-shuffle scan of the per-thread totals and one cross-warp step give the row prefix sum.
-//   * s1 lives in shared memory as W planes of u32, in a thread-striped XOR-swizzled layout
-//     slot(t,k) = k*T + (t ^ (k << log2(32/E))) which is bank-conflict free both for the owner-thread
-//     writes (fixed k, consecutive t) and for the coalesced read-out (consecutive i = t*E + k).  The perm2
-//     gather is the only randomly-banked access.
-//   * Output goes back through the planes so that consecutive lanes store consecutive 32-byte Int<4> values with
-//     one 256-bit store each (a scattered store costs the L1 data pipe one wavefront per 32-byte sector).
+//   * s1 lives in shared memory as W planes of u32.  Its layout is chosen per pp on the host so that BOTH the
+//     owner-thread writes and the perm2 gather are bank-conflict free: elements are the edges of a 32-regular
+//     bipartite multigraph (write group = warp x step on one side, read group = warp x step of the gathering
+//     position on the other); a proper 32-edge-colouring (Koenig; Euler splits) gives every element a bank
+//     such that no group sees a bank twice.  address = write_group * 32 + colour.
+//   * s2 uses a thread-striped XOR-swizzled layout slot(t,k) = k*T + (t ^ (k << log2(32/E))) which is
+//     conflict free for the owner-thread writes and for the coalesced read-out (consecutive i = t*E + k), so
+//     that consecutive lanes store consecutive 32-byte Int<4> values with one 256-bit store each.
+#include <vector>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -91,24 +95,95 @@ __device__ __forceinline__ void block_scan(uint32_t (&v)[E][W], uint32_t (&pre)[
     add_limbs<W>(pre, wp);
 }
 
-// Pre-translated permutation tables (built once per pp by build_encode_tables, below):
-//   tab1[i'] = word offset into the staged input row of the element that codeword position i gathers in pass 1
-//              ( (perm1[i] mod row_len) * IN32 )
-//   tab2[i'] = shared-memory slot of the s1 entry that codeword position i gathers in pass 2 ( slot(perm2[i]) )
-// stored "lane-major": position i = t*E + k lives at i' = (k / G) * (T * G) + t * G + (k % G) with G = min(E, 4), so
-// the G entries a thread needs for one group are one 16-byte load and consecutive lanes read consecutive
-// addresses (512 B per warp request, L2-resident: the tables are shared by every row).
+// ---- per-pp tables (built once by build_encode_tables, below) ---------------------------------------------
+//   tab1 (u16): element index of the staged input row that codeword position i gathers in pass 1
+//               ( perm1[i] mod row_len )
+//   tab2 (u16): shared-memory address (within a plane) of the s1 entry that position i gathers in pass 2
+//   colw (u8) : bank (edge colour) at which the owner of s1 entry i parks it; address = write_group*32 + colour
+// stored "lane-major" in groups of 16 bytes so that the entries a thread needs are whole vector loads and
+// consecutive lanes read consecutive addresses (the tables are shared by every row: L2-resident).
 template <int E>
-__device__ __forceinline__ uint32_t tab_index(uint32_t t, uint32_t k, uint32_t T) {
-    constexpr uint32_t G = E < 4 ? E : 4;
-    return (k / G) * (T * G) + t * G + (k % G);
+struct Tab16 {  // u16 entries
+    static constexpr int G = E < 8 ? E : 8;          // entries per group
+    static constexpr int NG = E / G;                 // groups per thread
+    static constexpr int NR = (E + 1) / 2;           // packed registers
+    __host__ __device__ static size_t at(uint32_t t, uint32_t k, uint32_t T) {
+        return ((size_t)(k / G) * T + t) * G + (k % G);
+    }
+    __device__ __forceinline__ static void load(const uint16_t *tab, uint32_t t, uint32_t T, uint32_t (&r)[NR]) {
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            const uint16_t *p = tab + ((size_t)g * T + t) * G;
+            if constexpr (G == 8) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+                r[4 * g] = v.x; r[4 * g + 1] = v.y; r[4 * g + 2] = v.z; r[4 * g + 3] = v.w;
+            } else if constexpr (G == 4) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+                r[0] = v.x; r[1] = v.y;
+            } else if constexpr (G == 2) {
+                r[0] = __ldg(reinterpret_cast<const uint32_t *>(p));
+            } else {
+                r[0] = __ldg(p);
+            }
+        }
+    }
+    __device__ __forceinline__ static uint32_t get(const uint32_t (&r)[NR], int k) {
+        return (k & 1) ? (r[k >> 1] >> 16) : (r[k >> 1] & 0xffffu);
+    }
+};
+template <int E>
+struct Tab8 {  // u8 entries
+    static constexpr int G = E < 16 ? E : 16;
+    static constexpr int NG = E / G;
+    static constexpr int NR = (E + 3) / 4;
+    __host__ __device__ static size_t at(uint32_t t, uint32_t k, uint32_t T) {
+        return ((size_t)(k / G) * T + t) * G + (k % G);
+    }
+    __device__ __forceinline__ static void load(const uint8_t *tab, uint32_t t, uint32_t T, uint32_t (&r)[NR]) {
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            const uint8_t *p = tab + ((size_t)g * T + t) * G;
+            if constexpr (G == 16) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+                r[4 * g] = v.x; r[4 * g + 1] = v.y; r[4 * g + 2] = v.z; r[4 * g + 3] = v.w;
+            } else if constexpr (G == 8) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+                r[0] = v.x; r[1] = v.y;
+            } else if constexpr (G == 4) {
+                r[0] = __ldg(reinterpret_cast<const uint32_t *>(p));
+            } else if constexpr (G == 2) {
+                r[0] = __ldg(reinterpret_cast<const uint16_t *>(p));
+            } else {
+                r[0] = __ldg(p);
+            }
+        }
+    }
+    __device__ __forceinline__ static uint32_t get(const uint32_t (&r)[NR], int k) {
+        return (r[k >> 2] >> (8 * (k & 3))) & 0xffu;
+    }
+};
+
+// coalesced, read-once copy of one input row into shared memory
+__device__ __forceinline__ void stage_row(const uint32_t *src, uint32_t *stage, uint32_t in_words, uint32_t t, uint32_t T) {
+    if ((in_words & 3u) == 0) {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+        uint4 *d4 = reinterpret_cast<uint4 *>(stage);
+        for (uint32_t i = t; i < (in_words >> 2); i += T) d4[i] = ld_stream_v4(s4 + i);
+    } else {
+        for (uint32_t i = t; i < in_words; i += T) stage[i] = src[i];
+    }
 }
 
-template <int IN32, int W, int E, bool CACHE_PERM, int MAXT, int MINB>
+// IN32 : u32 words per input value          W    : u32 limbs carried through the scans
+// E    : codeword positions per thread      OUT32: u32 words per output value (0 = run-time `out32`)
+// CACHE: the three tables stay in registers for every row of this persistent CTA (E <= 8)
+// EXACT: cw == T*E: no padding predicates
+template <int IN32, int W, int E, int OUT32, bool CACHE, bool EXACT, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
     raa_encode_kernel(const uint32_t *__restrict__ evals, uint32_t *__restrict__ rows_out,
-                      const uint32_t *__restrict__ tab1, const uint32_t *__restrict__ tab2, uint32_t num_rows,
-                      uint32_t row_len, uint32_t cw, uint32_t out32) {
+                      const uint16_t *__restrict__ tab1, const uint16_t *__restrict__ tab2,
+                      const uint8_t *__restrict__ colw, uint32_t num_rows, uint32_t row_len, uint32_t cw,
+                      uint32_t out32_rt) {
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t T = blockDim.x, t = threadIdx.x;
     const uint32_t P = T * E;   // plane size in words (>= cw)
@@ -117,59 +192,35 @@ __global__ void __launch_bounds__(MAXT, MINB)
     uint32_t *aux = smem + (size_t)W * P;
     const uint32_t nwarps = T >> 5;
     const uint32_t in_words = row_len * IN32;
-    constexpr int G = E < 4 ? E : 4;
-
-    // table entries of this thread, group g = entries k in [g*G, g*G+G)
-    auto load_group = [&](const uint32_t *tab, int g, uint32_t (&q)[G]) {
-        const uint32_t *p = tab + (size_t)g * (T * G) + t * G;
-        if constexpr (G == 4) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
-            q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < G; j++) q[j] = __ldg(p + j);
-        }
-    };
-
-    // CACHE_PERM (E <= 8): both tables stay in registers for every row this persistent CTA processes.
-    // Otherwise (E = 16 runs at a 64-register budget) the entries are re-read from L2 in each pass.
-    uint32_t src1[CACHE_PERM ? E : 1], slot2[CACHE_PERM ? E : 1];
-    if constexpr (CACHE_PERM) {
-#pragma unroll
-        for (int g = 0; g < E / G; g++) {
-            uint32_t q1[G], q2[G];
-            load_group(tab1, g, q1);
-            load_group(tab2, g, q2);
-#pragma unroll
-            for (int j = 0; j < G; j++) {
-                src1[CACHE_PERM ? g * G + j : 0] = q1[j];
-                slot2[CACHE_PERM ? g * G + j : 0] = q2[j];
-            }
-        }
+    const uint32_t out32 = OUT32 ? (uint32_t)OUT32 : out32_rt;
+    using T16 = Tab16<E>;
+    using T8 = Tab8<E>;
+    // CACHE: the three tables are loaded once.  !CACHE (E = 16 runs at a 64-register budget): tab1 is (re)loaded
+    // while the previous row is written out, colw and tab2 while the scans run, so their L2 latency is never
+    // exposed and their registers are only live when v[] is not
+    uint32_t c1[T16::NR], c2[T16::NR], cc[T8::NR];
+    T16::load(tab1, t, T, c1);
+    if constexpr (CACHE) {
+        T16::load(tab2, t, T, c2);
+        T8::load(colw, t, T, cc);
     }
+    const uint32_t wbase = (t >> 5) * (E * 32);  // s1 address of this thread's write group for k = 0
 
-    for (uint32_t row = blockIdx.x; row < num_rows; row += gridDim.x) {
-        // ---- 1. stage the input row (coalesced, read-once) ----
-        const uint32_t *src = evals + (size_t)row * in_words;
-        if ((in_words & 3u) == 0) {
-            const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-            uint4 *d4 = reinterpret_cast<uint4 *>(stage);
-            for (uint32_t i = t; i < (in_words >> 2); i += T) d4[i] = ld_stream_v4(s4 + i);
-        } else {
-            for (uint32_t i = t; i < in_words; i += T) stage[i] = src[i];
-        }
-        __syncthreads();
+    // ---- prologue: stage the first row ----
+    uint32_t row = blockIdx.x;
+    if (row < num_rows) stage_row(evals + (size_t)row * in_words, stage, in_words, t, T);
+    __syncthreads();
 
-        // ---- 2. y1 = widen(row[perm1[i] mod row_len]) ----
+    for (; row < num_rows; row += gridDim.x) {
+        // pull the next row's input into L2 now: one bulk prefetch, no registers, a whole row-time of lead
+        if (t == 0 && row + gridDim.x < num_rows)
+            prefetch_l2_bulk(evals + (size_t)(row + gridDim.x) * in_words, in_words * 4u);
+        // ---- 1. y1 = widen(row[perm1[i] mod row_len]) ----
         uint32_t v[E][W];
+        {
 #pragma unroll
-        for (int g = 0; g < E / G; g++) {
-            uint32_t q[G];
-            if constexpr (!CACHE_PERM) load_group(tab1, g, q);
-#pragma unroll
-            for (int j = 0; j < G; j++) {
-                const int k = g * G + j;
-                const uint32_t so = CACHE_PERM ? src1[CACHE_PERM ? k : 0] : q[j];
+            for (int k = 0; k < E; k++) {
+                const uint32_t so = T16::get(c1, k) * IN32;
                 if (IN32 == 2) {
                     const uint2 x = *reinterpret_cast<const uint2 *>(stage + so);
                     v[k][0] = x.x;
@@ -181,42 +232,40 @@ __global__ void __launch_bounds__(MAXT, MINB)
                 const uint32_t sign = (uint32_t)((int32_t)v[k][IN32 - 1] >> 31);
 #pragma unroll
                 for (int w = IN32; w < W; w++) v[k][w] = sign;
-                if ((t * E + k) >= cw) {  // padding positions (cw not a multiple of 32*E) contribute nothing
+                if (!EXACT && (t * E + k) >= cw) {  // padding positions contribute nothing
 #pragma unroll
                     for (int w = 0; w < W; w++) v[k][w] = 0u;
                 }
             }
         }
 
-        // ---- 3. s1 = prefix sum(y1), parked in the swizzled planes ----
+        // ---- 2. s1 = prefix sum(y1), parked at the edge-coloured addresses ----
         // (the barriers inside block_scan also order every thread's stage reads before the plane writes)
         uint32_t pre[W];
+        if constexpr (!CACHE) T8::load(colw, t, T, cc);  // in flight during the scan
         block_scan<W, E>(v, pre, aux, t, nwarps);
+        {
 #pragma unroll
-        for (int k = 0; k < E; k++) {
-            add_limbs<W>(v[k], pre);
-            const uint32_t s = slot_of<E>(t, k, T);
+            for (int k = 0; k < E; k++) {
+                add_limbs<W>(v[k], pre);
+                const uint32_t s = wbase + k * 32 + T8::get(cc, k);
 #pragma unroll
-            for (int w = 0; w < W; w++) planes[w * P + s] = v[k][w];
-        }
-        __syncthreads();
-
-        // ---- 4. y2 = s1[perm2[i]] ----
-#pragma unroll
-        for (int g = 0; g < E / G; g++) {
-            uint32_t q[G];
-            if constexpr (!CACHE_PERM) load_group(tab2, g, q);
-#pragma unroll
-            for (int j = 0; j < G; j++) {
-                const int k = g * G + j;
-                const uint32_t sl = CACHE_PERM ? slot2[CACHE_PERM ? k : 0] : q[j];
-                const bool valid = (t * E + k) < cw;
-#pragma unroll
-                for (int w = 0; w < W; w++) v[k][w] = valid ? planes[w * P + sl] : 0u;
+                for (int w = 0; w < W; w++) planes[w * P + s] = v[k][w];
             }
         }
+        if constexpr (!CACHE) T16::load(tab2, t, T, c2);  // in flight across the barrier
+        __syncthreads();
 
-        // ---- 5. s2 = prefix sum(y2), parked in the planes again (same conflict-free layout) ----
+        // ---- 3. y2 = s1[perm2[i]] (conflict free by construction of the colouring) ----
+#pragma unroll
+        for (int k = 0; k < E; k++) {
+            const uint32_t sl = T16::get(c2, k);
+            const bool valid = EXACT || (t * E + k) < cw;
+#pragma unroll
+            for (int w = 0; w < W; w++) v[k][w] = valid ? planes[w * P + sl] : 0u;
+        }
+
+        // ---- 4. s2 = prefix sum(y2), parked in the swizzled planes ----
         block_scan<W, E>(v, pre, aux, t, nwarps);
 #pragma unroll
         for (int k = 0; k < E; k++) {
@@ -227,21 +276,24 @@ __global__ void __launch_bounds__(MAXT, MINB)
         }
         __syncthreads();
 
-        // ---- 6. coalesced write-out with sign extension to out32 words: consecutive lanes read consecutive
+        const uint32_t next = row + gridDim.x;
+        if constexpr (!CACHE) T16::load(tab1, t, T, c1);  // for the next row; in flight during the write-out
+
+        // ---- 5. coalesced write-out with sign extension to out32 words: consecutive lanes read consecutive
         //         codeword entries back (conflict-free by the XOR swizzle) and each 32-byte Int<4> leaves as ONE
         //         256-bit store, so a warp request covers 1 KiB of contiguous output (8 full 128-byte lines). ----
         uint32_t *dst_row = rows_out + (size_t)row * cw * out32;
 #pragma unroll
         for (int it = 0; it < E; it++) {
             const uint32_t i = it * T + t;
-            if (i < cw) {
+            if (EXACT || i < cw) {
                 const uint32_t s = slot_of<E>(i / E, i % E, T);
                 uint32_t val[W];
 #pragma unroll
                 for (int w = 0; w < W; w++) val[w] = planes[w * P + s];
                 const uint32_t sign = (uint32_t)((int32_t)val[W - 1] >> 31);
                 uint32_t *d = dst_row + (size_t)i * out32;
-                if ((out32 & 7u) == 0) {
+                if (OUT32 ? (OUT32 % 8 == 0) : ((out32 & 7u) == 0)) {
                     constexpr int QV = (W + 7) / 8;  // 32-byte vectors that still carry value words
 #pragma unroll
                     for (int qv = 0; qv < QV; qv++) {
@@ -251,7 +303,12 @@ __global__ void __launch_bounds__(MAXT, MINB)
                         st_global_v8(d + 8 * qv, o);
                     }
                     const uint32_t sg[8] = {sign, sign, sign, sign, sign, sign, sign, sign};
-                    for (uint32_t q = 8 * QV; q < out32; q += 8) st_global_v8(d + q, sg);
+                    if constexpr (OUT32 != 0) {
+#pragma unroll
+                        for (int q = 8 * QV; q < OUT32; q += 8) st_global_v8(d + q, sg);
+                    } else {
+                        for (uint32_t q = 8 * QV; q < out32; q += 8) st_global_v8(d + q, sg);
+                    }
                 } else if ((out32 & 3u) == 0) {
                     constexpr int QV = (W + 3) / 4;
 #pragma unroll
@@ -273,17 +330,21 @@ __global__ void __launch_bounds__(MAXT, MINB)
             }
         }
         __syncthreads();  // the planes are reused as the next row's stage
+
+        // ---- 6. stage the next row (its lines were pulled into L2 a row-time ago) ----
+        if (next < num_rows) stage_row(evals + (size_t)next * in_words, stage, in_words, t, T);
+        __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------------------------------------------
-// host-side launcher
+// host side
 // ------------------------------------------------------------------------------------------------------
 namespace {
 
 struct EncodeCfg {
     int E, T;
-    bool cache_perm;
+    bool cache;
 };
 
 EncodeCfg pick_cfg(uint32_t cw) {
@@ -299,20 +360,37 @@ EncodeCfg pick_cfg(uint32_t cw) {
     return c;
 }
 
-template <int IN32, int W, int E, bool CP, int MAXT, int MINB>
-cudaError_t launch_one(const EncodeArgs &a, int T, size_t smem, int grid_cap_per_sm) {
-    auto kern = raa_encode_kernel<IN32, W, E, CP, MAXT, MINB>;
+bool cfg_exact(const EncodeCfg &c, uint32_t row_len, uint32_t cw) {
+    return (uint32_t)c.T * (uint32_t)c.E == cw && 2 * row_len == cw;
+}
+
+template <int IN32, int W, int E, int OUT32, bool CACHE, bool EXACT, int MAXT, int MINB>
+cudaError_t launch_one(const EncodeArgs &a, int T, size_t smem) {
+    auto kern = raa_encode_kernel<IN32, W, E, OUT32, CACHE, EXACT, MAXT, MINB>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     int occ = 0;
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem);
     if (err != cudaSuccess) return err;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
-    if (grid_cap_per_sm > 0 && occ > grid_cap_per_sm) occ = grid_cap_per_sm;
     uint32_t grid = (uint32_t)a.num_sms * (uint32_t)occ;
     if (grid > a.num_rows) grid = a.num_rows;
-    kern<<<grid, T, smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.num_rows, a.row_len, a.cw, a.out32);
+    kern<<<grid, T, smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows, a.row_len, a.cw,
+                                      a.out32);
     return cudaGetLastError();
+}
+
+template <int IN32, int W, int OUT32, bool EXACT>
+cudaError_t launch_e(const EncodeArgs &a, const EncodeCfg &c, size_t smem) {
+    switch (c.E) {
+        case 16:
+            if (c.T <= 512) return launch_one<IN32, W, 16, OUT32, false, EXACT, 512, 2>(a, c.T, smem);
+            return launch_one<IN32, W, 16, OUT32, false, EXACT, 1024, 1>(a, c.T, smem);
+        case 8: return launch_one<IN32, W, 8, OUT32, true, EXACT, 512, 2>(a, c.T, smem);
+        case 4: return launch_one<IN32, W, 4, OUT32, true, EXACT, 512, 2>(a, c.T, smem);
+        case 2: return launch_one<IN32, W, 2, OUT32, true, EXACT, 512, 2>(a, c.T, smem);
+        default: return launch_one<IN32, W, 1, OUT32, true, EXACT, 512, 2>(a, c.T, smem);
+    }
 }
 
 template <int IN32, int W>
@@ -321,15 +399,63 @@ cudaError_t launch_w(const EncodeArgs &a) {
     const size_t P = (size_t)c.T * c.E;
     const size_t smem = (W * P + 64 * W) * sizeof(uint32_t);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    switch (c.E) {
-        case 16:
-            if (c.T <= 512) return launch_one<IN32, W, 16, false, 512, 2>(a, c.T, smem, 0);
-            return launch_one<IN32, W, 16, false, 1024, 1>(a, c.T, smem, 0);
-        case 8: return launch_one<IN32, W, 8, true, 512, 2>(a, c.T, smem, 0);
-        case 4: return launch_one<IN32, W, 4, true, 512, 2>(a, c.T, smem, 0);
-        case 2: return launch_one<IN32, W, 2, true, 512, 2>(a, c.T, smem, 0);
-        default: return launch_one<IN32, W, 1, true, 512, 2>(a, c.T, smem, 0);
+    const bool exact = cfg_exact(c, a.row_len, a.cw);
+#ifdef ZIPGPU_DEV_HOT_ONLY  // development builds: only the nv=24 instantiation (fast ptxas -v iterations)
+    return launch_one<2, 3, 16, 8, false, true, 512, 2>(a, c.T, smem);
+#else
+    // the hot instantiations (ZipTypes K = 4N limbs, exact power-of-two shapes) get a compile-time output width,
+    // no padding predicates and the register prefetch of the next row
+    if (exact && a.out32 == 4 * IN32) return launch_e<IN32, W, 4 * IN32, true>(a, c, smem);
+    return launch_e<IN32, W, 0, false>(a, c, smem);
+#endif
+}
+
+// Proper edge colouring of a d-regular bipartite multigraph (d a power of two) by recursive Euler splits.
+// Edge e joins left node eu[e] and right node ev[e]; colour[e] in [0, d).
+void euler_colour(const std::vector<uint32_t> &edges, const std::vector<uint32_t> &eu, const std::vector<uint32_t> &ev,
+                  uint32_t n_left, uint32_t n_right, uint32_t d, uint32_t base, std::vector<uint8_t> &colour) {
+    if (d == 1) {
+        for (uint32_t e : edges) colour[e] = (uint8_t)base;
+        return;
     }
+    // adjacency over the combined node space [0, n_left) + [n_left, n_left + n_right)
+    const uint32_t n = n_left + n_right, m = (uint32_t)edges.size();
+    std::vector<uint32_t> head(n + 1, 0);
+    for (uint32_t e : edges) {
+        head[eu[e] + 1]++;
+        head[n_left + ev[e] + 1]++;
+    }
+    for (uint32_t i = 0; i < n; i++) head[i + 1] += head[i];
+    std::vector<uint32_t> adj(2 * (size_t)m), fill(head.begin(), head.end() - 1);
+    for (uint32_t j = 0; j < m; j++) {
+        const uint32_t e = edges[j];
+        adj[fill[eu[e]]++] = j;
+        adj[fill[n_left + ev[e]]++] = j;
+    }
+    std::vector<uint32_t> cur(head.begin(), head.end() - 1);
+    std::vector<uint8_t> used(m, 0);
+    std::vector<uint32_t> half[2];
+    half[0].reserve(m / 2);
+    half[1].reserve(m / 2);
+    for (uint32_t s = 0; s < n_left; s++) {
+        uint32_t u = s;
+        for (;;) {  // closed trail from s: edges walked left->right go to half 0, right->left to half 1
+            while (cur[u] < head[u + 1] && used[adj[cur[u]]]) cur[u]++;
+            if (cur[u] == head[u + 1]) break;  // all degrees are even: a trail can only get stuck at its start
+            const uint32_t j = adj[cur[u]++];
+            used[j] = 1;
+            const uint32_t e = edges[j];
+            if (u < n_left) {
+                half[0].push_back(e);
+                u = n_left + ev[e];
+            } else {
+                half[1].push_back(e);
+                u = eu[e];
+            }
+        }
+    }
+    euler_colour(half[0], eu, ev, n_left, n_right, d / 2, base, colour);
+    euler_colour(half[1], eu, ev, n_left, n_right, d / 2, base + d / 2, colour);
 }
 
 }  // namespace
@@ -339,25 +465,60 @@ size_t encode_perm_padded_len(uint32_t cw) {
     return (size_t)c.T * c.E;
 }
 
-// host side, once per pp: translate the two gather permutations into the kernel's table layout
-void build_encode_tables(const uint32_t *perm1, const uint32_t *perm2, uint32_t row_len, uint32_t cw, int in_limbs,
-                         uint32_t *tab1, uint32_t *tab2) {
+// host side, once per pp: translate the two gather permutations into the kernel's tables
+void build_encode_tables(const uint32_t *perm1, const uint32_t *perm2, uint32_t row_len, uint32_t cw, int /*in_limbs*/,
+                         uint16_t *tab1, uint16_t *tab2, uint8_t *colw) {
     const EncodeCfg c = pick_cfg(cw);
-    const uint32_t E = (uint32_t)c.E, T = (uint32_t)c.T, G = E < 4 ? E : 4;
-    const uint32_t sh = E >= 32 ? 0 : (E == 16 ? 1 : E == 8 ? 2 : E == 4 ? 3 : E == 2 ? 4 : 5);
-    const uint32_t in32 = (uint32_t)in_limbs * 2;
+    const uint32_t E = (uint32_t)c.E, T = (uint32_t)c.T, P = T * E;
+    auto at16 = [&](uint32_t t, uint32_t k) -> size_t {
+        const uint32_t G = E < 8 ? E : 8;
+        return ((size_t)(k / G) * T + t) * G + (k % G);
+    };
+    auto at8 = [&](uint32_t t, uint32_t k) -> size_t {
+        const uint32_t G = E < 16 ? E : 16;
+        return ((size_t)(k / G) * T + t) * G + (k % G);
+    };
+    auto group_of = [&](uint32_t pos) { return (pos / E / 32) * E + pos % E; };  // (warp, step) of a position
+
+    // bank of every s1 element: identity (the owner's lane) unless the shape is exact, where the colouring
+    // makes the gather conflict free as well
+    std::vector<uint8_t> colour(P);
+    for (uint32_t j = 0; j < P; j++) colour[j] = (uint8_t)((j / E) & 31u);
+    if (P == cw && T % 32 == 0) {
+        std::vector<uint32_t> eu(P), ev(P), edges(P);
+        for (uint32_t i = 0; i < cw; i++) {
+            const uint32_t j = perm2[i];  // element j is written by its owner and gathered by position i
+            eu[j] = group_of(j);
+            ev[j] = group_of(i);
+        }
+        for (uint32_t j = 0; j < P; j++) edges[j] = j;
+        std::vector<uint8_t> col(P, 0xff);
+        const uint32_t groups = (T / 32) * E;
+        euler_colour(edges, eu, ev, groups, groups, 32, 0, col);
+        // verify (cheap) before trusting it: every write group and every read group sees 32 distinct banks
+        std::vector<uint32_t> seen_w(groups, 0), seen_r(groups, 0);
+        bool ok = true;
+        for (uint32_t j = 0; j < P && ok; j++) {
+            if (col[j] > 31) { ok = false; break; }
+            const uint32_t bit = 1u << col[j];
+            if ((seen_w[eu[j]] & bit) || (seen_r[ev[j]] & bit)) ok = false;
+            seen_w[eu[j]] |= bit;
+            seen_r[ev[j]] |= bit;
+        }
+        if (ok) colour.swap(col);
+    }
+    auto addr1 = [&](uint32_t j) { return group_of(j) * 32 + colour[j]; };
     for (uint32_t t = 0; t < T; t++) {
         for (uint32_t k = 0; k < E; k++) {
             const uint32_t i = t * E + k;
-            const size_t at = (size_t)(k / G) * (T * G) + (size_t)t * G + (k % G);
             if (i < cw) {
-                const uint32_t p2 = perm2[i], t2 = p2 / E, k2 = p2 % E;
-                tab1[at] = (perm1[i] % row_len) * in32;
-                tab2[at] = k2 * T + (t2 ^ ((k2 << sh) & 31u));
+                tab1[at16(t, k)] = (uint16_t)(perm1[i] % row_len);
+                tab2[at16(t, k)] = (uint16_t)addr1(perm2[i]);
             } else {
-                tab1[at] = 0;
-                tab2[at] = 0;
+                tab1[at16(t, k)] = 0;
+                tab2[at16(t, k)] = 0;
             }
+            colw[at8(t, k)] = colour[i];
         }
     }
 }
@@ -369,12 +530,15 @@ int encode_compute_limbs(int in_limbs, uint32_t cw) {
     return (bits + 31) / 32;
 }
 
-bool encode_supported(int in_limbs, uint32_t cw) {
+bool encode_supported(int in_limbs, uint32_t cw, uint32_t row_len) {
     const int W = encode_compute_limbs(in_limbs, cw);
     if (!((in_limbs == 1 && (W == 3 || W == 4)) || (in_limbs == 2 && (W == 5 || W == 6)))) return false;
     const EncodeCfg c = pick_cfg(cw);
     if (c.T > 1024) return false;
+    if (row_len > 65535 || (size_t)c.T * c.E > 65536) return false;  // u16 tables
     const size_t P = (size_t)c.T * c.E;
+    // the staged input row aliases the planes
+    if ((size_t)row_len * in_limbs * 2 > (size_t)W * P) return false;
     return (W * P + 64 * W) * sizeof(uint32_t) <= 227 * 1024;
 }
 

@@ -68,7 +68,8 @@ struct zipgpu_code {
     size_t row_len, rep, cw;
     int in_limbs, out_limbs;
     int depth;  // -1 when cw is not a power of two (encode only)
-    uint32_t *d_perm1, *d_perm2;
+    uint16_t *d_tab1, *d_tab2;  // pre-translated gather tables (raa_encode.cu)
+    uint8_t *d_colw;
 };
 
 struct zipgpu_data {
@@ -345,7 +346,7 @@ extern "C" int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t rep, i
                                           std::to_string(64 * out_limbs) + " bits integers");
     if (!is_permutation(perm1, cw) || !is_permutation(perm2, cw))
         return fail(ZIPGPU_ERR_INVALID, "perm1/perm2 must be permutations of [0, codeword_len)");
-    if (!encode_supported(in_limbs, (uint32_t)cw))
+    if (!encode_supported(in_limbs, (uint32_t)cw, (uint32_t)row_len))
         return fail(ZIPGPU_ERR_UNSUPPORTED, "no encoder kernel for in_limbs=" + std::to_string(in_limbs) +
                                                 " codeword_len=" + std::to_string(cw) +
                                                 " (the codeword must fit one SM's shared memory)");
@@ -360,16 +361,23 @@ extern "C" int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t rep, i
     c->out_limbs = out_limbs;
     c->depth = is_pow2(cw) ? ilog2(cw) : -1;
     const size_t padded = encode_perm_padded_len((uint32_t)cw);
+    c->d_tab1 = c->d_tab2 = nullptr;
+    c->d_colw = nullptr;
     cudaError_t e;
-    if ((e = cudaMalloc(&c->d_perm1, padded * 4)) != cudaSuccess || (e = cudaMalloc(&c->d_perm2, padded * 4)) != cudaSuccess) {
+    if ((e = cudaMalloc(&c->d_tab1, padded * 2)) != cudaSuccess || (e = cudaMalloc(&c->d_tab2, padded * 2)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_colw, padded)) != cudaSuccess) {
+        cudaFree(c->d_tab1);
+        cudaFree(c->d_tab2);
         delete c;
-        return cuda_fail(e, "cudaMalloc(perm)");
+        return cuda_fail(e, "cudaMalloc(tables)");
     }
     // the kernel consumes pre-translated, lane-major tables (raa_encode.cu), not the raw permutations
-    std::vector<uint32_t> t1(padded, 0), t2(padded, 0);
-    build_encode_tables(perm1, perm2, (uint32_t)row_len, (uint32_t)cw, in_limbs, t1.data(), t2.data());
-    CU(cudaMemcpy(c->d_perm1, t1.data(), padded * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->d_perm2, t2.data(), padded * 4, cudaMemcpyHostToDevice));
+    std::vector<uint16_t> t1(padded, 0), t2(padded, 0);
+    std::vector<uint8_t> cl(padded, 0);
+    build_encode_tables(perm1, perm2, (uint32_t)row_len, (uint32_t)cw, in_limbs, t1.data(), t2.data(), cl.data());
+    CU(cudaMemcpy(c->d_tab1, t1.data(), padded * 2, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_tab2, t2.data(), padded * 2, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_colw, cl.data(), padded, cudaMemcpyHostToDevice));
     *out = c;
     return ZIPGPU_OK;
 }
@@ -378,8 +386,9 @@ extern "C" void zipgpu_code_destroy(zipgpu_code *c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(c->d_perm1);
-    cudaFree(c->d_perm2);
+    cudaFree(c->d_tab1);
+    cudaFree(c->d_tab2);
+    cudaFree(c->d_colw);
     delete c;
 }
 extern "C" size_t zipgpu_code_row_len(const zipgpu_code *c) { return c ? c->row_len : 0; }
@@ -419,8 +428,9 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     EncodeArgs a;
     a.evals = reinterpret_cast<const uint32_t *>(d_evals);
     a.rows_out = reinterpret_cast<uint32_t *>(d_rows);
-    a.tab1 = code->d_perm1;
-    a.tab2 = code->d_perm2;
+    a.tab1 = code->d_tab1;
+    a.tab2 = code->d_tab2;
+    a.colw = code->d_colw;
     a.num_rows = (uint32_t)num_rows;
     a.row_len = (uint32_t)code->row_len;
     a.cw = (uint32_t)code->cw;
