@@ -34,6 +34,12 @@ sys.path.insert(0, ROOT)
 KECCAK_SEEDS = (0xB9736F582676E7E8, 0xD7397E6260CE9C3E)  # fresh KeccakTranscript, as zip_benches.rs:102-106
 ENC_BYTES_PER_EVAL = 72.0          # 8 B read + 2 x 32 B written
 HASH_INSTR_PER_COMPRESSION = 680.0  # 7 rounds x 8 G x 12 + 8, minimum INT32 lane-instructions
+# alu-pipe (LOP3/SHF/PRMT/IADD3: 64 lanes/clk/SM on B200, scratch/pipes.cu) lane-instructions per compression: the
+# irreducible 7 x 8 x (4 xor + 4 rotate) + 8 feed-forward xors = 456, and what the SASS of merkle_subtree_kernel
+# actually issues (cuobjdump count, leaf + node average): 480
+HASH_ALU_MIN_PER_COMPRESSION = 456.0
+HASH_ALU_SASS_PER_COMPRESSION = 480.0
+ALU_LANES_PER_CLK_PER_SM = 64.0
 
 
 def shape_for(nv: int):
@@ -412,6 +418,18 @@ def main():
         enc_gbs = ENC_BYTES_PER_EVAL * n_evals / (enc_ms_avg * 1e-3) / 1e9
         compressions = num_rows * (2 * cw - 1)
         hash_rate = compressions / (hash_ms_avg * 1e-3)
+        clk = sampler.summary()
+        sm_hz = 1e6 * float(clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0)
+        num_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        alu_peak = ALU_LANES_PER_CLK_PER_SM * num_sms * sm_hz  # lane-instructions/s the alu pipe can issue
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (profiles/)
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tr = json.load(f).get("raa_encode_kernel", {})
+            if tr.get("nv") == nv:
+                traffic = tr.get("dram_bytes")
+        except Exception:
+            pass
         line = {
             "metric": "zip_commit_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -430,7 +448,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {
                 "kernel": "raa_encode_kernel", "bound": "hbm", "achieved": enc_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": enc_gbs / hbm_peak, "traffic": None, "ms_per_launch": enc_ms_avg,
+                "frac": enc_gbs / hbm_peak, "traffic": traffic, "ms_per_launch": enc_ms_avg,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": ENC_BYTES_PER_EVAL * n_evals,
             },
@@ -438,8 +456,12 @@ def main():
                 "kernels": "merkle_subtree_kernel x passes", "bound": "int32_alu", "ms_per_step": hash_ms_avg,
                 "compressions_per_step": compressions, "compressions_per_s": hash_rate,
                 "lane_instr_per_s_min": hash_rate * HASH_INSTR_PER_COMPRESSION,
-                "alu_pipe_peak_lane_ops_per_s": alu.value, "alu_fma_mix_peak_lane_ops_per_s": mix.value,
-                "frac_of_alu_pipe_peak": hash_rate * HASH_INSTR_PER_COMPRESSION / alu.value if alu.value else None,
+                "microbench_3alu_1fma_lane_ops_per_s": alu.value, "microbench_4alu_3fma_lane_ops_per_s": mix.value,
+                "alu_pipe_util_sass": hash_rate * HASH_ALU_SASS_PER_COMPRESSION / alu_peak,
+                "alu_pipe_frac_of_floor": hash_rate * HASH_ALU_MIN_PER_COMPRESSION / alu_peak,
+                "alu_pipe_peak_lane_instr_per_s": alu_peak,
+                "alu_model": "alu pipe = 64 lanes/clk/SM x SMs x sampled SM clock; 480 alu lane-instr per compression "
+                             "issued (SASS), 456 irreducible (xor + rotate + feed-forward)",
                 "share_of_step": hash_ms_avg / (hash_ms_avg + enc_ms_avg) if hash_ms_avg + enc_ms_avg > 0 else None,
             },
             "cpu_baseline": cpu_baseline,
