@@ -38,6 +38,9 @@ struct MerkleArgs {
 bool merkle_supported(int leaf32);
 // returns the number of kernel launches through *launches
 cudaError_t launch_merkle_rows(const MerkleArgs &a, int *launches);
+// pass plan (leaf pass = pass 0) and partial execution of it, for chunked pipelines
+int merkle_pass_plan(int depth, int *level_in, int *h);
+cudaError_t launch_merkle_passes(const MerkleArgs &a, int pass_begin, int pass_end, int *launches);
 
 // ---- K4: column openings (open_columns.cu) ----
 struct OpenArgs {

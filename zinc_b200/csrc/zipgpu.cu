@@ -15,6 +15,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/zipgpu.h"
@@ -32,6 +33,7 @@ using namespace zipgpu;
 struct ProfRec {
     cudaEvent_t e0, e1, e2;  // before encode, between, after hash
     bool has_enc, has_hash;
+    bool is_part;            // a continuation of an earlier record (deferred top passes): not a new call
 };
 
 // Device buffers are recycled through a small per-context cache (a freed buffer carries the event after which
@@ -49,6 +51,7 @@ struct zipgpu_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;  // kernels
+    cudaStream_t stream2 = nullptr; // kernels of every other chunk of a host job (tails overlap the next chunk)
     cudaStream_t h2d = nullptr;
     cudaStream_t d2h = nullptr;
     std::vector<cudaEvent_t> ring;  // timing-disabled events for cross-stream ordering
@@ -210,6 +213,7 @@ extern "C" int zipgpu_ctx_create(int device, zipgpu_ctx **out) {
     c->num_sms = prop.multiProcessorCount;
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking)) != cudaSuccess) {
         delete c;
@@ -241,6 +245,7 @@ extern "C" void zipgpu_ctx_destroy(zipgpu_ctx *c) {
     for (auto &b : c->cache_live) { cudaFree(b.p); cudaEventDestroy(b.ready); }
     if (c->d_sink) cudaFree(c->d_sink);
     cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->h2d);
     cudaStreamDestroy(c->d2h);
     delete c;
@@ -253,6 +258,7 @@ extern "C" int zipgpu_ctx_sync(zipgpu_ctx *c) {
     if (!c) return fail(ZIPGPU_ERR_INVALID, "ctx is NULL");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->h2d));
+    CU(cudaStreamSynchronize(c->stream2));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaStreamSynchronize(c->d2h));
     return ZIPGPU_OK;
@@ -408,7 +414,7 @@ static bool prof_begin(zipgpu_ctx *c, ProfRec *r) {
             cudaEventCreate(&r->e2) != cudaSuccess)
             return false;
     }
-    r->has_enc = r->has_hash = false;
+    r->has_enc = r->has_hash = r->is_part = false;
     return true;
 }
 
@@ -445,7 +451,7 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
 }
 
 static int merkle_dev(zipgpu_ctx *ctx, size_t num_rows, int depth, int leaf_limbs, const uint64_t *d_leaves,
-                      uint8_t *d_layers, uint8_t *d_roots, cudaStream_t s) {
+                      uint8_t *d_layers, uint8_t *d_roots, cudaStream_t s, int pass_begin = 0, int pass_end = -1) {
     if (num_rows == 0) return ZIPGPU_OK;
     if (num_rows > 0xffffffffull) return fail(ZIPGPU_ERR_UNSUPPORTED, "too many rows");
     if (depth < 0 || depth > 30) return fail(ZIPGPU_ERR_INVALID, "depth out of range");
@@ -460,15 +466,15 @@ static int merkle_dev(zipgpu_ctx *ctx, size_t num_rows, int depth, int leaf_limb
     a.leaf32 = leaf_limbs * 2;
     a.stream = s;
     int n = 0;
-    cudaError_t e = launch_merkle_rows(a, &n);
-    if (e != cudaSuccess) return cuda_fail(e, "launch_merkle_rows");
+    cudaError_t e = launch_merkle_passes(a, pass_begin, pass_end, &n);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_merkle_passes");
     ctx->launches += (uint64_t)n;
     return ZIPGPU_OK;
 }
 
 // encode + merkle of a row range on stream s, with optional profiling events
 static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_evals, uint64_t *d_rows, uint8_t *d_layers,
-                      uint8_t *d_roots, cudaStream_t s) {
+                      uint8_t *d_roots, cudaStream_t s, int merkle_pass_end = -1) {
     zipgpu_ctx *ctx = code->ctx;
     ProfRec r;
     const bool prof = prof_begin(ctx, &r);
@@ -480,7 +486,7 @@ static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
         r.has_enc = true;
     }
     if (d_roots) {
-        rc = merkle_dev(ctx, num_rows, code->depth, code->out_limbs, d_rows, d_layers, d_roots, s);
+        rc = merkle_dev(ctx, num_rows, code->depth, code->out_limbs, d_rows, d_layers, d_roots, s, 0, merkle_pass_end);
         if (rc) return rc;
         if (prof) {
             cudaEventRecord(r.e2, s);
@@ -488,6 +494,25 @@ static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
         }
     }
     if (prof) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->prof_pending.push_back(r);
+    }
+    return ZIPGPU_OK;
+}
+
+// the top passes [pass_begin, end) of the trees of `num_rows` rows whose lower levels are already in d_layers
+static int merkle_top_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_rows, uint8_t *d_layers, uint8_t *d_roots,
+                          cudaStream_t s, int pass_begin) {
+    zipgpu_ctx *ctx = code->ctx;
+    ProfRec r;
+    const bool prof = prof_begin(ctx, &r);
+    if (prof) cudaEventRecord(r.e1, s);
+    int rc = merkle_dev(ctx, num_rows, code->depth, code->out_limbs, d_rows, d_layers, d_roots, s, pass_begin, -1);
+    if (rc) return rc;
+    if (prof) {
+        cudaEventRecord(r.e2, s);
+        r.has_hash = true;
+        r.is_part = true;
         std::lock_guard<std::mutex> lk(ctx->mu);
         ctx->prof_pending.push_back(r);
     }
@@ -510,8 +535,8 @@ static size_t pick_chunk_rows(size_t num_rows, size_t bytes_per_row_in, int num_
         const long v = atol(env);
         if (v > 0) return std::min<size_t>((size_t)v, std::max<size_t>(num_rows, 1));
     }
-    // ~16 MiB of input per chunk, at least two CTAs per SM worth of rows, at most 32 chunks
-    size_t rows = std::max<size_t>((16u << 20) / std::max<size_t>(bytes_per_row_in, 1), (size_t)num_sms * 2);
+    // ~8 MiB of input per chunk (measured best on B200: copies stay back to back, the exposed tail is short)
+    size_t rows = std::max<size_t>((8u << 20) / std::max<size_t>(bytes_per_row_in, 1), (size_t)num_sms);
     rows = std::max(rows, (num_rows + 31) / 32);
     return std::min(rows, std::max<size_t>(num_rows, 1));
 }
@@ -553,19 +578,67 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
     const double t_alloc = now();
     if ((e = chain(ctx, s, ctx->h2d)) != cudaSuccess) return cuda_fail(e, "chain");
     if ((e = chain(ctx, s, ctx->d2h)) != cudaSuccess) return cuda_fail(e, "chain");
+    if ((e = chain(ctx, s, ctx->stream2)) != cudaSuccess) return cuda_fail(e, "chain");
+    // consecutive chunks alternate between two kernel streams: the tail of one chunk's kernels (partial waves, the
+    // latency-bound narrow passes) overlaps the head of the next chunk's
+    static const bool one_stream = getenv("ZIPGPU_ONE_STREAM") != nullptr;
+    cudaStream_t ks[2] = {s, one_stream ? s : ctx->stream2};
+    size_t chunk_no = 0;
 
+    // Chunk schedule: uniform chunks, the last one tapered (1/2, 1/4, 1/4) -- the H2D copies are the bottleneck
+    // resource of a host commit, so what remains exposed is the kernel work of the LAST chunk.
     const size_t chunk = pick_chunk_rows(num_rows, in_row_bytes, ctx->num_sms);
-    for (size_t r0 = 0; r0 < num_rows; r0 += chunk) {
-        const size_t n = std::min(chunk, num_rows - r0);
+    std::vector<std::pair<size_t, size_t>> sched;
+    for (size_t r0 = 0; r0 < num_rows; r0 += chunk) sched.emplace_back(r0, std::min(chunk, num_rows - r0));
+    if (sched.size() >= 3 && sched.back().second >= 256 && !getenv("ZIPGPU_NO_TAPER")) {
+        const std::pair<size_t, size_t> last = sched.back();
+        sched.pop_back();
+        const size_t a = last.second / 2, b = last.second / 4;
+        sched.emplace_back(last.first, a);
+        sched.emplace_back(last.first + a, b);
+        sched.emplace_back(last.first + a + b, last.second - a - b);
+    }
+    // The narrow top passes of the trees are latency-bound; per chunk they would cost their full latency every
+    // time.  Run the first two (wide) passes per chunk and the rest once over all rows -- unless the caller wants
+    // the layers streamed back chunk by chunk.
+    int pass_split = -1;
+    if (merkle && !job.layers_out && sched.size() > 1) {
+        int li[16], hh[16];
+        if (merkle_pass_plan(code->depth, li, hh) > 2) pass_split = 2;
+    }
+    // ZIPGPU_TIMELINE=1: timing events after every copy / chunk, printed relative to the first (diagnostics only)
+    static const bool timeline = getenv("ZIPGPU_TIMELINE") != nullptr;
+    std::vector<cudaEvent_t> tl_copy, tl_kern;
+    cudaEvent_t tl0 = nullptr;
+    if (timeline) {
+        cudaEventCreate(&tl0);
+        cudaEventRecord(tl0, ctx->h2d);
+    }
+    for (const auto &ch : sched) {
+        const size_t r0 = ch.first, n = ch.second;
         CU(cudaMemcpyAsync((uint8_t *)d_evals + r0 * in_row_bytes, (const uint8_t *)job.evals + r0 * in_row_bytes,
                            n * in_row_bytes, cudaMemcpyHostToDevice, ctx->h2d));
-        if ((e = chain(ctx, ctx->h2d, s)) != cudaSuccess) return cuda_fail(e, "chain");
+        if (timeline) {
+            cudaEvent_t ev;
+            cudaEventCreate(&ev);
+            cudaEventRecord(ev, ctx->h2d);
+            tl_copy.push_back(ev);
+        }
+        cudaStream_t k = ks[chunk_no++ & 1];
+        if ((e = chain(ctx, ctx->h2d, k)) != cudaSuccess) return cuda_fail(e, "chain");
         int rc = commit_dev(code, n, (const uint64_t *)((uint8_t *)d_evals + r0 * in_row_bytes),
                             (uint64_t *)((uint8_t *)d_rows + r0 * out_row_bytes),
-                            merkle ? d_layers + r0 * lay_row_bytes : nullptr, merkle ? d_roots + r0 * 32 : nullptr, s);
+                            merkle ? d_layers + r0 * lay_row_bytes : nullptr, merkle ? d_roots + r0 * 32 : nullptr, k,
+                            pass_split);
         if (rc) return rc;
+        if (timeline) {
+            cudaEvent_t ev;
+            cudaEventCreate(&ev);
+            cudaEventRecord(ev, k);
+            tl_kern.push_back(ev);
+        }
         if (job.rows_out || job.layers_out) {
-            if ((e = chain(ctx, s, ctx->d2h)) != cudaSuccess) return cuda_fail(e, "chain");
+            if ((e = chain(ctx, k, ctx->d2h)) != cudaSuccess) return cuda_fail(e, "chain");
             if (job.rows_out)
                 CU(cudaMemcpyAsync((uint8_t *)job.rows_out + r0 * out_row_bytes, (uint8_t *)d_rows + r0 * out_row_bytes,
                                    n * out_row_bytes, cudaMemcpyDeviceToHost, ctx->d2h));
@@ -573,6 +646,31 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
                 CU(cudaMemcpyAsync(job.layers_out + r0 * lay_row_bytes, d_layers + r0 * lay_row_bytes,
                                    n * lay_row_bytes, cudaMemcpyDeviceToHost, ctx->d2h));
         }
+    }
+    if ((e = chain(ctx, ctx->stream2, s)) != cudaSuccess) return cuda_fail(e, "chain");
+    if (pass_split >= 0) {
+        int rc = merkle_top_dev(code, num_rows, d_rows, d_layers, d_roots, s, pass_split);
+        if (rc) return rc;
+    }
+    if (timeline) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, s);
+        cudaEventSynchronize(ev);
+        float ms = 0;
+        fprintf(stderr, "[zipgpu timeline] chunk: rows, copy done (ms), kernels done (ms)\n");
+        for (size_t i = 0; i < sched.size(); i++) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, tl0, tl_copy[i]);
+            cudaEventElapsedTime(&b, tl0, tl_kern[i]);
+            fprintf(stderr, "  %2zu: %5zu  %7.3f  %7.3f\n", i, sched[i].second, a, b);
+            cudaEventDestroy(tl_copy[i]);
+            cudaEventDestroy(tl_kern[i]);
+        }
+        cudaEventElapsedTime(&ms, tl0, ev);
+        fprintf(stderr, "  all kernels done %7.3f ms\n", ms);
+        cudaEventDestroy(ev);
+        cudaEventDestroy(tl0);
     }
     if (merkle && job.roots_out) {
         if ((e = chain(ctx, s, ctx->d2h)) != cudaSuccess) return cuda_fail(e, "chain");
@@ -848,7 +946,7 @@ extern "C" int zipgpu_profile_read(zipgpu_ctx *c, double *encode_ms, double *has
             CU(cudaEventElapsedTime(&ms, r.e1, r.e2));
             c->hash_ms += ms;
         }
-        c->prof_calls++;
+        if (!r.is_part) c->prof_calls++;
         c->prof_free.push_back(r);
     }
     c->prof_pending.clear();
