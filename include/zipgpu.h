@@ -12,6 +12,7 @@
  *   MerkleTree::new                   src/zip/pcs/utils.rs:74-118     -> zipgpu_merkle_rows / zipgpu_merkle_rows_device
  *   MerkleProof::create_proof,
  *   ColumnOpening::open_at_column     src/zip/pcs/utils.rs:163-176,221-233, open_z.rs:124-143 -> zipgpu_data_open_columns
+ *   combine_rows (proximity test)     src/zip/utils.rs:94-127, open_z.rs:100-113        -> zipgpu_data_combine_rows / zipgpu_combine_rows_device
  *
  * Conventions
  *   - Integers are the in-memory layout of `[Int<n>]`: n little-endian u64 limbs per value, least significant
@@ -137,6 +138,16 @@ int zipgpu_data_read_layers(const zipgpu_data *data, size_t row_begin, size_t ro
  *   col_values_out: num_cols * num_rows * out_limbs u64;  paths_out: num_cols * num_rows * depth * 32 bytes */
 int zipgpu_data_open_columns(const zipgpu_data *data, size_t num_cols, const uint32_t *columns,
                              uint64_t *col_values_out, uint8_t *paths_out);
+
+/* Proximity-test row combination (open_z.rs:100-113; zip/utils.rs:94-127): combined[col] = sum_i coeffs[i] *
+ * evals[i*row_len + col], exact signed integer arithmetic, every operand expanded to out_limbs limbs as
+ * `expand::<N, M>` does (zip/utils.rs:129-137).  Int<1> operands only (in_limbs == 1); out_limbs >= 3.
+ *   coeffs: num_rows u64 (two's complement);  combined_out: row_len * out_limbs u64.
+ * zipgpu_data_combine_rows works on the evaluations kept behind a zipgpu_commit_resident handle (host coeffs in,
+ * host row out); the _device form takes device pointers (scratch is taken from the context's allocator). */
+int zipgpu_data_combine_rows(const zipgpu_data *data, const uint64_t *coeffs, int out_limbs, uint64_t *combined_out);
+int zipgpu_combine_rows_device(zipgpu_ctx *ctx, size_t num_rows, size_t row_len, const uint64_t *d_evals,
+                               const uint64_t *d_coeffs, int out_limbs, uint64_t *d_combined_out, void *stream);
 
 /* ---- measurement helpers (used by bench.py; no reference counterpart) -------------------------------- */
 /* When enabled, every commit/encode/merkle call records CUDA events around its kernels on the launch stream. */

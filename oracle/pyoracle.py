@@ -201,6 +201,20 @@ def encode_rows(evals: list[int], num_rows: int, row_len: int, rep: int, perm1, 
 # ----------------------------------------------------------------------------------------------
 # MerkleTree (pcs/utils.rs:66-118)
 # ----------------------------------------------------------------------------------------------
+def combine_rows(coeffs: list[int], evals: list[int], row_len: int, out_limbs: int) -> list[int]:
+    """zip/utils.rs:94-127 as used by the proximity test (open_z.rs:100-113): combined[col] = sum_i coeff_i *
+    evals[i*row_len + col] in M = Int<out_limbs> after `expand` (zip/utils.rs:129-137).  crypto-bigint's checked
+    mul/add would panic on overflow; `to_words` asserts the same range."""
+    out = []
+    for col in range(row_len):
+        acc = 0
+        for i, c in enumerate(coeffs):
+            acc += c * evals[i * row_len + col]
+        to_words(acc, out_limbs)  # range check
+        out.append(acc)
+    return out
+
+
 def merkle_tree(depth: int, leaves: list[int], leaf_limbs: int):
     """returns (root: bytes, layers: list[bytes]) with layers laid out as in utils.rs:77-85"""
     import blake3

@@ -1,0 +1,130 @@
+"""GPU parity at BASELINE.json's sizes and configs: nv = 20..24 commits against the multithreaded C oracle, the batched
+64 x 2^18 config, prover-flow shapes with live-transcript-like seeds, and the proximity-test row combination."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import I64_MAX, I64_MIN, KECCAK_SEEDS, shape_for
+
+pytestmark = pytest.mark.gpu
+
+
+def _code(nv, seeds, oracle):
+    from zinc_b200 import RaaCode, ZipTypes
+
+    row_len, num_rows, cw = shape_for(nv)
+    p1, p2 = oracle.perm_from_seed(cw, seeds[0]), oracle.perm_from_seed(cw, seeds[1])
+    return RaaCode.with_permutations(ZipTypes(), row_len, 2, p1, p2), row_len, num_rows, cw, p1, p2
+
+
+@pytest.mark.parametrize("nv", [22, 24])
+def test_commit_resident_full_size_matches_oracle(nv, oracle, ctx):
+    """BASELINE configs[1..2] shape rule at nv = 22 / 24: every root, plus the codewords and layers of sampled row
+    ranges read back from the device-resident prover data, bit for bit against the oracle."""
+    from zinc_b200 import DenseMultilinearExtension, MultilinearZip, MultilinearZipParams
+
+    code, row_len, num_rows, cw, p1, p2 = _code(nv, KECCAK_SEEDS, oracle)
+    pp = MultilinearZipParams.new(nv, num_rows, code)
+    evals = np.random.default_rng(0x21C0 + nv).integers(0, 1 << 64, size=1 << nv, dtype=np.uint64)
+    poly = DenseMultilinearExtension.from_evaluations_vec(nv, evals)
+    res, comm = MultilinearZip.commit_resident(pp, poly, ctx)
+    rc, _, _, roots = oracle.commit_mt(evals, num_rows, row_len, 2, 0, 0, p1, p2, threads=16, faithful=False,
+                                       want_rows=False, want_layers=False)
+    assert rc == 0
+    assert b"".join(comm.roots) == roots.tobytes(), "roots differ"
+    per = (2 * cw - 2) * 32
+    for r0, n in ((0, 3), (num_rows // 2 - 1, 2), (num_rows - 2, 2)):
+        rc, rows, layers, _ = oracle.commit(evals[r0 * row_len:(r0 + n) * row_len], n, row_len, 2, p1, p2)
+        assert rc == 0
+        assert np.array_equal(res.rows(r0, n).reshape(-1), rows), f"codewords differ at rows {r0}..{r0 + n}"
+        assert np.array_equal(res.layers(r0, n).reshape(-1), layers), f"layers differ at rows {r0}..{r0 + n}"
+    res.free()
+
+
+def test_commit_linearity_at_scale(oracle, ctx):
+    """commit.rs:559-583 at nv = 20: encode(3*r1 + 5*r2) == 3*encode(r1) + 5*encode(r2), checked on sampled entries
+    with Python integers (a size-independent property of the linear code)"""
+    from oracle import pyoracle as po
+    from zinc_b200 import DenseMultilinearExtension, MultilinearZip, MultilinearZipParams
+
+    nv = 20
+    code, row_len, num_rows, cw, p1, p2 = _code(nv, KECCAK_SEEDS, oracle)
+    pp = MultilinearZipParams.new(nv, num_rows, code)
+    rng = np.random.default_rng(5)
+    a = rng.integers(-(1 << 59), 1 << 59, size=1 << nv, dtype=np.int64)
+    b = rng.integers(-(1 << 59), 1 << 59, size=1 << nv, dtype=np.int64)
+    enc = lambda v: MultilinearZip.commit_no_merkle(pp, DenseMultilinearExtension.from_evaluations_vec(nv, v), ctx)[0].rows
+    ra, rb, rc_ = enc(a), enc(b), enc(3 * a + 5 * b)
+    idx = rng.integers(0, num_rows * cw, size=2000)
+    for i in idx:
+        va, vb, vc = (po.to_signed([int(w) for w in r[i]]) for r in (ra, rb, rc_))
+        assert vc == 3 * va + 5 * vb
+
+
+def test_batched_commit_64_polys_nv18(oracle, ctx):
+    """BASELINE configs[3]: 64 independent 2^18 MLEs sharing one pp (commit.rs:134-142), roots only, one submission"""
+    from zinc_b200 import _native as nat
+
+    nv, k = 18, 64
+    code, row_len, num_rows, cw, p1, p2 = _code(nv, KECCAK_SEEDS, oracle)
+    h = code.native(ctx, 1, 4)
+    rng = np.random.default_rng(18)
+    evals = [rng.integers(0, 1 << 64, size=1 << nv, dtype=np.uint64) for _ in range(k)]
+    roots = [np.zeros(num_rows * 32, dtype=np.uint8) for _ in range(k)]
+    arr = lambda xs: (C.c_void_p * k)(*[nat.ptr(x) for x in xs])
+    nat.check(nat.lib().zipgpu_batch_commit(h, k, num_rows, arr(evals), None, None, arr(roots)))
+    for p in range(k):
+        rc, _, _, exp = oracle.commit_mt(evals[p], num_rows, row_len, 2, 0, 0, p1, p2, threads=16, faithful=False,
+                                         want_rows=False, want_layers=False)
+        assert rc == 0 and np.array_equal(roots[p], exp), f"poly {p}"
+
+
+@pytest.mark.parametrize("nv", [3, 12, 13, 14, 15, 16])
+def test_prover_flow_shapes_with_live_seeds(nv, oracle, ctx):
+    """BASELINE configs[4]: the commit inside Prover::prove (zinc/prover.rs:305-328) draws its seeds from the live
+    Fiat-Shamir transcript, so they differ per proof: arbitrary 64-bit seeds, z-vector sizes 2^12..2^16 and the
+    8-entry z of examples/simple_r1cs.rs."""
+    from zinc_b200 import DenseMultilinearExtension, MultilinearZip, MultilinearZipParams
+
+    rng = np.random.default_rng(1000 + nv)
+    seeds = tuple(int(x) for x in rng.integers(0, 1 << 64, size=2, dtype=np.uint64))
+    code, row_len, num_rows, cw, p1, p2 = _code(nv, seeds, oracle)
+    pp = MultilinearZipParams.new(nv, num_rows, code)
+    evals = rng.integers(0, 1 << 64, size=1 << nv, dtype=np.uint64)
+    data, comm = MultilinearZip.commit(pp, DenseMultilinearExtension.from_evaluations_vec(nv, evals), ctx)
+    rc, rows, layers, roots = oracle.commit(evals, num_rows, row_len, 2, p1, p2)
+    assert rc == 0 and np.array_equal(data.rows.reshape(-1), rows)
+    assert np.array_equal(np.concatenate([t.layers.reshape(-1) for t in data.rows_merkle_trees]), layers)
+    assert b"".join(comm.roots) == roots.tobytes()
+
+
+@pytest.mark.parametrize("nv", [4, 9, 12, 16])
+def test_combine_rows_matches_bigint(nv, oracle, ctx):
+    """open_z.rs:100-113 / zip/utils.rs:94-127: u' = sum_i coeff_i * row_i in Int<8>, against Python integers"""
+    from oracle import pyoracle as po
+    from zinc_b200 import DenseMultilinearExtension, MultilinearZip, MultilinearZipParams
+
+    code, row_len, num_rows, cw, p1, p2 = _code(nv, KECCAK_SEEDS, oracle)
+    pp = MultilinearZipParams.new(nv, num_rows, code)
+    rng = np.random.default_rng(77 + nv)
+    for case in ("random", "extremes"):
+        if case == "random":
+            ev = rng.integers(I64_MIN, I64_MAX, size=1 << nv, dtype=np.int64, endpoint=True)
+            co = rng.integers(I64_MIN, I64_MAX, size=num_rows, dtype=np.int64, endpoint=True)
+        else:  # |sum| as large as it gets: i64::MIN * i64::MIN in every term, and alternating signs
+            ev = np.full(1 << nv, I64_MIN, dtype=np.int64)
+            ev[1::3] = I64_MAX
+            co = np.full(num_rows, I64_MIN, dtype=np.int64)
+            co[::2] = I64_MAX if nv % 2 else I64_MIN
+        res, _ = MultilinearZip.commit_resident(pp, DenseMultilinearExtension.from_evaluations_vec(nv, ev), ctx)
+        got = res.combine_rows(co, 8)
+        exp = po.combine_rows([int(c) for c in co], [int(e) for e in ev], row_len, 8)
+        assert [po.to_signed([int(w) for w in g]) for g in got] == exp, f"nv={nv} {case}"
+        res.free()
+
+
+def test_combine_rows_rejects_narrow_output(ctx):
+    from zinc_b200 import _native as nat
+
+    assert nat.lib().zipgpu_combine_rows_device(ctx.handle, 4, 4, 1, 1, 2, 1, None) == nat.ERR_WIDTH

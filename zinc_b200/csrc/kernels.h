@@ -55,6 +55,18 @@ struct OpenArgs {
 };
 cudaError_t launch_open_columns(const OpenArgs &a);
 
+// ---- K5: proximity-test row combination (combine_rows.cu) ----
+struct CombineArgs {
+    const uint64_t *evals;   // [num_rows][row_len] Int<1> (two's complement u64)
+    const uint64_t *coeffs;  // device [num_rows] Int<1>
+    uint64_t *scratch;       // combine_rows_scratch_bytes()
+    uint64_t *out;           // [row_len][out_limbs]
+    uint32_t num_rows, row_len, out_limbs;
+    cudaStream_t stream;
+};
+size_t combine_rows_scratch_bytes(uint32_t num_rows, uint32_t row_len);
+cudaError_t launch_combine_rows(const CombineArgs &a, int *launches);
+
 // ---- INT32 micro-benchmark (microbench.cu) ----
 cudaError_t launch_microbench_int32(int kind, int iters, int num_sms, cudaStream_t stream, uint32_t *d_sink,
                                     double *lane_ops);

@@ -77,8 +77,9 @@ struct zipgpu_code {
 
 struct zipgpu_data {
     zipgpu_ctx *ctx;
-    size_t num_rows, cw;
-    int out_limbs, depth;
+    size_t num_rows, cw, row_len;
+    int in_limbs, out_limbs, depth;
+    uint64_t *d_evals;  // the unencoded evaluations (the proximity test combines them, open_z.rs:100-113)
     uint64_t *d_rows;
     uint8_t *d_layers;
     uint8_t *d_roots;
@@ -680,7 +681,7 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
     if ((e = chain(ctx, ctx->d2h, s)) != cudaSuccess) return cuda_fail(e, "chain");
     if ((e = chain(ctx, ctx->h2d, s)) != cudaSuccess) return cuda_fail(e, "chain");
     const double t_enq = now();
-    DEV_FREE(ctx, d_evals, s);
+    if (!job.keep) DEV_FREE(ctx, d_evals, s);
     if (trace) fprintf(stderr, "[zipgpu] host job: alloc %.3f ms, enqueue %.3f ms\n", t_alloc - t_begin, t_enq - t_alloc);
     if (job.keep) {
         zipgpu_data *d = new (std::nothrow) zipgpu_data();
@@ -688,6 +689,9 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
         d->ctx = ctx;
         d->num_rows = num_rows;
         d->cw = code->cw;
+        d->row_len = code->row_len;
+        d->in_limbs = code->in_limbs;
+        d->d_evals = d_evals;
         d->out_limbs = code->out_limbs;
         d->depth = code->depth;
         d->d_rows = d_rows;
@@ -846,6 +850,7 @@ extern "C" void zipgpu_data_free(zipgpu_data *d) {
     if (!d) return;
     cudaSetDevice(d->ctx->device);
     cudaStream_t s = d->ctx->stream;
+    dev_free(d->ctx, d->d_evals, s);
     dev_free(d->ctx, d->d_rows, s);
     dev_free(d->ctx, d->d_layers, s);
     dev_free(d->ctx, d->d_roots, s);
@@ -919,6 +924,54 @@ extern "C" int zipgpu_data_open_columns(const zipgpu_data *d, size_t num_cols, c
     DEV_FREE(ctx, d_paths, s);
     CU(cudaStreamSynchronize(s));
     return ZIPGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// proximity-test row combination
+// ------------------------------------------------------------------------------------------------------
+extern "C" int zipgpu_combine_rows_device(zipgpu_ctx *ctx, size_t num_rows, size_t row_len, const uint64_t *d_evals,
+                                          const uint64_t *d_coeffs, int out_limbs, uint64_t *d_out, void *stream) {
+    if (!ctx || (num_rows && row_len && (!d_evals || !d_coeffs || !d_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (out_limbs < 3) return fail(ZIPGPU_ERR_WIDTH, "combine_rows needs out_limbs >= 3 (products of Int<1> are 128 bits wide)");
+    if (num_rows > 0xffffffffull || row_len > 0xffffffffull) return fail(ZIPGPU_ERR_UNSUPPORTED, "shape too large");
+    if (num_rows == 0 || row_len == 0) return ZIPGPU_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    uint64_t *scratch = nullptr;
+    DEV_ALLOC(ctx, &scratch, combine_rows_scratch_bytes((uint32_t)num_rows, (uint32_t)row_len), s);
+    CombineArgs a;
+    a.evals = d_evals;
+    a.coeffs = d_coeffs;
+    a.scratch = scratch;
+    a.out = d_out;
+    a.num_rows = (uint32_t)num_rows;
+    a.row_len = (uint32_t)row_len;
+    a.out_limbs = (uint32_t)out_limbs;
+    a.stream = s;
+    int n = 0;
+    cudaError_t e = launch_combine_rows(a, &n);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_combine_rows");
+    ctx->launches += (uint64_t)n;
+    DEV_FREE(ctx, scratch, s);
+    return ZIPGPU_OK;
+}
+
+extern "C" int zipgpu_data_combine_rows(const zipgpu_data *d, const uint64_t *coeffs, int out_limbs, uint64_t *combined_out) {
+    if (!d || !coeffs || !combined_out) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (d->in_limbs != 1) return fail(ZIPGPU_ERR_UNSUPPORTED, "combine_rows is implemented for Int<1> evaluations");
+    zipgpu_ctx *ctx = d->ctx;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    uint64_t *d_coeffs = nullptr, *d_out = nullptr;
+    DEV_ALLOC(ctx, &d_coeffs, d->num_rows * 8, s);
+    DEV_ALLOC(ctx, &d_out, d->row_len * (size_t)out_limbs * 8, s);
+    CU(cudaMemcpyAsync(d_coeffs, coeffs, d->num_rows * 8, cudaMemcpyHostToDevice, s));
+    int rc = zipgpu_combine_rows_device(ctx, d->num_rows, d->row_len, d->d_evals, d_coeffs, out_limbs, d_out, s);
+    if (rc == 0) CU(cudaMemcpyAsync(combined_out, d_out, d->row_len * (size_t)out_limbs * 8, cudaMemcpyDeviceToHost, s));
+    DEV_FREE(ctx, d_coeffs, s);
+    DEV_FREE(ctx, d_out, s);
+    CU(cudaStreamSynchronize(s));
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -337,8 +337,9 @@ class MultilinearZipCommitment:
 class ResidentZipData:
     """Device-resident MultilinearZipData (rows + layers stay in HBM for `open`); see zipgpu_commit_resident."""
 
-    def __init__(self, handle: C.c_void_p, num_rows: int, cw: int, out_limbs: int, depth: int):
+    def __init__(self, handle: C.c_void_p, num_rows: int, cw: int, out_limbs: int, depth: int, row_len: int):
         self.handle, self.num_rows, self.cw, self.out_limbs, self.depth = handle, num_rows, cw, out_limbs, depth
+        self.row_len = row_len
 
     def rows(self, row_begin: int = 0, row_count: int | None = None) -> np.ndarray:
         row_count = self.num_rows - row_begin if row_count is None else row_count
@@ -360,6 +361,16 @@ class ResidentZipData:
         nat.check(nat.lib().zipgpu_data_open_columns(self.handle, cols.size, nat.ptr(cols), nat.ptr(vals),
                                                      nat.ptr(paths) if paths.size else None))
         return vals, paths
+
+    def combine_rows(self, coeffs, out_limbs: int = 8) -> np.ndarray:
+        """open_z.rs:100-113 / zip/utils.rs:94-127: u' = sum_i coeffs[i] * row_i over the unencoded evaluations,
+        operands expanded N -> M; -> [row_len, out_limbs] uint64"""
+        c = as_limbs(coeffs, 1).reshape(-1)
+        assert c.size == self.num_rows, "one coefficient per row"
+        row_len = self.row_len
+        out = np.empty((row_len, out_limbs), dtype=np.uint64)
+        nat.check(nat.lib().zipgpu_data_combine_rows(self.handle, nat.ptr(c), out_limbs, nat.ptr(out)))
+        return out
 
     def free(self) -> None:
         if self.handle:
@@ -489,5 +500,5 @@ class MultilinearZip:
         h = C.c_void_p()
         nat.check(nat.lib().zipgpu_commit_resident(lc.native(ctx, zt.N, zt.K), pp.num_rows, nat.ptr(ev),
                                                    nat.ptr(roots), C.byref(h)))
-        return (ResidentZipData(h, pp.num_rows, cw, zt.K, depth),
+        return (ResidentZipData(h, pp.num_rows, cw, zt.K, depth, lc.row_len()),
                 MultilinearZipCommitment([roots[i].tobytes() for i in range(pp.num_rows)]))
