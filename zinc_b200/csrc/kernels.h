@@ -20,7 +20,7 @@ struct EncodeArgs {
 };
 size_t encode_perm_padded_len(uint32_t cw);
 void build_encode_tables(const uint32_t *perm1, const uint32_t *perm2, uint32_t row_len, uint32_t cw, int in_limbs,
-                         uint16_t *tab1, uint16_t *tab2, uint8_t *colw);
+                         int out_limbs, uint16_t *tab1, uint16_t *tab2, uint8_t *colw);
 int encode_compute_limbs(int in_limbs, uint32_t cw);
 bool encode_supported(int in_limbs, uint32_t cw, uint32_t row_len);
 cudaError_t launch_raa_encode(const EncodeArgs &a);

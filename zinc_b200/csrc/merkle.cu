@@ -64,8 +64,8 @@ __device__ __forceinline__ void load_leaf(const uint32_t *p, uint32_t (&x)[LEAF3
 
 // LEAF32 > 0: inputs are raw leaves (LEAF32 u32 words each), level_in must be 0 and level-0 digests are produced.
 // LEAF32 == 0: inputs are the digests of level `level_in`, already in `layers`.
-template <int LEAF32, int H>
-__global__ void __launch_bounds__(128)
+template <int LEAF32, int H, int MINB>
+__global__ void __launch_bounds__(128, MINB)
     merkle_subtree_kernel(const uint32_t *__restrict__ leaves, uint8_t *layers, uint8_t *roots, uint32_t num_rows,
                           TreeGeom g, uint32_t level_in, uint32_t one) {
     const uint32_t chunks_per_row = (g.cw >> level_in) >> H;
@@ -112,14 +112,16 @@ __global__ void __launch_bounds__(128)
     }
 }
 
-template <int LEAF32, int H>
+// MINB = 5: ptxas then keeps the whole working set in 92 registers without spills; measured on B200 the leaf pass
+// runs 2 % faster at 5 resident blocks/SM than squeezed into 80 registers for 6 (1.837 vs 1.880 ms at nv = 24)
+template <int LEAF32, int H, int MINB = 5>
 cudaError_t launch_pass(const MerkleArgs &a, const TreeGeom &g, uint32_t level_in) {
     const size_t threads = (size_t)a.num_rows * ((g.cw >> level_in) >> H);
     const uint32_t block = 128;
     const size_t grid = (threads + block - 1) / block;
     if (grid == 0) return cudaSuccess;
     if (grid > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    merkle_subtree_kernel<LEAF32, H><<<(uint32_t)grid, block, 0, a.stream>>>(a.leaves, a.layers, a.roots, a.num_rows,
+    merkle_subtree_kernel<LEAF32, H, MINB><<<(uint32_t)grid, block, 0, a.stream>>>(a.leaves, a.layers, a.roots, a.num_rows,
                                                                            g, level_in, 1u);
     return cudaGetLastError();
 }

@@ -22,6 +22,7 @@
 //   * s2 uses a thread-striped XOR-swizzled layout slot(t,k) = k*T + (t ^ (k << log2(32/E))) which is
 //     conflict free for the owner-thread writes and for the coalesced read-out (consecutive i = t*E + k), so
 //     that consecutive lanes store consecutive 32-byte Int<4> values with one 256-bit store each.
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -174,10 +175,36 @@ __device__ __forceinline__ void stage_row(const uint32_t *src, uint32_t *stage, 
     }
 }
 
+// EXACT shapes: every warp stages ITS OWN 1/nwarps of the input row into ITS OWN plane slots (the slots whose s2
+// entries it alone reads back in the write-out), so staging the next row needs no CTA-wide barrier after the
+// write-out: linear word x of the warp's chunk -> row r = x / 32 of the warp's 32-word slot rows, column x % 32;
+// slot row r lives in plane r / E at k = r % E.  build_encode_tables emits tab1 in the same layout.
+template <int IN32, int E>
+struct WarpStage {
+    static constexpr int WPL = E * IN32 / 2;  // words per lane
+    static constexpr int NV = WPL / 4 > 0 ? WPL / 4 : 1;
+    uint4 v[NV];
+    __device__ __forceinline__ void load(const uint32_t *row_src, uint32_t t) {
+        static_assert(WPL % 4 == 0, "warp staging moves 16-byte vectors");
+        const uint32_t w = t >> 5, L = t & 31u;
+        const uint4 *src = reinterpret_cast<const uint4 *>(row_src + (size_t)w * (32 * WPL));
+#pragma unroll
+        for (int j = 0; j < WPL / 4; j++) v[j] = ld_stream_v4(src + j * 32 + L);
+    }
+    __device__ __forceinline__ void store(uint32_t *stage, uint32_t P, uint32_t T, uint32_t t) const {
+        const uint32_t w = t >> 5, L = t & 31u;
+#pragma unroll
+        for (int j = 0; j < WPL / 4; j++) {
+            const uint32_t r = 4 * j + (L >> 3), col = (L & 7u) * 4;
+            *reinterpret_cast<uint4 *>(stage + (r / E) * P + (r % E) * T + 32 * w + col) = v[j];
+        }
+    }
+};
+
 // IN32 : u32 words per input value          W    : u32 limbs carried through the scans
 // E    : codeword positions per thread      OUT32: u32 words per output value (0 = run-time `out32`)
 // CACHE: the three tables stay in registers for every row of this persistent CTA (E <= 8)
-// EXACT: cw == T*E: no padding predicates
+// EXACT: cw == T*E, rep == 2, E*IN32 >= 8: no padding predicates; warp-local staging and write-out (see above)
 template <int IN32, int W, int E, int OUT32, bool CACHE, bool EXACT, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
     raa_encode_kernel(const uint32_t *__restrict__ evals, uint32_t *__restrict__ rows_out,
@@ -208,7 +235,15 @@ __global__ void __launch_bounds__(MAXT, MINB)
 
     // ---- prologue: stage the first row ----
     uint32_t row = blockIdx.x;
-    if (row < num_rows) stage_row(evals + (size_t)row * in_words, stage, in_words, t, T);
+    if (row < num_rows) {
+        if constexpr (EXACT) {
+            WarpStage<IN32, E> ws;
+            ws.load(evals + (size_t)row * in_words, t);
+            ws.store(stage, P, T, t);
+        } else {
+            stage_row(evals + (size_t)row * in_words, stage, in_words, t, T);
+        }
+    }
     __syncthreads();
 
     for (; row < num_rows; row += gridDim.x) {
@@ -274,7 +309,9 @@ __global__ void __launch_bounds__(MAXT, MINB)
 #pragma unroll
             for (int w = 0; w < W; w++) planes[w * P + s] = v[k][w];
         }
-        __syncthreads();
+        // EXACT: a warp reads back only what it wrote itself
+        if constexpr (EXACT) __syncwarp();
+        else __syncthreads();
 
         const uint32_t next = row + gridDim.x;
         if constexpr (!CACHE) T16::load(tab1, t, T, c1);  // for the next row; in flight during the write-out
@@ -285,7 +322,8 @@ __global__ void __launch_bounds__(MAXT, MINB)
         uint32_t *dst_row = rows_out + (size_t)row * cw * out32;
 #pragma unroll
         for (int it = 0; it < E; it++) {
-            const uint32_t i = it * T + t;
+            // EXACT: warp w writes out positions [w*32E, (w+1)*32E), 32 consecutive ones per step
+            const uint32_t i = EXACT ? ((t >> 5) * (32 * E) + it * 32 + (t & 31u)) : (it * T + t);
             if (EXACT || i < cw) {
                 const uint32_t s = slot_of<E>(i / E, i % E, T);
                 uint32_t val[W];
@@ -329,10 +367,19 @@ __global__ void __launch_bounds__(MAXT, MINB)
                 }
             }
         }
-        __syncthreads();  // the planes are reused as the next row's stage
-
-        // ---- 6. stage the next row (its lines were pulled into L2 a row-time ago) ----
-        if (next < num_rows) stage_row(evals + (size_t)next * in_words, stage, in_words, t, T);
+        // ---- 6. stage the next row (its lines were pulled into L2 a row-time ago); the planes are reused ----
+        if constexpr (EXACT) {
+            __syncwarp();  // this warp's slots are free once IT has written its share out
+            // (issuing these loads before the write-out was measured slower: the 16 extra live registers spill)
+            if (next < num_rows) {
+                WarpStage<IN32, E> ws;
+                ws.load(evals + (size_t)next * in_words, t);
+                ws.store(stage, P, T, t);
+            }
+        } else {
+            __syncthreads();
+            if (next < num_rows) stage_row(evals + (size_t)next * in_words, stage, in_words, t, T);
+        }
         __syncthreads();
     }
 }
@@ -360,8 +407,10 @@ EncodeCfg pick_cfg(uint32_t cw) {
     return c;
 }
 
-bool cfg_exact(const EncodeCfg &c, uint32_t row_len, uint32_t cw) {
-    return (uint32_t)c.T * (uint32_t)c.E == cw && 2 * row_len == cw;
+// the fast variant (and its table layout): exact power-of-two shape, rep = 2, ZipTypes' K = 4N output width
+bool cfg_exact(const EncodeCfg &c, uint32_t row_len, uint32_t cw, int in_limbs, uint32_t out32) {
+    return (uint32_t)c.T * (uint32_t)c.E == cw && 2 * row_len == cw && (c.E * in_limbs * 2) % 8 == 0 &&
+           out32 == 8u * (uint32_t)in_limbs;
 }
 
 template <int IN32, int W, int E, int OUT32, bool CACHE, bool EXACT, int MAXT, int MINB>
@@ -373,6 +422,8 @@ cudaError_t launch_one(const EncodeArgs &a, int T, size_t smem) {
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem);
     if (err != cudaSuccess) return err;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
+    static const int env_occ = getenv("ZIPGPU_ENC_CTAS_PER_SM") ? atoi(getenv("ZIPGPU_ENC_CTAS_PER_SM")) : 0;  // tuning knob
+    if (env_occ > 0 && env_occ < occ) occ = env_occ;
     uint32_t grid = (uint32_t)a.num_sms * (uint32_t)occ;
     if (grid > a.num_rows) grid = a.num_rows;
     kern<<<grid, T, smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows, a.row_len, a.cw,
@@ -380,16 +431,23 @@ cudaError_t launch_one(const EncodeArgs &a, int T, size_t smem) {
     return cudaGetLastError();
 }
 
+// EXACT variants only exist where a lane's share of the input row is whole 16-byte vectors (cfg_exact checks it)
+template <int IN32, int W, int E, int OUT32, bool CACHE, bool EXACT, int MAXT, int MINB>
+cudaError_t launch_if_valid(const EncodeArgs &a, int T, size_t smem) {
+    if constexpr (EXACT && (E * IN32) % 8 != 0) return cudaErrorInvalidConfiguration;
+    else return launch_one<IN32, W, E, OUT32, CACHE, EXACT, MAXT, MINB>(a, T, smem);
+}
+
 template <int IN32, int W, int OUT32, bool EXACT>
 cudaError_t launch_e(const EncodeArgs &a, const EncodeCfg &c, size_t smem) {
     switch (c.E) {
         case 16:
-            if (c.T <= 512) return launch_one<IN32, W, 16, OUT32, false, EXACT, 512, 2>(a, c.T, smem);
-            return launch_one<IN32, W, 16, OUT32, false, EXACT, 1024, 1>(a, c.T, smem);
-        case 8: return launch_one<IN32, W, 8, OUT32, true, EXACT, 512, 2>(a, c.T, smem);
-        case 4: return launch_one<IN32, W, 4, OUT32, true, EXACT, 512, 2>(a, c.T, smem);
-        case 2: return launch_one<IN32, W, 2, OUT32, true, EXACT, 512, 2>(a, c.T, smem);
-        default: return launch_one<IN32, W, 1, OUT32, true, EXACT, 512, 2>(a, c.T, smem);
+            if (c.T <= 512) return launch_if_valid<IN32, W, 16, OUT32, false, EXACT, 512, 2>(a, c.T, smem);
+            return launch_if_valid<IN32, W, 16, OUT32, false, EXACT, 1024, 1>(a, c.T, smem);
+        case 8: return launch_if_valid<IN32, W, 8, OUT32, true, EXACT, 512, 2>(a, c.T, smem);
+        case 4: return launch_if_valid<IN32, W, 4, OUT32, true, EXACT, 512, 2>(a, c.T, smem);
+        case 2: return launch_if_valid<IN32, W, 2, OUT32, true, EXACT, 512, 2>(a, c.T, smem);
+        default: return launch_if_valid<IN32, W, 1, OUT32, true, EXACT, 512, 2>(a, c.T, smem);
     }
 }
 
@@ -399,13 +457,13 @@ cudaError_t launch_w(const EncodeArgs &a) {
     const size_t P = (size_t)c.T * c.E;
     const size_t smem = (W * P + 64 * W) * sizeof(uint32_t);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    const bool exact = cfg_exact(c, a.row_len, a.cw);
+    const bool exact = cfg_exact(c, a.row_len, a.cw, a.in_limbs, a.out32);
 #ifdef ZIPGPU_DEV_HOT_ONLY  // development builds: only the nv=24 instantiation (fast ptxas -v iterations)
     return launch_one<2, 3, 16, 8, false, true, 512, 2>(a, c.T, smem);
 #else
     // the hot instantiations (ZipTypes K = 4N limbs, exact power-of-two shapes) get a compile-time output width,
     // no padding predicates and the register prefetch of the next row
-    if (exact && a.out32 == 4 * IN32) return launch_e<IN32, W, 4 * IN32, true>(a, c, smem);
+    if (exact) return launch_e<IN32, W, 4 * IN32, true>(a, c, smem);
     return launch_e<IN32, W, 0, false>(a, c, smem);
 #endif
 }
@@ -466,10 +524,19 @@ size_t encode_perm_padded_len(uint32_t cw) {
 }
 
 // host side, once per pp: translate the two gather permutations into the kernel's tables
-void build_encode_tables(const uint32_t *perm1, const uint32_t *perm2, uint32_t row_len, uint32_t cw, int /*in_limbs*/,
-                         uint16_t *tab1, uint16_t *tab2, uint8_t *colw) {
+void build_encode_tables(const uint32_t *perm1, const uint32_t *perm2, uint32_t row_len, uint32_t cw, int in_limbs,
+                         int out_limbs, uint16_t *tab1, uint16_t *tab2, uint8_t *colw) {
     const EncodeCfg c = pick_cfg(cw);
     const uint32_t E = (uint32_t)c.E, T = (uint32_t)c.T, P = T * E;
+    const uint32_t in32 = (uint32_t)in_limbs * 2;
+    const bool exact = cfg_exact(c, row_len, cw, in_limbs, (uint32_t)out_limbs * 2);
+    // where input element e sits in the stage, in units of one element (kernel: word offset = tab1 * IN32)
+    auto stage_unit = [&](uint32_t e) -> uint32_t {
+        if (!exact) return e;  // linear
+        const uint32_t per_warp = 16 * E, epr = 32 / in32;  // elements per warp / per 32-word slot row
+        const uint32_t w = e / per_warp, m = e % per_warp, r = m / epr, q = m % epr;
+        return ((r / E) * P + (r % E) * T + 32 * w + in32 * q) / in32;
+    };
     auto at16 = [&](uint32_t t, uint32_t k) -> size_t {
         const uint32_t G = E < 8 ? E : 8;
         return ((size_t)(k / G) * T + t) * G + (k % G);
@@ -512,7 +579,7 @@ void build_encode_tables(const uint32_t *perm1, const uint32_t *perm2, uint32_t 
         for (uint32_t k = 0; k < E; k++) {
             const uint32_t i = t * E + k;
             if (i < cw) {
-                tab1[at16(t, k)] = (uint16_t)(perm1[i] % row_len);
+                tab1[at16(t, k)] = (uint16_t)stage_unit(perm1[i] % row_len);
                 tab2[at16(t, k)] = (uint16_t)addr1(perm2[i]);
             } else {
                 tab1[at16(t, k)] = 0;

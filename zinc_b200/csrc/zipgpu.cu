@@ -381,7 +381,7 @@ extern "C" int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t rep, i
     // the kernel consumes pre-translated, lane-major tables (raa_encode.cu), not the raw permutations
     std::vector<uint16_t> t1(padded, 0), t2(padded, 0);
     std::vector<uint8_t> cl(padded, 0);
-    build_encode_tables(perm1, perm2, (uint32_t)row_len, (uint32_t)cw, in_limbs, t1.data(), t2.data(), cl.data());
+    build_encode_tables(perm1, perm2, (uint32_t)row_len, (uint32_t)cw, in_limbs, out_limbs, t1.data(), t2.data(), cl.data());
     CU(cudaMemcpy(c->d_tab1, t1.data(), padded * 2, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_tab2, t2.data(), padded * 2, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_colw, cl.data(), padded, cudaMemcpyHostToDevice));
