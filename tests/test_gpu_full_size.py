@@ -128,3 +128,55 @@ def test_combine_rows_rejects_narrow_output(ctx):
     from zinc_b200 import _native as nat
 
     assert nat.lib().zipgpu_combine_rows_device(ctx.handle, 4, 4, 1, 1, 2, 1, None) == nat.ERR_WIDTH
+
+
+def _commit_device(ctx, code, num_rows, cw, evals):
+    """zipgpu_commit_device on torch device buffers -> (rows, layers, roots) as numpy"""
+    import torch
+
+    from zinc_b200 import _native as nat
+
+    depth = cw.bit_length() - 1
+    dev = torch.device("cuda", ctx.device)
+    d_ev = torch.from_numpy(evals.view(np.int64)).to(dev)
+    d_rows = torch.empty(num_rows * cw * 4, dtype=torch.int64, device=dev)
+    d_lay = torch.empty(num_rows * ((2 << depth) - 2) * 32, dtype=torch.uint8, device=dev)
+    d_roots = torch.empty(num_rows * 32, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    nat.check(nat.lib().zipgpu_commit_device(code.native(ctx, 1, 4), num_rows, d_ev.data_ptr(), d_rows.data_ptr(),
+                                             d_lay.data_ptr(), d_roots.data_ptr(), None))
+    ctx.sync()
+    return d_rows.cpu().numpy().view(np.uint64), d_lay.cpu().numpy(), d_roots.cpu().numpy()
+
+
+@pytest.mark.parametrize("nv", [16, 18, 20])
+def test_fused_commit_kernel_forced_at_small_shapes(nv, oracle, ctx, monkeypatch):
+    """the fused commit kernel (encode + leaf hashes + the lowest tree levels in one launch) for every entries-per-
+    thread variant (E = 4 at nv 16, E = 8 at nv 18/20), forced on, against the oracle and the two-kernel path"""
+    code, row_len, num_rows, cw, p1, p2 = _code(nv, KECCAK_SEEDS, oracle)
+    evals = np.random.default_rng(nv).integers(0, 1 << 64, size=1 << nv, dtype=np.uint64)
+    rc, rows, layers, roots = oracle.commit_mt(evals, num_rows, row_len, 2, 0, 0, p1, p2, threads=8, faithful=False)
+    assert rc == 0
+    monkeypatch.setenv("ZIPGPU_FUSE_MIN_ROWS", "1")
+    launches0 = ctx.launch_count
+    f_rows, f_lay, f_roots = _commit_device(ctx, code, num_rows, cw, evals)
+    fused_launches = ctx.launch_count - launches0
+    monkeypatch.setenv("ZIPGPU_NO_FUSE", "1")
+    launches0 = ctx.launch_count
+    u_rows, u_lay, u_roots = _commit_device(ctx, code, num_rows, cw, evals)
+    assert fused_launches <= ctx.launch_count - launches0  # the leaf pass is folded into the encoder launch
+    for got in ((f_rows, f_lay, f_roots), (u_rows, u_lay, u_roots)):
+        assert np.array_equal(got[0], rows) and np.array_equal(got[1], layers) and np.array_equal(got[2], roots)
+
+
+def test_fused_commit_kernel_default_at_nv22(oracle, ctx):
+    """zipgpu_commit_device takes the fused kernel by itself from 10 x SMs rows: rows, every layer and the roots"""
+    nv = 22
+    code, row_len, num_rows, cw, p1, p2 = _code(nv, KECCAK_SEEDS, oracle)
+    evals = np.random.default_rng(nv).integers(0, 1 << 64, size=1 << nv, dtype=np.uint64)
+    rc, rows, layers, roots = oracle.commit_mt(evals, num_rows, row_len, 2, 0, 0, p1, p2, threads=16, faithful=False)
+    assert rc == 0
+    g_rows, g_lay, g_roots = _commit_device(ctx, code, num_rows, cw, evals)
+    assert np.array_equal(g_roots, roots)
+    assert np.array_equal(g_rows, rows)
+    assert np.array_equal(g_lay, layers)

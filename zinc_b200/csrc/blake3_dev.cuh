@@ -110,7 +110,7 @@ __device__ __forceinline__ void hash_node(const uint32_t (&l)[8], const uint32_t
 // Out-of-line copy: the subtree kernels call this from several merge levels; keeping ONE instance of the ~700
 // instruction compression keeps the kernel inside the instruction cache (the fully inlined version stalled on
 // instruction fetch: smsp no_instruction 2.9 warps per issue, profiles/r1_hash_leaf_after_imad.txt).
-__device__ __noinline__ Digest hash_node_call(Digest l, Digest r, uint32_t one) {
+static __device__ __noinline__ Digest hash_node_call(Digest l, Digest r, uint32_t one) {
     Digest o;
     hash_node(l.w, r.w, o.w, one);
     return o;

@@ -16,8 +16,10 @@ struct EncodeArgs {
     uint32_t num_rows, row_len, cw, out32;
     int in_limbs;
     int num_sms;
+    uint8_t *fuse_layers = nullptr;  // non-NULL: the fused commit kernel also writes Merkle levels 0..encode_fused_levels()
     cudaStream_t stream;
 };
+int encode_fused_levels(int in_limbs, int out_limbs, uint32_t row_len, uint32_t cw);
 size_t encode_perm_padded_len(uint32_t cw);
 void build_encode_tables(const uint32_t *perm1, const uint32_t *perm2, uint32_t row_len, uint32_t cw, int in_limbs,
                          int out_limbs, uint16_t *tab1, uint16_t *tab2, uint8_t *colw);
@@ -38,9 +40,11 @@ struct MerkleArgs {
 bool merkle_supported(int leaf32);
 // returns the number of kernel launches through *launches
 cudaError_t launch_merkle_rows(const MerkleArgs &a, int *launches);
-// pass plan (leaf pass = pass 0) and partial execution of it, for chunked pipelines
-int merkle_pass_plan(int depth, int *level_in, int *h);
-cudaError_t launch_merkle_passes(const MerkleArgs &a, int pass_begin, int pass_end, int *launches);
+// Runs tree passes starting from level `from_level` (0 = from the raw leaves; > 0 = that level is already in `layers`)
+// until a level >= `until_level` is reached (until_level < 0: up to the roots).  *reached = the level produced last.
+// Splitting lets a chunked host pipeline run the wide bottom passes per chunk and the narrow, latency-bound top passes
+// once over all rows, and lets the fused commit kernel (raa_encode.cu) hand over at level log2(E).
+cudaError_t launch_merkle_levels(const MerkleArgs &a, int from_level, int until_level, int *reached, int *launches);
 
 // ---- K4: column openings (open_columns.cu) ----
 struct OpenArgs {

@@ -151,58 +151,44 @@ bool merkle_supported(int leaf32) {
     return leaf32 == 2 || leaf32 == 4 || leaf32 == 6 || leaf32 == 8 || leaf32 == 16;
 }
 
-// The pass plan of a depth-`depth` tree: the leaf pass covers levels 0..min(3,depth), every further pass 3 levels
-// (the last one up to 4).  Returns the number of passes; pass p consumes level level_in[p] and produces h[p] more.
-int merkle_pass_plan(int depth, int *level_in, int *h) {
-    int n = 0;
-    int hh = depth < 3 ? depth : 3;
-    level_in[n] = 0;
-    h[n] = hh;
-    n++;
-    int level = hh, remaining = depth - hh;
-    while (remaining > 0) {
-        hh = remaining <= 4 ? remaining : 3;
-        level_in[n] = level;
-        h[n] = hh;
-        n++;
-        level += hh;
-        remaining -= hh;
-    }
-    return n;
-}
-
-// Runs passes [pass_begin, pass_end) of the plan (pass_end < 0: to the end).  Splitting lets a chunked host pipeline
-// run the wide bottom passes per chunk and the narrow, latency-bound top passes once over all rows.
-cudaError_t launch_merkle_passes(const MerkleArgs &a, int pass_begin, int pass_end, int *launches) {
+cudaError_t launch_merkle_levels(const MerkleArgs &a, int from_level, int until_level, int *reached, int *launches) {
     TreeGeom g;
     g.depth = (uint32_t)a.depth;
     g.cw = 1u << a.depth;
     g.row_stride = 2 * (size_t)g.cw - 2;
-    int level_in[16], h[16];
-    const int np = merkle_pass_plan(a.depth, level_in, h);
-    if (pass_end < 0 || pass_end > np) pass_end = np;
-    int n = 0;
-    for (int p = pass_begin; p < pass_end; p++) {
-        cudaError_t err;
-        if (p == 0) {
-            switch (a.leaf32) {
-                case 2: err = launch_leaf_pass<2>(a, g, h[0]); break;
-                case 4: err = launch_leaf_pass<4>(a, g, h[0]); break;
-                case 6: err = launch_leaf_pass<6>(a, g, h[0]); break;
-                case 8: err = launch_leaf_pass<8>(a, g, h[0]); break;
-                case 16: err = launch_leaf_pass<16>(a, g, h[0]); break;
-                default: return cudaErrorInvalidValue;
-            }
-        } else {
-            err = launch_node_pass(a, g, (uint32_t)level_in[p], h[p]);
+    if (until_level < 0 || until_level > a.depth) until_level = a.depth;
+    int n = 0, level = from_level;
+    cudaError_t err = cudaSuccess;
+    if (level == 0 && (until_level > 0 || a.depth == 0)) {
+        // the leaf pass covers levels 0..min(3, depth) (15/16 of all compressions)
+        const int h = a.depth < 3 ? a.depth : 3;
+        switch (a.leaf32) {
+            case 2: err = launch_leaf_pass<2>(a, g, h); break;
+            case 4: err = launch_leaf_pass<4>(a, g, h); break;
+            case 6: err = launch_leaf_pass<6>(a, g, h); break;
+            case 8: err = launch_leaf_pass<8>(a, g, h); break;
+            case 16: err = launch_leaf_pass<16>(a, g, h); break;
+            default: return cudaErrorInvalidValue;
         }
         if (err != cudaSuccess) return err;
         n++;
+        level = h;
     }
+    while (level < until_level) {  // every further pass 3 levels, the last one up to 4
+        const int remaining = a.depth - level;
+        const int h = remaining <= 4 ? remaining : 3;
+        err = launch_node_pass(a, g, (uint32_t)level, h);
+        if (err != cudaSuccess) return err;
+        n++;
+        level += h;
+    }
+    if (reached) *reached = level;
     if (launches) *launches = n;
     return cudaSuccess;
 }
 
-cudaError_t launch_merkle_rows(const MerkleArgs &a, int *launches) { return launch_merkle_passes(a, 0, -1, launches); }
+cudaError_t launch_merkle_rows(const MerkleArgs &a, int *launches) {
+    return launch_merkle_levels(a, 0, -1, nullptr, launches);
+}
 
 }  // namespace zipgpu

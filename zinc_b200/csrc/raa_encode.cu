@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "blake3_dev.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -205,12 +206,18 @@ struct WarpStage {
 // E    : codeword positions per thread      OUT32: u32 words per output value (0 = run-time `out32`)
 // CACHE: the three tables stay in registers for every row of this persistent CTA (E <= 8)
 // EXACT: cw == T*E, rep == 2, E*IN32 >= 8: no padding predicates; warp-local staging and write-out (see above)
-template <int IN32, int W, int E, int OUT32, bool CACHE, bool EXACT, int MAXT, int MINB>
+// FUSE : (EXACT only) the commit kernel: after a row's codeword is written out, every thread BLAKE3-hashes the E
+//        entries it owns straight from shared memory and reduces them to one node of level log2(E) of the row's
+//        Merkle tree (pcs/utils.rs:87-118), writing levels 0..log2(E) to `layers`.  With two CTAs per SM one CTA's
+//        memory-bound encode phases run under the other's ALU-bound hash phase, and the codeword is never re-read
+//        from HBM.  The levels above log2(E) are left to the batched passes of merkle.cu.
+template <int IN32, int W, int E, int OUT32, bool CACHE, bool EXACT, bool FUSE, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
     raa_encode_kernel(const uint32_t *__restrict__ evals, uint32_t *__restrict__ rows_out,
                       const uint16_t *__restrict__ tab1, const uint16_t *__restrict__ tab2,
                       const uint8_t *__restrict__ colw, uint32_t num_rows, uint32_t row_len, uint32_t cw,
-                      uint32_t out32_rt) {
+                      uint32_t out32_rt, uint8_t *__restrict__ layers, uint32_t one) {
+    static_assert(!FUSE || (EXACT && OUT32 != 0), "the fused commit kernel exists for exact shapes only");
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t T = blockDim.x, t = threadIdx.x;
     const uint32_t P = T * E;   // plane size in words (>= cw)
@@ -367,6 +374,38 @@ __global__ void __launch_bounds__(MAXT, MINB)
                 }
             }
         }
+        // ---- 5b. FUSE: leaf hashes and the lowest log2(E) tree levels of the entries this thread owns ----
+        if constexpr (FUSE) {
+            constexpr int H = E >= 16 ? 4 : E >= 8 ? 3 : E >= 4 ? 2 : E >= 2 ? 1 : 0;
+            static_assert((1 << H) == E, "E is a power of two");
+            uint8_t *lay_row = layers + (size_t)row * (2 * (size_t)cw - 2) * 32;
+            b3::Digest stack[H > 0 ? H : 1];  // binary-counter stack; indexed at run time, so it lives in local memory
+#pragma unroll 1
+            for (uint32_t k = 0; k < (uint32_t)E; k++) {
+                const uint32_t s = slot_of<E>(t, k, T);
+                uint32_t x[OUT32];
+#pragma unroll
+                for (int w = 0; w < W; w++) x[w] = planes[w * P + s];
+                const uint32_t sign = (uint32_t)((int32_t)x[W - 1] >> 31);
+#pragma unroll
+                for (int w = W; w < OUT32; w++) x[w] = sign;
+                const uint32_t idx = t * E + k;  // leaf index within the row
+                b3::Digest d;
+                b3::hash_leaf<OUT32>(x, d.w, one);
+                st_global_v8(lay_row + (size_t)idx * 32, d.w);
+#pragma unroll 1
+                for (int l = 0; l < H; l++) {
+                    if ((k >> l) & 1u) {
+                        d = b3::hash_node_call(stack[l], d, one);
+                        const size_t off = 2 * (size_t)cw - ((2 * (size_t)cw) >> (l + 1));
+                        st_global_v8(lay_row + (off + (idx >> (l + 1))) * 32, d.w);
+                    } else {
+                        stack[l] = d;
+                        break;
+                    }
+                }
+            }
+        }
         // ---- 6. stage the next row (its lines were pulled into L2 a row-time ago); the planes are reused ----
         if constexpr (EXACT) {
             __syncwarp();  // this warp's slots are free once IT has written its share out
@@ -413,9 +452,9 @@ bool cfg_exact(const EncodeCfg &c, uint32_t row_len, uint32_t cw, int in_limbs, 
            out32 == 8u * (uint32_t)in_limbs;
 }
 
-template <int IN32, int W, int E, int OUT32, bool CACHE, bool EXACT, int MAXT, int MINB>
+template <int IN32, int W, int E, int OUT32, bool CACHE, bool EXACT, bool FUSE, int MAXT, int MINB>
 cudaError_t launch_one(const EncodeArgs &a, int T, size_t smem) {
-    auto kern = raa_encode_kernel<IN32, W, E, OUT32, CACHE, EXACT, MAXT, MINB>;
+    auto kern = raa_encode_kernel<IN32, W, E, OUT32, CACHE, EXACT, FUSE, MAXT, MINB>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     int occ = 0;
@@ -427,27 +466,27 @@ cudaError_t launch_one(const EncodeArgs &a, int T, size_t smem) {
     uint32_t grid = (uint32_t)a.num_sms * (uint32_t)occ;
     if (grid > a.num_rows) grid = a.num_rows;
     kern<<<grid, T, smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows, a.row_len, a.cw,
-                                      a.out32);
+                                      a.out32, a.fuse_layers, 1u);
     return cudaGetLastError();
 }
 
 // EXACT variants only exist where a lane's share of the input row is whole 16-byte vectors (cfg_exact checks it)
-template <int IN32, int W, int E, int OUT32, bool CACHE, bool EXACT, int MAXT, int MINB>
+template <int IN32, int W, int E, int OUT32, bool CACHE, bool EXACT, bool FUSE, int MAXT, int MINB>
 cudaError_t launch_if_valid(const EncodeArgs &a, int T, size_t smem) {
     if constexpr (EXACT && (E * IN32) % 8 != 0) return cudaErrorInvalidConfiguration;
-    else return launch_one<IN32, W, E, OUT32, CACHE, EXACT, MAXT, MINB>(a, T, smem);
+    else return launch_one<IN32, W, E, OUT32, CACHE, EXACT, FUSE, MAXT, MINB>(a, T, smem);
 }
 
-template <int IN32, int W, int OUT32, bool EXACT>
+template <int IN32, int W, int OUT32, bool EXACT, bool FUSE>
 cudaError_t launch_e(const EncodeArgs &a, const EncodeCfg &c, size_t smem) {
     switch (c.E) {
         case 16:
-            if (c.T <= 512) return launch_if_valid<IN32, W, 16, OUT32, false, EXACT, 512, 2>(a, c.T, smem);
-            return launch_if_valid<IN32, W, 16, OUT32, false, EXACT, 1024, 1>(a, c.T, smem);
-        case 8: return launch_if_valid<IN32, W, 8, OUT32, true, EXACT, 512, 2>(a, c.T, smem);
-        case 4: return launch_if_valid<IN32, W, 4, OUT32, true, EXACT, 512, 2>(a, c.T, smem);
-        case 2: return launch_if_valid<IN32, W, 2, OUT32, true, EXACT, 512, 2>(a, c.T, smem);
-        default: return launch_if_valid<IN32, W, 1, OUT32, true, EXACT, 512, 2>(a, c.T, smem);
+            if (c.T <= 512) return launch_if_valid<IN32, W, 16, OUT32, false, EXACT, FUSE, 512, 2>(a, c.T, smem);
+            return launch_if_valid<IN32, W, 16, OUT32, false, EXACT, FUSE, 1024, 1>(a, c.T, smem);
+        case 8: return launch_if_valid<IN32, W, 8, OUT32, true, EXACT, FUSE, 512, 2>(a, c.T, smem);
+        case 4: return launch_if_valid<IN32, W, 4, OUT32, true, EXACT, FUSE, 512, 2>(a, c.T, smem);
+        case 2: return launch_if_valid<IN32, W, 2, OUT32, true, EXACT, FUSE, 512, 2>(a, c.T, smem);
+        default: return launch_if_valid<IN32, W, 1, OUT32, true, EXACT, FUSE, 512, 2>(a, c.T, smem);
     }
 }
 
@@ -459,12 +498,17 @@ cudaError_t launch_w(const EncodeArgs &a) {
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     const bool exact = cfg_exact(c, a.row_len, a.cw, a.in_limbs, a.out32);
 #ifdef ZIPGPU_DEV_HOT_ONLY  // development builds: only the nv=24 instantiation (fast ptxas -v iterations)
-    return launch_one<2, 3, 16, 8, false, true, 512, 2>(a, c.T, smem);
+    if (a.fuse_layers) return launch_one<2, 3, 16, 8, false, true, true, 512, 2>(a, c.T, smem);
+    return launch_one<2, 3, 16, 8, false, true, false, 512, 2>(a, c.T, smem);
 #else
     // the hot instantiations (ZipTypes K = 4N limbs, exact power-of-two shapes) get a compile-time output width,
     // no padding predicates and the register prefetch of the next row
-    if (exact) return launch_e<IN32, W, 4 * IN32, true>(a, c, smem);
-    return launch_e<IN32, W, 0, false>(a, c, smem);
+    if (a.fuse_layers) {
+        if (!exact) return cudaErrorInvalidConfiguration;
+        return launch_e<IN32, W, 4 * IN32, true, true>(a, c, smem);
+    }
+    if (exact) return launch_e<IN32, W, 4 * IN32, true, false>(a, c, smem);
+    return launch_e<IN32, W, 0, false, false>(a, c, smem);
 #endif
 }
 
@@ -588,6 +632,16 @@ void build_encode_tables(const uint32_t *perm1, const uint32_t *perm2, uint32_t 
             colw[at8(t, k)] = colour[i];
         }
     }
+}
+
+// Merkle levels the fused commit kernel produces (0 = no fused variant for this shape): log2 of the entries per thread
+int encode_fused_levels(int in_limbs, int out_limbs, uint32_t row_len, uint32_t cw) {
+    const EncodeCfg c = pick_cfg(cw);
+    if (!cfg_exact(c, row_len, cw, in_limbs, (uint32_t)out_limbs * 2)) return 0;
+    if (cw & (cw - 1)) return 0;
+    int h = 0;
+    while ((1 << h) < c.E) h++;
+    return h;
 }
 
 int encode_compute_limbs(int in_limbs, uint32_t cw) {

@@ -71,6 +71,7 @@ struct zipgpu_code {
     size_t row_len, rep, cw;
     int in_limbs, out_limbs;
     int depth;  // -1 when cw is not a power of two (encode only)
+    int fused_levels;  // Merkle levels the fused commit kernel produces (0: no fused variant for this shape)
     uint16_t *d_tab1, *d_tab2;  // pre-translated gather tables (raa_encode.cu)
     uint8_t *d_colw;
 };
@@ -367,6 +368,8 @@ extern "C" int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t rep, i
     c->in_limbs = in_limbs;
     c->out_limbs = out_limbs;
     c->depth = is_pow2(cw) ? ilog2(cw) : -1;
+    c->fused_levels = c->depth > 0 ? encode_fused_levels(in_limbs, out_limbs, (uint32_t)row_len, (uint32_t)cw) : 0;
+    if (!merkle_supported(out_limbs * 2)) c->fused_levels = 0;
     const size_t padded = encode_perm_padded_len((uint32_t)cw);
     c->d_tab1 = c->d_tab2 = nullptr;
     c->d_colw = nullptr;
@@ -427,7 +430,9 @@ static int check_align16(const void *p, const char *name) {  // 32 bytes: rows, 
     return ZIPGPU_OK;
 }
 
-static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_evals, uint64_t *d_rows, cudaStream_t s) {
+// fuse_layers != NULL: the fused commit kernel (encode + Merkle levels 0..code->fused_levels into fuse_layers)
+static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_evals, uint64_t *d_rows, cudaStream_t s,
+                      uint8_t *fuse_layers = nullptr) {
     if (num_rows == 0) return ZIPGPU_OK;
     if (num_rows > 0xffffffffull) return fail(ZIPGPU_ERR_UNSUPPORTED, "too many rows");
     int rc;
@@ -444,6 +449,7 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     a.out32 = (uint32_t)code->out_limbs * 2;
     a.in_limbs = code->in_limbs;
     a.num_sms = code->ctx->num_sms;
+    a.fuse_layers = fuse_layers;
     a.stream = s;
     cudaError_t e = launch_raa_encode(a);
     if (e != cudaSuccess) return cuda_fail(e, "launch_raa_encode");
@@ -451,8 +457,11 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     return ZIPGPU_OK;
 }
 
+// tree passes from `from_level` (0 = from the raw leaves) until a level >= until_level (-1: the roots)
 static int merkle_dev(zipgpu_ctx *ctx, size_t num_rows, int depth, int leaf_limbs, const uint64_t *d_leaves,
-                      uint8_t *d_layers, uint8_t *d_roots, cudaStream_t s, int pass_begin = 0, int pass_end = -1) {
+                      uint8_t *d_layers, uint8_t *d_roots, cudaStream_t s, int from_level = 0, int until_level = -1,
+                      int *reached = nullptr) {
+    if (reached) *reached = from_level;
     if (num_rows == 0) return ZIPGPU_OK;
     if (num_rows > 0xffffffffull) return fail(ZIPGPU_ERR_UNSUPPORTED, "too many rows");
     if (depth < 0 || depth > 30) return fail(ZIPGPU_ERR_INVALID, "depth out of range");
@@ -467,27 +476,45 @@ static int merkle_dev(zipgpu_ctx *ctx, size_t num_rows, int depth, int leaf_limb
     a.leaf32 = leaf_limbs * 2;
     a.stream = s;
     int n = 0;
-    cudaError_t e = launch_merkle_passes(a, pass_begin, pass_end, &n);
-    if (e != cudaSuccess) return cuda_fail(e, "launch_merkle_passes");
+    cudaError_t e = launch_merkle_levels(a, from_level, until_level, reached, &n);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_merkle_levels");
     ctx->launches += (uint64_t)n;
     return ZIPGPU_OK;
 }
 
-// encode + merkle of a row range on stream s, with optional profiling events
+static bool fusion_enabled() {
+    return getenv("ZIPGPU_NO_FUSE") == nullptr;  // A/B knob: the two-kernel path (encode, then hash)
+}
+// rows from which commit_dev takes the fused kernel (ZIPGPU_FUSE_MIN_ROWS overrides: tests force it at small shapes)
+static size_t fuse_min_rows(const zipgpu_ctx *ctx) {
+    if (const char *env = getenv("ZIPGPU_FUSE_MIN_ROWS")) return (size_t)atol(env);
+    return (size_t)10 * ctx->num_sms;
+}
+
+// Encode + Merkle of a row range on stream s, with optional profiling events.  until_level >= 0 stops the trees at the
+// first pass boundary >= until_level (chunked pipelines finish them with merkle_top_dev); *reached reports it.
+// Exact shapes run the fused commit kernel: encode + the lowest log2(E) tree levels in one launch.
 static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_evals, uint64_t *d_rows, uint8_t *d_layers,
-                      uint8_t *d_roots, cudaStream_t s, int merkle_pass_end = -1) {
+                      uint8_t *d_roots, cudaStream_t s, int until_level = -1, int *reached = nullptr) {
     zipgpu_ctx *ctx = code->ctx;
     ProfRec r;
     const bool prof = prof_begin(ctx, &r);
     if (prof) cudaEventRecord(r.e0, s);
-    int rc = encode_dev(code, num_rows, d_evals, d_rows, s);
+    // The fused kernel is one persistent CTA pair per SM: it needs enough rows per CTA (>= 5 rounds) for the pairs to
+    // drift into complementary phases and for the row quantisation not to matter; below that the two-kernel path,
+    // whose hash passes balance at subtree granularity, is faster (measured at nv = 16, 20).
+    const bool fuse = d_roots && d_layers && code->fused_levels > 0 && code->fused_levels <= code->depth &&
+                      num_rows >= fuse_min_rows(ctx) && fusion_enabled();
+    int rc = encode_dev(code, num_rows, d_evals, d_rows, s, fuse ? d_layers : nullptr);
     if (rc) return rc;
     if (prof) {
         cudaEventRecord(r.e1, s);
         r.has_enc = true;
     }
+    if (reached) *reached = 0;
     if (d_roots) {
-        rc = merkle_dev(ctx, num_rows, code->depth, code->out_limbs, d_rows, d_layers, d_roots, s, 0, merkle_pass_end);
+        rc = merkle_dev(ctx, num_rows, code->depth, code->out_limbs, d_rows, d_layers, d_roots, s,
+                        fuse ? code->fused_levels : 0, until_level, reached);
         if (rc) return rc;
         if (prof) {
             cudaEventRecord(r.e2, s);
@@ -501,14 +528,14 @@ static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     return ZIPGPU_OK;
 }
 
-// the top passes [pass_begin, end) of the trees of `num_rows` rows whose lower levels are already in d_layers
+// the passes above `from_level` of the trees of `num_rows` rows whose lower levels are already in d_layers
 static int merkle_top_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_rows, uint8_t *d_layers, uint8_t *d_roots,
-                          cudaStream_t s, int pass_begin) {
+                          cudaStream_t s, int from_level) {
     zipgpu_ctx *ctx = code->ctx;
     ProfRec r;
     const bool prof = prof_begin(ctx, &r);
     if (prof) cudaEventRecord(r.e1, s);
-    int rc = merkle_dev(ctx, num_rows, code->depth, code->out_limbs, d_rows, d_layers, d_roots, s, pass_begin, -1);
+    int rc = merkle_dev(ctx, num_rows, code->depth, code->out_limbs, d_rows, d_layers, d_roots, s, from_level, -1);
     if (rc) return rc;
     if (prof) {
         cudaEventRecord(r.e2, s);
@@ -602,11 +629,9 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
     // The narrow top passes of the trees are latency-bound; per chunk they would cost their full latency every
     // time.  Run the first two (wide) passes per chunk and the rest once over all rows -- unless the caller wants
     // the layers streamed back chunk by chunk.
-    int pass_split = -1;
-    if (merkle && !job.layers_out && sched.size() > 1) {
-        int li[16], hh[16];
-        if (merkle_pass_plan(code->depth, li, hh) > 2) pass_split = 2;
-    }
+    // Per chunk the trees are taken to the first pass boundary >= level 6 (the wide passes); the rest is deferred.
+    const bool defer_top = merkle && !job.layers_out && sched.size() > 1 && code->depth > 7;
+    int split_level = -1;
     // ZIPGPU_TIMELINE=1: timing events after every copy / chunk, printed relative to the first (diagnostics only)
     static const bool timeline = getenv("ZIPGPU_TIMELINE") != nullptr;
     std::vector<cudaEvent_t> tl_copy, tl_kern;
@@ -630,7 +655,7 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
         int rc = commit_dev(code, n, (const uint64_t *)((uint8_t *)d_evals + r0 * in_row_bytes),
                             (uint64_t *)((uint8_t *)d_rows + r0 * out_row_bytes),
                             merkle ? d_layers + r0 * lay_row_bytes : nullptr, merkle ? d_roots + r0 * 32 : nullptr, k,
-                            pass_split);
+                            defer_top ? 6 : -1, &split_level);
         if (rc) return rc;
         if (timeline) {
             cudaEvent_t ev;
@@ -649,8 +674,8 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
         }
     }
     if ((e = chain(ctx, ctx->stream2, s)) != cudaSuccess) return cuda_fail(e, "chain");
-    if (pass_split >= 0) {
-        int rc = merkle_top_dev(code, num_rows, d_rows, d_layers, d_roots, s, pass_split);
+    if (defer_top && split_level < code->depth) {
+        int rc = merkle_top_dev(code, num_rows, d_rows, d_layers, d_roots, s, split_level);
         if (rc) return rc;
     }
     if (timeline) {
