@@ -29,7 +29,7 @@ def _all_gather_bytes(local: np.ndarray, counts: list[int], group=None) -> np.nd
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     mx = max(counts)
     buf = torch.zeros(mx, dtype=torch.uint8, device=dev)
-    buf[: local.size] = torch.from_numpy(np.ascontiguousarray(local).reshape(-1)).to(dev)
+    buf[: local.size] = torch.from_numpy(np.array(local, dtype=np.uint8, copy=True).reshape(-1)).to(dev)
     out = [torch.empty(mx, dtype=torch.uint8, device=dev) for _ in counts]
     dist.all_gather(out, buf, group=group)
     return np.concatenate([o[:c].cpu().numpy() for o, c in zip(out, counts)])
