@@ -1,1 +1,1 @@
-for ns in 0 10000 20000 40000 60000 100000 200000; do echo -n "stagger=$ns: "; ZIPGPU_FUSE_STAGGER_NS=$ns python bench.py --kernels-only --steps 10 --warmup 3 | cut -c60-180; done
+for ns in 0 2000 4000 6000 8000 10000 14000 20000; do echo -n "stagger=$ns: "; ZIPGPU_STAGGER_NS=$ns python scratch/enc_only.py; done

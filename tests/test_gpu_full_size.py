@@ -180,3 +180,18 @@ def test_fused_commit_kernel_default_at_nv22(oracle, ctx):
     assert np.array_equal(g_roots, roots)
     assert np.array_equal(g_rows, rows)
     assert np.array_equal(g_lay, layers)
+
+
+@pytest.mark.parametrize("row_len", [64, 1024, 4096, 8192])
+def test_encode_wide_to_M_matches_oracle(row_len, oracle, ctx):
+    """LinearCode::encode = encode_wide::<N, M> (code.rs:35-37; the verifier re-encodes the combined row in Int<8>,
+    verify_z.rs:74-78): 16-word outputs take the generic (run-time width, CTA-wide write-out) encoder variant"""
+    from zinc_b200 import RaaCode, ZipTypes
+
+    cw = 2 * row_len
+    p1, p2 = oracle.perm_from_seed(cw, 21), oracle.perm_from_seed(cw, 22)
+    code = RaaCode.with_permutations(ZipTypes(), row_len, 2, p1, p2)
+    row = np.random.default_rng(row_len).integers(0, 1 << 64, size=row_len, dtype=np.uint64)
+    rc, exp = oracle.encode_rows(row, 1, row_len, 2, p1, p2, in_limbs=1, out_limbs=8)
+    assert rc == 0
+    assert np.array_equal(code.encode(row, ctx).reshape(-1), exp)

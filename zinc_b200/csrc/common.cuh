@@ -28,6 +28,20 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) 
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// ---- bulk asynchronous shared -> global copies (the TMA engine; sm_90+).  The stores of the encoder leave the SM
+// through this path instead of the LSU, whose data stage is the kernel's bottleneck.  `bytes` and both addresses must
+// be multiples of 16.  Completion is tracked per thread in bulk async-groups. ----
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_s2g(void *gmem, const void *smem, uint32_t bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem), "r"(s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all bulk groups of this thread have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all bulk groups of this thread are complete (the global writes are done)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // 32-byte global accesses (sm_100: LDG/STG.E.ENL2.256): one full sector per lane, so a 32-byte digest or Int<4>
 // never reaches L2 as two partial-sector writes
 struct __align__(32) u32x8 {
@@ -35,6 +49,13 @@ struct __align__(32) u32x8 {
 };
 __device__ __forceinline__ void st_global_v8(void *p, const uint32_t (&v)[8]) {
     asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+// streaming (evict-first) 256-bit store: the 1 GiB of codewords passes through L2 once and must not push out the
+// next rows' prefetched inputs or the permutation tables
+__device__ __forceinline__ void st_stream_v8(void *p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.cs.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
                  "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
 }

@@ -211,19 +211,24 @@ struct WarpStage {
 //        Merkle tree (pcs/utils.rs:87-118), writing levels 0..log2(E) to `layers`.  With two CTAs per SM one CTA's
 //        memory-bound encode phases run under the other's ALU-bound hash phase, and the codeword is never re-read
 //        from HBM.  The levels above log2(E) are left to the batched passes of merkle.cu.
-template <int IN32, int W, int E, int OUT32, bool CACHE, bool EXACT, bool FUSE, int MAXT, int MINB>
+// BULK : (EXACT, Int<4> outputs) the write-out goes through 1 KiB record tiles in shared memory and bulk asynchronous
+//        copies (TMA) instead of 256-bit STG: the LSU data stage, which the stores would occupy for 8 k cycles per row,
+//        stays free for the shared-memory traffic of the next row's gathers
+template <int IN32, int W, int E, int OUT32, bool CACHE, bool EXACT, bool FUSE, bool BULK, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
     raa_encode_kernel(const uint32_t *__restrict__ evals, uint32_t *__restrict__ rows_out,
                       const uint16_t *__restrict__ tab1, const uint16_t *__restrict__ tab2,
                       const uint8_t *__restrict__ colw, uint32_t num_rows, uint32_t row_len, uint32_t cw,
                       uint32_t out32_rt, uint8_t *__restrict__ layers, uint32_t one) {
     static_assert(!FUSE || (EXACT && OUT32 != 0), "the fused commit kernel exists for exact shapes only");
+    static_assert(!BULK || (EXACT && OUT32 == 8 && W <= 4), "bulk write-out: exact shapes, 32-byte records");
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t T = blockDim.x, t = threadIdx.x;
     const uint32_t P = T * E;   // plane size in words (>= cw)
     uint32_t *planes = smem;    // [W][P]
     uint32_t *stage = smem;     // input row, aliases the planes (dead before s1 is written)
     uint32_t *aux = smem + (size_t)W * P;
+    uint32_t *tile = aux + 64 * W + (t >> 5) * 256;  // BULK: this warp's 1 KiB record tile
     const uint32_t nwarps = T >> 5;
     const uint32_t in_words = row_len * IN32;
     const uint32_t out32 = OUT32 ? (uint32_t)OUT32 : out32_rt;
@@ -327,6 +332,35 @@ __global__ void __launch_bounds__(MAXT, MINB)
         //         codeword entries back (conflict-free by the XOR swizzle) and each 32-byte Int<4> leaves as ONE
         //         256-bit store, so a warp request covers 1 KiB of contiguous output (8 full 128-byte lines). ----
         uint32_t *dst_row = rows_out + (size_t)row * cw * out32;
+        if constexpr (BULK) {
+            // warp w writes out positions [w*32E, (w+1)*32E), 32 consecutive ones (1 KiB of output) per step: the three
+            // limbs come back from the planes, the sign-extended 32-byte records go into the warp's tile (lane L puts
+            // the half (L>>2)&1 of its record first: the quarter-warps then hit 8 distinct 16-byte bank groups), and
+            // one lane hands the tile to the TMA engine.
+            const uint32_t lane = t & 31u;
+            const uint32_t ha = (lane >> 2) & 1u;
+            uint8_t *dst_w = reinterpret_cast<uint8_t *>(dst_row) + (size_t)(t >> 5) * (32 * E) * 32;
+#pragma unroll
+            for (int it = 0; it < E; it++) {
+                const uint32_t i = (t >> 5) * (32 * E) + it * 32 + lane;
+                const uint32_t s = slot_of<E>(i / E, i % E, T);
+                uint32_t val[W];
+#pragma unroll
+                for (int w = 0; w < W; w++) val[w] = planes[w * P + s];
+                const uint32_t sign = (uint32_t)((int32_t)val[W - 1] >> 31);
+                const uint4 lo = make_uint4(val[0], W > 1 ? val[W > 1 ? 1 : 0] : sign, W > 2 ? val[W > 2 ? 2 : 0] : sign,
+                                            W > 3 ? val[W > 3 ? 3 : 0] : sign);
+                const uint4 hi = make_uint4(sign, sign, sign, sign);
+                if (lane == 0) bulk_wait_read_all();  // the previous step's copy has read the tile
+                __syncwarp();
+                uint4 *rec = reinterpret_cast<uint4 *>(tile) + lane * 2;
+                rec[ha] = ha ? hi : lo;
+                rec[ha ^ 1u] = ha ? lo : hi;
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) bulk_store_s2g(dst_w + (size_t)it * 1024, tile, 1024);
+            }
+        } else {
 #pragma unroll
         for (int it = 0; it < E; it++) {
             // EXACT: warp w writes out positions [w*32E, (w+1)*32E), 32 consecutive ones per step
@@ -373,6 +407,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
                     for (uint32_t q = W; q < out32; q++) d[q] = sign;
                 }
             }
+        }
         }
         // ---- 5b. FUSE: leaf hashes and the lowest log2(E) tree levels of the entries this thread owns ----
         if constexpr (FUSE) {
@@ -421,6 +456,9 @@ __global__ void __launch_bounds__(MAXT, MINB)
         }
         __syncthreads();
     }
+    if constexpr (BULK) {
+        if ((t & 31u) == 0) bulk_wait_all();  // the tile must stay alive until the TMA engine is done with it
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -454,7 +492,9 @@ bool cfg_exact(const EncodeCfg &c, uint32_t row_len, uint32_t cw, int in_limbs, 
 
 template <int IN32, int W, int E, int OUT32, bool CACHE, bool EXACT, bool FUSE, int MAXT, int MINB>
 cudaError_t launch_one(const EncodeArgs &a, int T, size_t smem) {
-    auto kern = raa_encode_kernel<IN32, W, E, OUT32, CACHE, EXACT, FUSE, MAXT, MINB>;
+    constexpr bool BULK = EXACT && OUT32 == 8 && W <= 4;
+    if (BULK) smem += (size_t)(T / 32) * 1024;  // one record tile per warp
+    auto kern = raa_encode_kernel<IN32, W, E, OUT32, CACHE, EXACT, FUSE, BULK, MAXT, MINB>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     int occ = 0;
