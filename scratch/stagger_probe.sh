@@ -1,1 +1,1 @@
-for ns in 0 2000 4000 6000 8000 10000 14000 20000; do echo -n "stagger=$ns: "; ZIPGPU_STAGGER_NS=$ns python scratch/enc_only.py; done
+for ns in 0 300 600 1000 1500 2500; do echo -n "stagger16=$ns: "; ZIPGPU_STAGGER_NS=$ns python scratch/enc_only.py; done
