@@ -42,6 +42,16 @@ HASH_ALU_SASS_PER_COMPRESSION = 480.0
 ALU_LANES_PER_CLK_PER_SM = 64.0
 
 
+# stdout must carry exactly ONE JSON line: everything any library prints on fd 1 (NCCL's version banner, build chatter)
+# is diverted to stderr, and the result line is written to the saved descriptor
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 def shape_for(nv: int):
     """row_len / num_rows / cw for a 2^nv MLE: row_len = isqrt(2^nv).next_power_of_two() (code_raa.rs:42-43),
     num_rows = (2^nv / row_len).next_power_of_two() (structs.rs:82), cw = 2 * row_len (rep = 2)"""
@@ -181,7 +191,7 @@ def run_reference_arm(args, rank: int, world: int):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ms_per_full_commit_extrapolated": 1e3 * (1 << nv) / value,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -223,6 +233,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION/INFO is set in the environment; stdout must
+        # carry exactly one JSON line, so keep NCCL quiet here (ZINC_KEEP_NCCL_DEBUG=1 leaves the setting alone)
+        if not os.environ.get("ZINC_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -324,10 +338,10 @@ def main():
     enc_ms.value, hash_ms.value, calls.value = enc_only_ms, hash_only_ms, 1
     if args.kernels_only:
         if rank == 0:
-            print(json.dumps({"metric": "zip_commit_evals_per_sec", "value": value, "unit": "evals/s",
-                              "ms_per_step": ms_per_step, "fused_kernel_ms": fused_ms, "upper_passes_ms": upper_ms,
-                              "encode_only_ms": enc_only_ms, "hash_only_ms": hash_only_ms,
-                              "gpu_launches": int(launches), "note": "kernels-only run"}), flush=True)
+            emit({"metric": "zip_commit_evals_per_sec", "value": value, "unit": "evals/s",
+                  "ms_per_step": ms_per_step, "fused_kernel_ms": fused_ms, "upper_passes_ms": upper_ms,
+                  "encode_only_ms": enc_only_ms, "hash_only_ms": hash_only_ms,
+                  "gpu_launches": int(launches), "note": "kernels-only run"})
         return
 
     # ---- e2e leg: host buffers through the C ABI (pinned H2D of evals + D2H of roots inside the timed region) ----
@@ -506,7 +520,7 @@ def main():
             "cpu_baseline": cpu_baseline,
             "sizes": sizes,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -29,7 +29,7 @@ def main():
     from helpers import KECCAK_SEEDS, shape_for
     from oracle import cbind
     from zinc_b200 import Context, DenseMultilinearExtension, MultilinearZipParams, RaaCode, ZipTypes
-    from zinc_b200.dist import sharded_batch_commit, sharded_commit
+    from zinc_b200.dist import sharded_batch_commit, sharded_commit, sharded_open_columns
 
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
@@ -52,6 +52,20 @@ def main():
     per = ((2 * cw) - 2) * 32
     mine_l = data.layers().reshape(-1) if data is not None else np.empty(0, dtype=np.uint8)
     ok &= np.array_equal(mine_l, layers[begin * per:(begin + count) * per])
+
+    # row -> column redistribution for `open`: 16 columns, every rank serves its resident rows, NCCL all-gather
+    cols = np.random.default_rng(7).integers(0, cw, size=16).astype(np.uint32)
+    got_v, got_p = sharded_open_columns(data, cols, num_rows)
+    depth = cw.bit_length() - 1
+    for ci, col in enumerate(cols):
+        exp = rows.reshape(num_rows, cw, 4)[:, col, :]
+        ok &= np.array_equal(got_v[ci], exp)
+        off = 0
+        for lvl in range(depth):  # path level lvl = sibling of (col >> lvl) in that level of every row's layers
+            sib = (int(col) >> lvl) ^ 1
+            exp_p = layers.reshape(num_rows, per // 32, 32)[:, off + sib, :]
+            ok &= np.array_equal(got_p[ci, :, lvl, :], exp_p)
+            off += cw >> lvl
 
     polys = [DenseMultilinearExtension.from_evaluations_vec(
         nv, np.random.default_rng(500 + k).integers(0, 1 << 64, size=1 << nv, dtype=np.uint64))

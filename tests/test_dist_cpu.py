@@ -25,7 +25,7 @@ def _worker(rank, world, port, nv, out_dir):
 
     from oracle import cbind
     from zinc_b200 import DenseMultilinearExtension, MultilinearZipParams, RaaCode, ZipTypes
-    from zinc_b200.dist import sharded_batch_commit, sharded_commit
+    from zinc_b200.dist import sharded_batch_commit, sharded_commit, sharded_open_columns
     from helpers import shape_for
 
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
@@ -46,6 +46,29 @@ def _worker(rank, world, port, nv, out_dir):
     rc, rows, layers, roots = cbind.commit(evals, num_rows, row_len, 2, p1, p2)
     ok = b"".join(comm.roots) == roots.tobytes()
     ok &= np.array_equal(data[0], rows[begin * cw * 4:(begin + count) * cw * 4])
+
+    # column openings of the sharded commitment: each rank serves its rows, the ranges are all-gathered
+    import ctypes as C
+    depth = cw.bit_length() - 1
+    per = (2 << depth) - 2
+    cols = np.array([0, 3, cw - 1, cw // 2], dtype=np.uint32)
+    p8 = C.POINTER(C.c_uint8)
+
+    def open_rows(rows_, layers_, n_rows):
+        vals = np.empty((cols.size, n_rows, 4), dtype=np.uint64)
+        paths = np.empty((cols.size, n_rows, depth, 32), dtype=np.uint8)
+        path = np.zeros(depth * 32, dtype=np.uint8)
+        for ci, col in enumerate(cols):
+            for r in range(n_rows):
+                vals[ci, r] = rows_[(r * cw + col) * 4:(r * cw + col) * 4 + 4]
+                lay = np.ascontiguousarray(layers_[r * per * 32:(r + 1) * per * 32])
+                cbind.lib().zo_merkle_create_proof(depth, lay.ctypes.data_as(p8), int(col), path.ctypes.data_as(p8))
+                paths[ci, r] = path.reshape(depth, 32)
+        return vals, paths
+
+    got_v, got_p = sharded_open_columns(data, cols, num_rows, open_local=lambda d, c: open_rows(d[0], d[1], count))
+    exp_v, exp_p = open_rows(rows, layers, num_rows)
+    ok &= np.array_equal(got_v, exp_v) and np.array_equal(got_p, exp_p)
 
     polys = [DenseMultilinearExtension.from_evaluations_vec(
         nv, np.random.default_rng(50 + k).integers(0, 1 << 64, size=1 << nv, dtype=np.uint64)) for k in range(5)]

@@ -76,6 +76,56 @@ def sharded_commit(pp, poly, ctx=None, group=None, commit_rows: Callable | None 
     return local_data, begin, count, MultilinearZipCommitment([roots[i].tobytes() for i in range(pp.num_rows)])
 
 
+def sharded_open_columns(local_data, columns, num_rows: int, group=None, open_local: Callable | None = None):
+    """Column openings of a row-sharded commitment (open_z.rs:124-143): every rank extracts, from ITS resident rows, the
+    entries of the requested columns and their Merkle paths (zipgpu_data_open_columns), and the row ranges are
+    all-gathered in rank order -- the row -> column redistribution of the opening phase.  No codeword or layer data
+    other than the opened columns ever leaves a GPU.
+
+    Returns (values uint64 [ncols, num_rows, K], paths uint8 [ncols, num_rows, depth, 32]) on every rank.
+    `open_local(local_data, columns)` defaults to ResidentZipData.open_columns; the CPU tests inject the oracle."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    cols = np.ascontiguousarray(columns, dtype=np.uint32)
+    if open_local is None:
+        open_local = lambda d, c: d.open_columns(c)
+    if local_data is not None:
+        vals, paths = open_local(local_data, cols)  # [ncols, local_rows, K], [ncols, local_rows, depth, 32]
+    else:
+        vals, paths = None, None
+    if world == 1:
+        return vals, paths
+    # shapes are known from rank-independent quantities except K and depth: take them from a rank that has rows
+    meta = np.zeros(2, dtype=np.int64)
+    if vals is not None:
+        meta[:] = (vals.shape[2], paths.shape[2])
+    import torch
+
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mt = torch.from_numpy(meta).to(dev)
+    dist.all_reduce(mt, op=dist.ReduceOp.MAX, group=group)
+    k, depth = int(mt[0].item()), int(mt[1].item())
+    ncols = cols.size
+    counts_rows = [shard_range(num_rows, r, world)[1] for r in range(world)]
+    v_local = (vals if vals is not None else np.empty((ncols, 0, k), dtype=np.uint64))
+    p_local = (paths if paths is not None else np.empty((ncols, 0, depth, 32), dtype=np.uint8))
+    v_all = _all_gather_bytes(np.ascontiguousarray(v_local).view(np.uint8).reshape(-1),
+                              [ncols * c * k * 8 for c in counts_rows], group)
+    p_all = _all_gather_bytes(np.ascontiguousarray(p_local).reshape(-1),
+                              [ncols * c * depth * 32 for c in counts_rows], group)
+    out_v = np.empty((ncols, num_rows, k), dtype=np.uint64)
+    out_p = np.empty((ncols, num_rows, depth, 32), dtype=np.uint8)
+    ov = op = r0 = 0
+    for c in counts_rows:
+        nv_, np_ = ncols * c * k * 8, ncols * c * depth * 32
+        out_v[:, r0:r0 + c] = v_all[ov:ov + nv_].view(np.uint64).reshape(ncols, c, k)
+        out_p[:, r0:r0 + c] = p_all[op:op + np_].reshape(ncols, c, depth, 32)
+        ov, op, r0 = ov + nv_, op + np_, r0 + c
+    return out_v, out_p
+
+
 def sharded_batch_commit(pp, polys, ctx=None, group=None, commit_poly: Callable | None = None):
     """batch_commit with polynomial p handled by rank p % world; every rank gets all commitments.
 
