@@ -195,3 +195,35 @@ def test_encode_wide_to_M_matches_oracle(row_len, oracle, ctx):
     rc, exp = oracle.encode_rows(row, 1, row_len, 2, p1, p2, in_limbs=1, out_limbs=8)
     assert rc == 0
     assert np.array_equal(code.encode(row, ctx).reshape(-1), exp)
+
+
+def test_zero_copy_commit_opt_in(oracle, ctx, monkeypatch):
+    """ZIPGPU_ZEROCOPY=1: the fused commit kernel reads pinned host evaluations in place over PCIe and keeps a copy in
+    HBM for the opening phase; same roots, rows, layers, and the proximity row combination sees the copied evals"""
+    import torch
+
+    from oracle import pyoracle as po
+    from zinc_b200 import DenseMultilinearExtension, MultilinearZip, MultilinearZipParams
+
+    nv = 22
+    code, row_len, num_rows, cw, p1, p2 = _code(nv, KECCAK_SEEDS, oracle)
+    pp = MultilinearZipParams.new(nv, num_rows, code)
+    pinned = torch.empty((1 << nv, 1), dtype=torch.int64).pin_memory()
+    evals = np.random.default_rng(3).integers(0, 1 << 64, size=1 << nv, dtype=np.uint64)
+    pinned.numpy().view(np.uint64)[:, 0] = evals
+    monkeypatch.setenv("ZIPGPU_ZEROCOPY", "1")
+    poly = DenseMultilinearExtension(pinned.numpy().view(np.uint64), nv)
+    res, comm = MultilinearZip.commit_resident(pp, poly, ctx)
+    rc, _, _, roots = oracle.commit_mt(evals, num_rows, row_len, 2, 0, 0, p1, p2, threads=16, faithful=False,
+                                       want_rows=False, want_layers=False)
+    assert rc == 0 and b"".join(comm.roots) == roots.tobytes()
+    rc, rows, layers, _ = oracle.commit(evals[5 * row_len:7 * row_len], 2, row_len, 2, p1, p2)
+    assert np.array_equal(res.rows(5, 2).reshape(-1), rows) and np.array_equal(res.layers(5, 2).reshape(-1), layers)
+    co = np.zeros(num_rows, dtype=np.int64)
+    co[[0, 7, num_rows - 1]] = (3, -5, 11)  # sparse coefficients keep the big-int check cheap
+    got = res.combine_rows(co, 8)
+    ev = evals.view(np.int64)
+    for col in (0, 1, row_len - 1):
+        exp = 3 * int(ev[col]) - 5 * int(ev[7 * row_len + col]) + 11 * int(ev[(num_rows - 1) * row_len + col])
+        assert po.to_signed([int(w) for w in got[col]]) == exp
+    res.free()

@@ -16,6 +16,8 @@ struct EncodeArgs {
     uint32_t num_rows, row_len, cw, out32;
     int in_limbs;
     int num_sms;
+    uint32_t *evals_copy = nullptr;  // non-NULL (exact shapes only): `evals` is mapped pinned HOST memory read in place
+                                     // (zero-copy over PCIe); every staged row is also written here, in HBM
     uint8_t *fuse_layers = nullptr;  // non-NULL: the fused commit kernel also writes Merkle levels 0..encode_fused_levels()
     cudaStream_t stream;
 };

@@ -200,6 +200,13 @@ struct WarpStage {
             *reinterpret_cast<uint4 *>(stage + (r / E) * P + (r % E) * T + 32 * w + col) = v[j];
         }
     }
+    // zero-copy input (the row was read straight from pinned host memory): keep a copy in HBM for the opening phase
+    __device__ __forceinline__ void copy_out(uint32_t *row_dst, uint32_t t) const {
+        const uint32_t w = t >> 5, L = t & 31u;
+        uint4 *dst = reinterpret_cast<uint4 *>(row_dst + (size_t)w * (32 * WPL));
+#pragma unroll
+        for (int j = 0; j < WPL / 4; j++) st_stream_v4(dst + j * 32 + L, v[j]);
+    }
 };
 
 // IN32 : u32 words per input value          W    : u32 limbs carried through the scans
@@ -219,7 +226,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
     raa_encode_kernel(const uint32_t *__restrict__ evals, uint32_t *__restrict__ rows_out,
                       const uint16_t *__restrict__ tab1, const uint16_t *__restrict__ tab2,
                       const uint8_t *__restrict__ colw, uint32_t num_rows, uint32_t row_len, uint32_t cw,
-                      uint32_t out32_rt, uint8_t *__restrict__ layers, uint32_t one) {
+                      uint32_t out32_rt, uint8_t *__restrict__ layers, uint32_t one, uint32_t *__restrict__ evals_copy) {
     static_assert(!FUSE || (EXACT && OUT32 != 0), "the fused commit kernel exists for exact shapes only");
     static_assert(!BULK || (EXACT && OUT32 == 8 && W <= 4), "bulk write-out: exact shapes, 32-byte records");
     extern __shared__ __align__(16) uint32_t smem[];
@@ -252,6 +259,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
             WarpStage<IN32, E> ws;
             ws.load(evals + (size_t)row * in_words, t);
             ws.store(stage, P, T, t);
+            if (evals_copy) ws.copy_out(evals_copy + (size_t)row * in_words, t);
         } else {
             stage_row(evals + (size_t)row * in_words, stage, in_words, t, T);
         }
@@ -260,7 +268,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
 
     for (; row < num_rows; row += gridDim.x) {
         // pull the next row's input into L2 now: one bulk prefetch, no registers, a whole row-time of lead
-        if (t == 0 && row + gridDim.x < num_rows)
+        if (t == 0 && row + gridDim.x < num_rows && !evals_copy)  // (a no-op on system memory)
             prefetch_l2_bulk(evals + (size_t)(row + gridDim.x) * in_words, in_words * 4u);
         // ---- 1. y1 = widen(row[perm1[i] mod row_len]) ----
         uint32_t v[E][W];
@@ -449,6 +457,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
                 WarpStage<IN32, E> ws;
                 ws.load(evals + (size_t)next * in_words, t);
                 ws.store(stage, P, T, t);
+                if (evals_copy) ws.copy_out(evals_copy + (size_t)next * in_words, t);
             }
         } else {
             __syncthreads();
@@ -506,7 +515,7 @@ cudaError_t launch_one(const EncodeArgs &a, int T, size_t smem) {
     uint32_t grid = (uint32_t)a.num_sms * (uint32_t)occ;
     if (grid > a.num_rows) grid = a.num_rows;
     kern<<<grid, T, smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows, a.row_len, a.cw,
-                                      a.out32, a.fuse_layers, 1u);
+                                      a.out32, a.fuse_layers, 1u, a.evals_copy);
     return cudaGetLastError();
 }
 
