@@ -530,7 +530,9 @@ template <int IN32, int W, int OUT32, bool EXACT, bool FUSE>
 cudaError_t launch_e(const EncodeArgs &a, const EncodeCfg &c, size_t smem) {
     switch (c.E) {
         case 16:
-            if (c.T <= 512) return launch_if_valid<IN32, W, 16, OUT32, false, EXACT, FUSE, 512, 2>(a, c.T, smem);
+            // W >= 5 (Int<2> inputs): 16 x W live limbs do not fit 64 registers and the planes only allow one CTA per
+            // SM anyway, so those variants are compiled for one resident CTA (up to 128 registers, no spills)
+            if (c.T <= 512) return launch_if_valid<IN32, W, 16, OUT32, false, EXACT, FUSE, 512, (W >= 5 ? 1 : 2)>(a, c.T, smem);
             return launch_if_valid<IN32, W, 16, OUT32, false, EXACT, FUSE, 1024, 1>(a, c.T, smem);
         case 8: return launch_if_valid<IN32, W, 8, OUT32, true, EXACT, FUSE, 512, 2>(a, c.T, smem);
         case 4: return launch_if_valid<IN32, W, 4, OUT32, true, EXACT, FUSE, 512, 2>(a, c.T, smem);
