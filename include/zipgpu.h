@@ -28,7 +28,9 @@
  *   - Every function returns 0 on success or a negative zipgpu_status; it never aborts or unwinds.
  *     zipgpu_last_error() gives a thread-local message for the last failure.
  *   - `*_device` entry points take device pointers and enqueue on `stream` (a cudaStream_t passed as void*,
- *     NULL = the context's own stream) without synchronising.  The others take HOST pointers, perform the
+ *     NULL = the context's own stream) without synchronising.  The context's stream is NON-BLOCKING: it does not
+ *     order itself against the legacy default stream, so a caller that prepares buffers on another stream passes
+ *     that stream here or synchronises first (zipgpu_ctx_sync waits for the context's streams).  The others take HOST pointers, perform the
  *     host<->device copies themselves (pipelined with the kernels) and return when the outputs are valid.
  *   - A context is bound to one GPU.  Multi-GPU = one context (and one process/thread) per GPU, each working on a
  *     contiguous row range (commit) or on a subset of the polynomials (batch_commit); see INTEGRATION.md.
