@@ -17,4 +17,4 @@ for _ in range(3): e2e()
 t0=time.perf_counter()
 for _ in range(10): e2e()
 dt=(time.perf_counter()-t0)/10
-print(f"{'zero-copy' if not os.environ.get('ZIPGPU_NO_ZEROCOPY') else 'staged   '}: e2e {dt*1e3:.3f} ms  roots[0:4]={roots[:4].tolist()}")
+print(f"e2e {dt*1e3:.3f} ms  roots[0:4]={roots[:4].tolist()}")
