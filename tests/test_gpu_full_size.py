@@ -227,3 +227,41 @@ def test_zero_copy_commit_opt_in(oracle, ctx, monkeypatch):
         exp = 3 * int(ev[col]) - 5 * int(ev[7 * row_len + col]) + 11 * int(ev[(num_rows - 1) * row_len + col])
         assert po.to_signed([int(w) for w in got[col]]) == exp
     res.free()
+
+
+def test_two_host_threads_share_one_context(oracle, ctx):
+    """encoding_is_consistent_across_threads (commit.rs:439-470) in the GPU setting: the C ABI is thread-safe per
+    context, so concurrent commits from two host threads on ONE context give the single-threaded results"""
+    import threading
+
+    from zinc_b200 import DenseMultilinearExtension, MultilinearZip, MultilinearZipParams
+
+    nv = 16
+    code, row_len, num_rows, cw, p1, p2 = _code(nv, KECCAK_SEEDS, oracle)
+    pp = MultilinearZipParams.new(nv, num_rows, code)
+    code.native(ctx, 1, 4)  # create the per-pp state once, before the threads start
+    polys = [DenseMultilinearExtension.rand(nv, np.random.default_rng(100 + i)) for i in range(4)]
+    expect = []
+    for p in polys:
+        rc, rows, layers, roots = oracle.commit(p.evaluations.reshape(-1), num_rows, row_len, 2, p1, p2)
+        assert rc == 0
+        expect.append((rows, roots))
+    results, errors = {}, []
+
+    def worker(tid):
+        try:
+            for rep in range(6):
+                for i in range(tid, len(polys), 2):
+                    data, comm = MultilinearZip.commit(pp, polys[i], ctx)
+                    results[(i, rep)] = (data.rows.reshape(-1).copy(), b"".join(comm.roots))
+        except Exception as ex:  # surfaced below
+            errors.append(ex)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for (i, rep), (rows, roots) in results.items():
+        assert np.array_equal(rows, expect[i][0]) and roots == expect[i][1].tobytes(), (i, rep)

@@ -64,7 +64,11 @@ struct zipgpu_ctx {
     uint64_t prof_calls = 0;
     uint32_t *d_sink = nullptr;
     std::mutex mu;
+    // Public entry points serialise on this (recursive: some call each other), so several host threads may share one
+    // context; their jobs are then enqueued one after the other on the context's streams.
+    std::recursive_mutex api_mu;
 };
+#define API_LOCK(c) std::lock_guard<std::recursive_mutex> api_lock__((c)->api_mu)
 
 struct zipgpu_code {
     zipgpu_ctx *ctx;
@@ -258,6 +262,7 @@ extern "C" uint64_t zipgpu_ctx_launch_count(const zipgpu_ctx *c) { return c ? c-
 
 extern "C" int zipgpu_ctx_sync(zipgpu_ctx *c) {
     if (!c) return fail(ZIPGPU_ERR_INVALID, "ctx is NULL");
+    API_LOCK(c);
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->h2d));
     CU(cudaStreamSynchronize(c->stream2));
@@ -358,6 +363,7 @@ extern "C" int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t rep, i
         return fail(ZIPGPU_ERR_UNSUPPORTED, "no encoder kernel for in_limbs=" + std::to_string(in_limbs) +
                                                 " codeword_len=" + std::to_string(cw) +
                                                 " (the codeword must fit one SM's shared memory)");
+    API_LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     zipgpu_code *c = new (std::nothrow) zipgpu_code();
     if (!c) return fail(ZIPGPU_ERR_NOMEM, "host allocation failed");
@@ -556,6 +562,7 @@ static int merkle_top_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_
 extern "C" int zipgpu_encode_rows_device(zipgpu_code *code, size_t num_rows, const uint64_t *d_evals,
                                          uint64_t *d_rows_out, void *stream) {
     if (!code || (num_rows && (!d_evals || !d_rows_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    API_LOCK(code->ctx);
     CU(cudaSetDevice(code->ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : code->ctx->stream;
     return commit_dev(code, num_rows, d_evals, d_rows_out, nullptr, nullptr, s);
@@ -801,6 +808,7 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
 
 extern "C" int zipgpu_encode_rows(zipgpu_code *code, size_t num_rows, const uint64_t *evals, uint64_t *rows_out) {
     if (!code || (num_rows && (!evals || !rows_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    API_LOCK(code->ctx);
     CU(cudaSetDevice(code->ctx->device));
     HostJob job{evals, rows_out, nullptr, nullptr, false, nullptr};
     int rc = run_host_job(code, num_rows, job);
@@ -815,6 +823,7 @@ extern "C" int zipgpu_merkle_rows_device(zipgpu_ctx *ctx, size_t num_rows, int d
                                          const uint64_t *d_leaves, uint8_t *d_layers_out, uint8_t *d_roots_out,
                                          void *stream) {
     if (!ctx || (num_rows && (!d_leaves || !d_roots_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    API_LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     int rc;
@@ -845,6 +854,7 @@ extern "C" int zipgpu_merkle_rows(zipgpu_ctx *ctx, size_t num_rows, int depth, i
     if (!ctx || (num_rows && (!leaves || !roots_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
     if (depth < 0 || depth > 30) return fail(ZIPGPU_ERR_INVALID, "depth out of range");
     if (num_rows == 0) return ZIPGPU_OK;
+    API_LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const size_t nleaves = num_rows << depth;
@@ -878,6 +888,7 @@ extern "C" int zipgpu_commit_device(zipgpu_code *code, size_t num_rows, const ui
         return fail(ZIPGPU_ERR_INVALID, "leaves.len().is_power_of_two(): codeword_len is not a power of two");
     if (num_rows == 0) return ZIPGPU_OK;
     zipgpu_ctx *ctx = code->ctx;
+    API_LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     int rc;
@@ -901,6 +912,7 @@ extern "C" int zipgpu_commit_device(zipgpu_code *code, size_t num_rows, const ui
 extern "C" int zipgpu_commit(zipgpu_code *code, size_t num_rows, const uint64_t *evals, uint64_t *rows_out,
                              uint8_t *layers_out, uint8_t *roots_out) {
     if (!code || (num_rows && (!evals || !roots_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    API_LOCK(code->ctx);
     CU(cudaSetDevice(code->ctx->device));
     HostJob job{evals, rows_out, layers_out, roots_out, true, nullptr};
     int rc = run_host_job(code, num_rows, job);
@@ -911,6 +923,7 @@ extern "C" int zipgpu_commit(zipgpu_code *code, size_t num_rows, const uint64_t 
 extern "C" int zipgpu_batch_commit(zipgpu_code *code, size_t num_polys, size_t num_rows, const uint64_t *const *evals,
                                    uint64_t *const *rows_out, uint8_t *const *layers_out, uint8_t *const *roots_out) {
     if (!code || (num_polys && (!evals || !roots_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    API_LOCK(code->ctx);
     CU(cudaSetDevice(code->ctx->device));
     int rc = ZIPGPU_OK;
     for (size_t p = 0; p < num_polys && rc == 0; p++) {
@@ -932,6 +945,7 @@ extern "C" int zipgpu_batch_commit(zipgpu_code *code, size_t num_polys, size_t n
 extern "C" int zipgpu_commit_resident(zipgpu_code *code, size_t num_rows, const uint64_t *evals, uint8_t *roots_out,
                                       zipgpu_data **handle) {
     if (!code || !handle || (num_rows && (!evals || !roots_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    API_LOCK(code->ctx);
     CU(cudaSetDevice(code->ctx->device));
     HostJob job{evals, nullptr, nullptr, roots_out, true, handle};
     int rc = run_host_job(code, num_rows, job);
@@ -941,6 +955,7 @@ extern "C" int zipgpu_commit_resident(zipgpu_code *code, size_t num_rows, const 
 
 extern "C" void zipgpu_data_free(zipgpu_data *d) {
     if (!d) return;
+    API_LOCK(d->ctx);
     cudaSetDevice(d->ctx->device);
     cudaStream_t s = d->ctx->stream;
     dev_free(d->ctx, d->d_evals, s);
@@ -957,6 +972,7 @@ extern "C" const uint8_t *zipgpu_data_roots_device(const zipgpu_data *d) { retur
 extern "C" int zipgpu_data_read_rows(const zipgpu_data *d, size_t row_begin, size_t row_count, uint64_t *rows_out) {
     if (!d || (row_count && !rows_out)) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
     if (row_begin + row_count > d->num_rows) return fail(ZIPGPU_ERR_INVALID, "row range out of bounds");
+    API_LOCK(d->ctx);
     CU(cudaSetDevice(d->ctx->device));
     const size_t rb = d->cw * d->out_limbs * 8;
     CU(cudaMemcpyAsync(rows_out, (const uint8_t *)d->d_rows + row_begin * rb, row_count * rb, cudaMemcpyDeviceToHost,
@@ -967,6 +983,7 @@ extern "C" int zipgpu_data_read_rows(const zipgpu_data *d, size_t row_begin, siz
 extern "C" int zipgpu_data_read_layers(const zipgpu_data *d, size_t row_begin, size_t row_count, uint8_t *layers_out) {
     if (!d || (row_count && !layers_out)) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
     if (row_begin + row_count > d->num_rows) return fail(ZIPGPU_ERR_INVALID, "row range out of bounds");
+    API_LOCK(d->ctx);
     CU(cudaSetDevice(d->ctx->device));
     const size_t lb = layers_per_row(d->depth) * 32;
     if (lb * row_count) {
@@ -985,6 +1002,7 @@ extern "C" int zipgpu_data_open_columns(const zipgpu_data *d, size_t num_cols, c
     for (size_t i = 0; i < num_cols; i++)
         if (columns[i] >= d->cw) return fail(ZIPGPU_ERR_INVALID, "column index out of range");
     zipgpu_ctx *ctx = d->ctx;
+    API_LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const size_t val_bytes = num_cols * d->num_rows * d->out_limbs * 8;
@@ -1028,6 +1046,7 @@ extern "C" int zipgpu_combine_rows_device(zipgpu_ctx *ctx, size_t num_rows, size
     if (out_limbs < 3) return fail(ZIPGPU_ERR_WIDTH, "combine_rows needs out_limbs >= 3 (products of Int<1> are 128 bits wide)");
     if (num_rows > 0xffffffffull || row_len > 0xffffffffull) return fail(ZIPGPU_ERR_UNSUPPORTED, "shape too large");
     if (num_rows == 0 || row_len == 0) return ZIPGPU_OK;
+    API_LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     uint64_t *scratch = nullptr;
@@ -1053,6 +1072,7 @@ extern "C" int zipgpu_data_combine_rows(const zipgpu_data *d, const uint64_t *co
     if (!d || !coeffs || !combined_out) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
     if (d->in_limbs != 1) return fail(ZIPGPU_ERR_UNSUPPORTED, "combine_rows is implemented for Int<1> evaluations");
     zipgpu_ctx *ctx = d->ctx;
+    API_LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     uint64_t *d_coeffs = nullptr, *d_out = nullptr;
@@ -1078,6 +1098,7 @@ extern "C" int zipgpu_profile_enable(zipgpu_ctx *c, int on) {
 
 extern "C" int zipgpu_profile_read(zipgpu_ctx *c, double *encode_ms, double *hash_ms, uint64_t *calls, int reset) {
     if (!c) return fail(ZIPGPU_ERR_INVALID, "ctx is NULL");
+    API_LOCK(c);
     CU(cudaSetDevice(c->device));
     std::lock_guard<std::mutex> lk(c->mu);
     for (auto &r : c->prof_pending) {
@@ -1109,6 +1130,7 @@ extern "C" int zipgpu_profile_read(zipgpu_ctx *c, double *encode_ms, double *has
 extern "C" int zipgpu_microbench_int32(zipgpu_ctx *c, int kind, int iters, double *lane_ops_per_s) {
     if (!c || !lane_ops_per_s) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
     if (kind < 0 || kind > 1 || iters < 1) return fail(ZIPGPU_ERR_INVALID, "bad kind/iters");
+    API_LOCK(c);
     CU(cudaSetDevice(c->device));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
