@@ -83,7 +83,7 @@ def sharded_open_columns(local_data, columns, num_rows: int, group=None, open_lo
     other than the opened columns ever leaves a GPU.
 
     Returns (values uint64 [ncols, num_rows, K], paths uint8 [ncols, num_rows, depth, 32]) on every rank.
-    `open_local(local_data, columns)` defaults to ResidentZipData.open_columns; the CPU tests inject the oracle."""
+    `open_local(local_data, columns)` defaults to ResidentZipData.open_columns (the CPU tests inject a host function)."""
     import torch.distributed as dist
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
