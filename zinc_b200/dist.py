@@ -40,7 +40,7 @@ def sharded_commit(pp, poly, ctx=None, group=None, commit_rows: Callable | None 
 
     Returns (local_data, begin, count, MultilinearZipCommitment with ALL roots).  `commit_rows(pp, evals_slice,
     num_rows_local)` -> (local_data, roots uint8[num_rows_local, 32]) defaults to the GPU path; the CPU tests
-    inject the oracle here to exercise the sharding/gather logic without a GPU.
+    inject a host function here to exercise the sharding/gather logic without a GPU.
     """
     import torch.distributed as dist
 
