@@ -688,22 +688,22 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
     cudaStream_t ks[2] = {s, one_stream ? s : ctx->stream2};
     size_t chunk_no = 0;
 
-    // Chunk schedule: uniform chunks, the last one tapered (1/2, 1/4, 1/4) -- the H2D copies are the bottleneck
-    // resource of a host commit, so what remains exposed is the kernel work of the LAST chunk.
+    // Chunk schedule: uniform chunks with a short last one.  The H2D copies run back to back and the kernels of a chunk
+    // finish about one chunk-time after its copy, so what stays exposed after the last copy is the kernel work of the
+    // LAST chunk -- which cannot take less than the ~50 us latency of its three launches, hence exactly one short chunk.
     const size_t chunk = pick_chunk_rows(num_rows, in_row_bytes, ctx->num_sms);
     std::vector<std::pair<size_t, size_t>> sched;
     for (size_t r0 = 0; r0 < num_rows; r0 += chunk) sched.emplace_back(r0, std::min(chunk, num_rows - r0));
-    if (sched.size() >= 3 && sched.back().second >= 256 && !getenv("ZIPGPU_NO_TAPER")) {
-        const std::pair<size_t, size_t> last = sched.back();
-        sched.pop_back();
-        const size_t a = last.second / 2, b = last.second / 4;
-        sched.emplace_back(last.first, a);
-        sched.emplace_back(last.first + a, b);
-        sched.emplace_back(last.first + a + b, last.second - a - b);
+    {
+        size_t tail = 64;
+        if (const char *env = getenv("ZIPGPU_TAIL_ROWS")) tail = (size_t)atol(env);
+        if (tail > 0 && sched.size() >= 2 && sched.back().second >= 2 * tail) {
+            const std::pair<size_t, size_t> last = sched.back();
+            sched.pop_back();
+            sched.emplace_back(last.first, last.second - tail);
+            sched.emplace_back(last.first + last.second - tail, tail);
+        }
     }
-    // The narrow top passes of the trees are latency-bound; per chunk they would cost their full latency every
-    // time.  Run the first two (wide) passes per chunk and the rest once over all rows -- unless the caller wants
-    // the layers streamed back chunk by chunk.
     // Per chunk the trees are taken to the first pass boundary >= level 6 (the wide passes); the rest is deferred.
     const bool defer_top = merkle && !job.layers_out && sched.size() > 1 && code->depth > 7;
     int split_level = -1;
