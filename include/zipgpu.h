@@ -12,6 +12,8 @@
  *   MerkleTree::new                   src/zip/pcs/utils.rs:74-118     -> zipgpu_merkle_rows / zipgpu_merkle_rows_device
  *   MerkleProof::create_proof,
  *   ColumnOpening::open_at_column     src/zip/pcs/utils.rs:163-176,221-233, open_z.rs:124-143 -> zipgpu_data_open_columns
+ *   PcsTranscript::write_integers /
+ *   write_merkle_proof (wire bytes)   src/zip/pcs_transcript.rs:115-135,198-211           -> zipgpu_data_open_columns_wire
  *   combine_rows (proximity test)     src/zip/utils.rs:94-127, open_z.rs:100-113        -> zipgpu_data_combine_rows / zipgpu_combine_rows_device
  *
  * Conventions
@@ -140,6 +142,13 @@ int zipgpu_data_read_layers(const zipgpu_data *data, size_t row_begin, size_t ro
  *   col_values_out: num_cols * num_rows * out_limbs u64;  paths_out: num_cols * num_rows * depth * 32 bytes */
 int zipgpu_data_open_columns(const zipgpu_data *data, size_t num_cols, const uint32_t *columns,
                              uint64_t *col_values_out, uint8_t *paths_out);
+
+/* The same openings as the exact byte stream `open` appends to the proof for these columns (open_z.rs:124-143 over
+ * PcsTranscript::write_integers / write_merkle_proof, pcs_transcript.rs:115-135,198-211): per column the num_rows
+ * entries as little-endian u64 limbs, then per row be64(depth) followed by the depth path digests.
+ *   stream_out: num_cols * zipgpu_data_open_columns_wire_bytes(data) bytes (host). */
+size_t zipgpu_data_open_columns_wire_bytes(const zipgpu_data *data);
+int zipgpu_data_open_columns_wire(const zipgpu_data *data, size_t num_cols, const uint32_t *columns, uint8_t *stream_out);
 
 /* Proximity-test row combination (open_z.rs:100-113; zip/utils.rs:94-127): combined[col] = sum_i coeffs[i] *
  * evals[i*row_len + col], exact signed integer arithmetic, every operand expanded to out_limbs limbs as

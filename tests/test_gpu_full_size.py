@@ -265,3 +265,28 @@ def test_two_host_threads_share_one_context(oracle, ctx):
     assert not errors, errors
     for (i, rep), (rows, roots) in results.items():
         assert np.array_equal(rows, expect[i][0]) and roots == expect[i][1].tobytes(), (i, rep)
+
+
+def test_open_columns_wire_format(oracle, ctx):
+    """the proof-stream bytes of the column openings: write_integers (LE u64 limbs) then per row be64(depth) || path
+    (pcs_transcript.rs:115-135,198-211), assembled here from the structured openings and from the oracle's layers"""
+    from zinc_b200 import DenseMultilinearExtension, MultilinearZip, MultilinearZipParams
+
+    nv = 10
+    code, row_len, num_rows, cw, p1, p2 = _code(nv, KECCAK_SEEDS, oracle)
+    depth = cw.bit_length() - 1
+    pp = MultilinearZipParams.new(nv, num_rows, code)
+    poly = DenseMultilinearExtension.rand(nv, np.random.default_rng(4))
+    res, _ = MultilinearZip.commit_resident(pp, poly, ctx)
+    cols = np.array([5, 0, cw - 1, 5], dtype=np.uint32)
+    vals, paths = res.open_columns(cols)
+    rc, rows, layers, _ = oracle.commit(poly.evaluations.reshape(-1), num_rows, row_len, 2, p1, p2)
+    assert rc == 0 and np.array_equal(vals[0, :, :].reshape(-1), rows.reshape(num_rows, cw, 4)[:, 5, :].reshape(-1))
+    expect = b""
+    for ci in range(cols.size):
+        expect += vals[ci].astype("<u8").tobytes()
+        for r in range(num_rows):
+            expect += depth.to_bytes(8, "big") + paths[ci, r].tobytes()
+    got = res.open_columns_wire(cols)
+    assert len(got) == len(expect) and got == expect
+    res.free()

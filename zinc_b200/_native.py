@@ -54,6 +54,8 @@ SIGNATURES = {
     "zipgpu_data_read_rows": (i32, [vp, sz, sz, vp]),
     "zipgpu_data_read_layers": (i32, [vp, sz, sz, vp]),
     "zipgpu_data_open_columns": (i32, [vp, sz, vp, vp, vp]),
+    "zipgpu_data_open_columns_wire_bytes": (sz, [vp]),
+    "zipgpu_data_open_columns_wire": (i32, [vp, sz, vp, vp]),
     "zipgpu_data_combine_rows": (i32, [vp, vp, i32, vp]),
     "zipgpu_combine_rows_device": (i32, [vp, sz, sz, vp, vp, i32, vp, vp]),
     "zipgpu_profile_enable": (i32, [vp, i32]),

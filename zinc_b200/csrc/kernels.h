@@ -60,6 +60,9 @@ struct OpenArgs {
     cudaStream_t stream;
 };
 cudaError_t launch_open_columns(const OpenArgs &a);
+// the same openings as proof-stream bytes (col_values / paths of OpenArgs unused)
+size_t open_columns_wire_bytes(uint32_t num_rows, uint32_t out_limbs, int depth);  // per column
+cudaError_t launch_open_columns_wire(const OpenArgs &a, uint8_t *stream_out);
 
 // ---- K5: proximity-test row combination (combine_rows.cu) ----
 struct CombineArgs {

@@ -1037,6 +1037,48 @@ extern "C" int zipgpu_data_open_columns(const zipgpu_data *d, size_t num_cols, c
     return ZIPGPU_OK;
 }
 
+extern "C" size_t zipgpu_data_open_columns_wire_bytes(const zipgpu_data *d) {
+    return d ? open_columns_wire_bytes((uint32_t)d->num_rows, (uint32_t)d->out_limbs, d->depth) : 0;
+}
+
+extern "C" int zipgpu_data_open_columns_wire(const zipgpu_data *d, size_t num_cols, const uint32_t *columns,
+                                             uint8_t *stream_out) {
+    if (!d || (num_cols && (!columns || !stream_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (num_cols == 0) return ZIPGPU_OK;
+    for (size_t i = 0; i < num_cols; i++)
+        if (columns[i] >= d->cw) return fail(ZIPGPU_ERR_INVALID, "column index out of range");
+    zipgpu_ctx *ctx = d->ctx;
+    API_LOCK(ctx);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t bytes = num_cols * zipgpu_data_open_columns_wire_bytes(d);
+    uint32_t *d_cols = nullptr;
+    uint8_t *d_out = nullptr;
+    DEV_ALLOC(ctx, &d_cols, num_cols * 4, s);
+    DEV_ALLOC(ctx, &d_out, bytes, s);
+    CU(cudaMemcpyAsync(d_cols, columns, num_cols * 4, cudaMemcpyHostToDevice, s));
+    OpenArgs a;
+    a.rows = reinterpret_cast<const uint32_t *>(d->d_rows);
+    a.layers = d->d_layers;
+    a.columns = d_cols;
+    a.col_values = nullptr;
+    a.paths = nullptr;
+    a.num_rows = (uint32_t)d->num_rows;
+    a.cw = (uint32_t)d->cw;
+    a.out32 = (uint32_t)d->out_limbs * 2;
+    a.num_cols = (uint32_t)num_cols;
+    a.depth = d->depth;
+    a.stream = s;
+    cudaError_t e = launch_open_columns_wire(a, d_out);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_open_columns_wire");
+    ctx->launches++;
+    CU(cudaMemcpyAsync(stream_out, d_out, bytes, cudaMemcpyDeviceToHost, s));
+    DEV_FREE(ctx, d_cols, s);
+    DEV_FREE(ctx, d_out, s);
+    CU(cudaStreamSynchronize(s));
+    return ZIPGPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // proximity-test row combination
 // ------------------------------------------------------------------------------------------------------

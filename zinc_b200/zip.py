@@ -362,6 +362,15 @@ class ResidentZipData:
                                                      nat.ptr(paths) if paths.size else None))
         return vals, paths
 
+    def open_columns_wire(self, columns) -> bytes:
+        """open_z.rs:124-143 as proof-stream bytes (PcsTranscript::write_integers + write_merkle_proof,
+        pcs_transcript.rs:115-135,198-211): what `open` appends to the transcript stream for these columns"""
+        cols = np.ascontiguousarray(columns, dtype=np.uint32)
+        per = int(nat.lib().zipgpu_data_open_columns_wire_bytes(self.handle))
+        out = np.empty(cols.size * per, dtype=np.uint8)
+        nat.check(nat.lib().zipgpu_data_open_columns_wire(self.handle, cols.size, nat.ptr(cols), nat.ptr(out)))
+        return out.tobytes()
+
     def combine_rows(self, coeffs, out_limbs: int = 8) -> np.ndarray:
         """open_z.rs:100-113 / zip/utils.rs:94-127: u' = sum_i coeffs[i] * row_i over the unencoded evaluations,
         operands expanded N -> M; -> [row_len, out_limbs] uint64"""
