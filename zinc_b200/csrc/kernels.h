@@ -18,6 +18,7 @@ struct EncodeArgs {
     int num_sms;
     uint32_t *evals_copy = nullptr;  // non-NULL (exact shapes only): `evals` is mapped pinned HOST memory read in place
                                      // (zero-copy over PCIe); every staged row is also written here, in HBM
+    uint32_t *row_counter = nullptr; // device word for dynamic row claiming (armed by the launcher); NULL = static rows
     uint8_t *fuse_layers = nullptr;  // non-NULL: the fused commit kernel also writes Merkle levels 0..encode_fused_levels()
     cudaStream_t stream;
 };

@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(MAXT, MINB)
     raa_encode_kernel(const uint32_t *__restrict__ evals, uint32_t *__restrict__ rows_out,
                       const uint16_t *__restrict__ tab1, const uint16_t *__restrict__ tab2,
                       const uint8_t *__restrict__ colw, uint32_t num_rows, uint32_t row_len, uint32_t cw,
-                      uint32_t out32_rt, uint8_t *__restrict__ layers, uint32_t one, uint32_t *__restrict__ evals_copy) {
+                      uint32_t out32_rt, uint8_t *__restrict__ layers, uint32_t one, uint32_t *__restrict__ evals_copy,
+                      uint32_t *__restrict__ row_counter) {
     static_assert(!FUSE || (EXACT && OUT32 != 0), "the fused commit kernel exists for exact shapes only");
     static_assert(!BULK || (EXACT && OUT32 == 8 && W <= 4), "bulk write-out: exact shapes, 32-byte records");
     extern __shared__ __align__(16) uint32_t smem[];
@@ -266,10 +267,19 @@ __global__ void __launch_bounds__(MAXT, MINB)
     }
     __syncthreads();
 
-    for (; row < num_rows; row += gridDim.x) {
-        // pull the next row's input into L2 now: one bulk prefetch, no registers, a whole row-time of lead
-        if (t == 0 && row + gridDim.x < num_rows && !evals_copy)  // (a no-op on system memory)
-            prefetch_l2_bulk(evals + (size_t)(row + gridDim.x) * in_words, in_words * 4u);
+    // Rows are claimed dynamically (row_counter starts at gridDim.x): the warp schedulers do not share an SM fairly
+    // between its two CTAs -- measured with static rows, one CTA of every pair finished its 14 rows in 1.05 ms and
+    // left the other alone for the remaining 0.9 ms, with nobody to hide its encode phases.  Claiming keeps every
+    // pair together to the end.  The claim for the row after this one is made early and published through a barrier.
+    __shared__ uint32_t s_next;
+    while (row < num_rows) {
+        if (t == 0) {
+            const uint32_t nx = row_counter ? atomicAdd(row_counter, 1u) : row + gridDim.x;
+            s_next = nx;
+            // pull that row's input into L2 now: one bulk prefetch, no registers, a whole row-time of lead
+            if (nx < num_rows && !evals_copy)  // (a no-op on system memory)
+                prefetch_l2_bulk(evals + (size_t)nx * in_words, in_words * 4u);
+        }
         // ---- 1. y1 = widen(row[perm1[i] mod row_len]) ----
         uint32_t v[E][W];
         {
@@ -333,7 +343,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
         if constexpr (EXACT) __syncwarp();
         else __syncthreads();
 
-        const uint32_t next = row + gridDim.x;
+        const uint32_t next = s_next;  // published before the scans' barriers
         if constexpr (!CACHE) T16::load(tab1, t, T, c1);  // for the next row; in flight during the write-out
 
         // ---- 5. coalesced write-out with sign extension to out32 words: consecutive lanes read consecutive
@@ -464,6 +474,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
             if (next < num_rows) stage_row(evals + (size_t)next * in_words, stage, in_words, t, T);
         }
         __syncthreads();
+        row = next;
     }
     if constexpr (BULK) {
         if ((t & 31u) == 0) bulk_wait_all();  // the tile must stay alive until the TMA engine is done with it
@@ -499,6 +510,16 @@ bool cfg_exact(const EncodeCfg &c, uint32_t row_len, uint32_t cw, int in_limbs, 
            out32 == 8u * (uint32_t)in_limbs;
 }
 
+// a static table i -> i: the source of the asynchronous 4-byte copies that arm the row counters (must outlive the copy)
+const uint32_t *grid_init_values() {
+    static const std::vector<uint32_t> v = [] {
+        std::vector<uint32_t> x(4096);
+        for (uint32_t i = 0; i < x.size(); i++) x[i] = i;
+        return x;
+    }();
+    return v.data();
+}
+
 template <int IN32, int W, int E, int OUT32, bool CACHE, bool EXACT, bool FUSE, int MAXT, int MINB>
 cudaError_t launch_one(const EncodeArgs &a, int T, size_t smem) {
     constexpr bool BULK = EXACT && OUT32 == 8 && W <= 4;
@@ -514,8 +535,12 @@ cudaError_t launch_one(const EncodeArgs &a, int T, size_t smem) {
     if (env_occ > 0 && env_occ < occ) occ = env_occ;
     uint32_t grid = (uint32_t)a.num_sms * (uint32_t)occ;
     if (grid > a.num_rows) grid = a.num_rows;
+    if (a.row_counter) {  // the first gridDim.x rows are taken statically
+        err = cudaMemcpyAsync(a.row_counter, &grid_init_values()[grid], sizeof(uint32_t), cudaMemcpyHostToDevice, a.stream);
+        if (err != cudaSuccess) return err;
+    }
     kern<<<grid, T, smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows, a.row_len, a.cw,
-                                      a.out32, a.fuse_layers, 1u, a.evals_copy);
+                                      a.out32, a.fuse_layers, 1u, a.evals_copy, a.row_counter);
     return cudaGetLastError();
 }
 

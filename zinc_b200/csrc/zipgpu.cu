@@ -63,6 +63,8 @@ struct zipgpu_ctx {
     double enc_ms = 0, hash_ms = 0;
     uint64_t prof_calls = 0;
     uint32_t *d_sink = nullptr;
+    uint32_t *d_row_counters = nullptr;  // ring of row-claim counters, one per encoder launch in flight
+    size_t row_counter_pos = 0;
     std::mutex mu;
     // Public entry points serialise on this (recursive: some call each other), so several host threads may share one
     // context; their jobs are then enqueued one after the other on the context's streams.
@@ -232,7 +234,8 @@ extern "C" int zipgpu_ctx_create(int device, zipgpu_ctx **out) {
             return cuda_fail(e, "cudaEventCreate");
         }
     }
-    if ((e = cudaMalloc(&c->d_sink, 256)) != cudaSuccess) {
+    if ((e = cudaMalloc(&c->d_row_counters, 256 * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_sink, 256)) != cudaSuccess) {
         delete c;
         return cuda_fail(e, "cudaMalloc");
     }
@@ -250,6 +253,7 @@ extern "C" void zipgpu_ctx_destroy(zipgpu_ctx *c) {
     for (auto &b : c->cache_free) { cudaFree(b.p); cudaEventDestroy(b.ready); }
     for (auto &b : c->cache_live) { cudaFree(b.p); cudaEventDestroy(b.ready); }
     if (c->d_sink) cudaFree(c->d_sink);
+    if (c->d_row_counters) cudaFree(c->d_row_counters);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->h2d);
@@ -457,6 +461,9 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     a.num_sms = code->ctx->num_sms;
     a.fuse_layers = fuse_layers;
     a.evals_copy = reinterpret_cast<uint32_t *>(evals_copy);
+    if (!getenv("ZIPGPU_STATIC_ROWS")) {
+        a.row_counter = code->ctx->d_row_counters + (code->ctx->row_counter_pos++ % 256);
+    }
     a.stream = s;
     cudaError_t e = launch_raa_encode(a);
     if (e != cudaSuccess) return cuda_fail(e, "launch_raa_encode");
