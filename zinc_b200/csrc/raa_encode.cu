@@ -271,10 +271,31 @@ __global__ void __launch_bounds__(MAXT, MINB)
     // between its two CTAs -- measured with static rows, one CTA of every pair finished its 14 rows in 1.05 ms and
     // left the other alone for the remaining 0.9 ms, with nobody to hide its encode phases.  Claiming keeps every
     // pair together to the end.  The claim for the row after this one is made early and published through a barrier.
+    // End game: the CTA that is being starved by its SM-mate (its rows take several times the fastest CTA's) stops
+    // claiming once less than one round of rows is left, so that the last rows go to CTAs that finish them quickly and
+    // the kernel does not wait for a slow CTA that has just started a row.  row_counter[1] = fastest row time seen.
     __shared__ uint32_t s_next;
+    unsigned long long t_row = 0;
+    uint32_t my_row_ns = 0;
     while (row < num_rows) {
         if (t == 0) {
-            const uint32_t nx = row_counter ? atomicAdd(row_counter, 1u) : row + gridDim.x;
+            uint32_t nx;
+            if (row_counter) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t_row) {
+                    my_row_ns = (uint32_t)(now - t_row);
+                    atomicMin(row_counter + 1, my_row_ns);
+                }
+                t_row = now;
+                const uint32_t fastest = *reinterpret_cast<volatile uint32_t *>(row_counter + 1);
+                const uint32_t claimed = *reinterpret_cast<volatile uint32_t *>(row_counter);
+                const bool slow = my_row_ns > 2u * fastest;
+                const bool last_round = claimed + gridDim.x / 2 >= num_rows;
+                nx = (slow && last_round) ? num_rows : atomicAdd(row_counter, 1u);
+            } else {
+                nx = row + gridDim.x;
+            }
             s_next = nx;
             // pull that row's input into L2 now: one bulk prefetch, no registers, a whole row-time of lead
             if (nx < num_rows && !evals_copy)  // (a no-op on system memory)
@@ -510,11 +531,15 @@ bool cfg_exact(const EncodeCfg &c, uint32_t row_len, uint32_t cw, int in_limbs, 
            out32 == 8u * (uint32_t)in_limbs;
 }
 
-// a static table i -> i: the source of the asynchronous 4-byte copies that arm the row counters (must outlive the copy)
+// a static table of pairs {i, UINT_MAX}: the source of the asynchronous copies that arm the row counters (it must
+// outlive the copy)
 const uint32_t *grid_init_values() {
     static const std::vector<uint32_t> v = [] {
-        std::vector<uint32_t> x(4096);
-        for (uint32_t i = 0; i < x.size(); i++) x[i] = i;
+        std::vector<uint32_t> x(2 * 4096);  // pairs {i, 0xffffffff}
+        for (uint32_t i = 0; i < 4096; i++) {
+            x[2 * i] = i;
+            x[2 * i + 1] = 0xffffffffu;
+        }
         return x;
     }();
     return v.data();
@@ -535,8 +560,9 @@ cudaError_t launch_one(const EncodeArgs &a, int T, size_t smem) {
     if (env_occ > 0 && env_occ < occ) occ = env_occ;
     uint32_t grid = (uint32_t)a.num_sms * (uint32_t)occ;
     if (grid > a.num_rows) grid = a.num_rows;
-    if (a.row_counter) {  // the first gridDim.x rows are taken statically
-        err = cudaMemcpyAsync(a.row_counter, &grid_init_values()[grid], sizeof(uint32_t), cudaMemcpyHostToDevice, a.stream);
+    if (a.row_counter) {  // word 0: next row to claim (the first gridDim.x rows are taken statically); word 1: fastest row
+        err = cudaMemcpyAsync(a.row_counter, &grid_init_values()[2 * grid], 2 * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                              a.stream);
         if (err != cudaSuccess) return err;
     }
     kern<<<grid, T, smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows, a.row_len, a.cw,

@@ -234,7 +234,7 @@ extern "C" int zipgpu_ctx_create(int device, zipgpu_ctx **out) {
             return cuda_fail(e, "cudaEventCreate");
         }
     }
-    if ((e = cudaMalloc(&c->d_row_counters, 256 * sizeof(uint32_t))) != cudaSuccess ||
+    if ((e = cudaMalloc(&c->d_row_counters, 2 * 256 * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&c->d_sink, 256)) != cudaSuccess) {
         delete c;
         return cuda_fail(e, "cudaMalloc");
@@ -462,7 +462,7 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     a.fuse_layers = fuse_layers;
     a.evals_copy = reinterpret_cast<uint32_t *>(evals_copy);
     if (!getenv("ZIPGPU_STATIC_ROWS")) {
-        a.row_counter = code->ctx->d_row_counters + (code->ctx->row_counter_pos++ % 256);
+        a.row_counter = code->ctx->d_row_counters + 2 * (code->ctx->row_counter_pos++ % 256);
     }
     a.stream = s;
     cudaError_t e = launch_raa_encode(a);
@@ -500,9 +500,10 @@ static bool fusion_enabled() {
     return getenv("ZIPGPU_NO_FUSE") == nullptr;  // A/B knob: the two-kernel path (encode, then hash)
 }
 // rows from which commit_dev takes the fused kernel (ZIPGPU_FUSE_MIN_ROWS overrides: tests force it at small shapes)
-static size_t fuse_min_rows(const zipgpu_ctx *ctx) {
+static size_t fuse_min_rows(const zipgpu_ctx *ctx, size_t cw) {
     if (const char *env = getenv("ZIPGPU_FUSE_MIN_ROWS")) return (size_t)atol(env);
-    return (size_t)10 * ctx->num_sms;
+    // measured break-even (scratch/fuse_threshold_probe.py): 1024 rows at cw = 8192, 2048 rows at cw = 4096
+    return (size_t)(cw >= 8192 ? 6 : 10) * ctx->num_sms;
 }
 
 // Encode + Merkle of a row range on stream s, with optional profiling events.  until_level >= 0 stops the trees at the
@@ -515,11 +516,11 @@ static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     ProfRec r;
     const bool prof = prof_begin(ctx, &r);
     if (prof) cudaEventRecord(r.e0, s);
-    // The fused kernel is one persistent CTA pair per SM: it needs enough rows per CTA (>= 5 rounds) for the pairs to
-    // drift into complementary phases and for the row quantisation not to matter; below that the two-kernel path,
-    // whose hash passes balance at subtree granularity, is faster (measured at nv = 16, 20).
+    // The fused kernel is one persistent CTA pair per SM: it needs a few rows per CTA for one CTA's encode phases to
+    // run under the other's hashing; below that the two-kernel path, whose hash passes balance at subtree granularity,
+    // is faster.
     const bool fuse = d_roots && d_layers && code->fused_levels > 0 && code->fused_levels <= code->depth &&
-                      num_rows >= fuse_min_rows(ctx) && fusion_enabled();
+                      num_rows >= fuse_min_rows(ctx, code->cw) && fusion_enabled();
     if (evals_copy && !fuse) return fail(ZIPGPU_ERR_INVALID, "zero-copy input needs the fused commit kernel");
     int rc = encode_dev(code, num_rows, d_evals, d_rows, s, fuse ? d_layers : nullptr, evals_copy);
     if (rc) return rc;
@@ -604,7 +605,7 @@ struct HostJob {
 // and an L2 prefetch of system memory is a no-op), so the DMA pipeline stays the default.
 static bool zero_copy_eligible(zipgpu_code *code, size_t num_rows, const HostJob &job, const uint64_t **dev_alias) {
     if (!job.want_roots || job.rows_out || job.layers_out) return false;
-    if (code->fused_levels <= 0 || code->depth < code->fused_levels || num_rows < fuse_min_rows(code->ctx)) return false;
+    if (code->fused_levels <= 0 || code->depth < code->fused_levels || num_rows < fuse_min_rows(code->ctx, code->cw)) return false;
     if (!fusion_enabled() || !getenv("ZIPGPU_ZEROCOPY")) return false;
     if (((uintptr_t)job.evals & 31) != 0) return false;
     cudaPointerAttributes attr;
