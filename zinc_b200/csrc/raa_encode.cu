@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
                       const uint16_t *__restrict__ tab1, const uint16_t *__restrict__ tab2,
                       const uint8_t *__restrict__ colw, uint32_t num_rows, uint32_t row_len, uint32_t cw,
                       uint32_t out32_rt, uint8_t *__restrict__ layers, uint32_t one, uint32_t *__restrict__ evals_copy,
-                      uint32_t *__restrict__ row_counter) {
+                      uint32_t *__restrict__ row_counter, uint32_t endgame_q) {
     static_assert(!FUSE || (EXACT && OUT32 != 0), "the fused commit kernel exists for exact shapes only");
     static_assert(!BULK || (EXACT && OUT32 == 8 && W <= 4), "bulk write-out: exact shapes, 32-byte records");
     extern __shared__ __align__(16) uint32_t smem[];
@@ -274,32 +274,45 @@ __global__ void __launch_bounds__(MAXT, MINB)
     // End game: the CTA that is being starved by its SM-mate (its rows take several times the fastest CTA's) stops
     // claiming once less than one round of rows is left, so that the last rows go to CTAs that finish them quickly and
     // the kernel does not wait for a slow CTA that has just started a row.  row_counter[1] = fastest row time seen.
-    __shared__ uint32_t s_next;
+    // FUSE: the claim is made only after the hash phase (a starved CTA spends ~0.4 ms in it; claiming a row ahead would
+    // commit it to a row long before it can know that the rows are running out); the other kernels claim a row ahead,
+    // which gives the L2 prefetch of the input a whole row-time of lead.
+    __shared__ volatile uint32_t s_next;
+    constexpr uint32_t kPending = 0xffffffffu;
     unsigned long long t_row = 0;
     uint32_t my_row_ns = 0;
+    auto claim_next = [&](uint32_t cur_row) {  // thread 0 only
+        uint32_t nx;
+        if (row_counter) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t_row) {
+                my_row_ns = (uint32_t)(now - t_row);
+                atomicMin(row_counter + 1, my_row_ns);
+            }
+            t_row = now;
+            const uint32_t fastest = *reinterpret_cast<volatile uint32_t *>(row_counter + 1);
+            const uint32_t claimed = *reinterpret_cast<volatile uint32_t *>(row_counter);
+            // a starved CTA (its rows take several times the fastest CTA's) starts another row only if that row can be
+            // finished before the fast CTAs have consumed what is left -- otherwise the whole kernel would wait for it
+            const bool slow = my_row_ns > 2u * fastest;
+            const unsigned long long left = claimed < num_rows ? num_rows - claimed : 0;
+            const unsigned long long t_left = left * fastest / (gridDim.x / 2 + 1);  // ns until the rows run out
+            const bool too_late = (unsigned long long)my_row_ns * endgame_q > 4ull * t_left;
+            nx = (slow && too_late) ? num_rows : atomicAdd(row_counter, 1u);
+        } else {
+            nx = cur_row + gridDim.x;
+        }
+        // pull that row's input into L2 now: one bulk prefetch, no registers
+        if (nx < num_rows && !evals_copy)  // (a no-op on system memory)
+            prefetch_l2_bulk(evals + (size_t)nx * in_words, in_words * 4u);
+        s_next = nx;
+    };
+    constexpr bool LATE_CLAIM = FUSE;
     while (row < num_rows) {
         if (t == 0) {
-            uint32_t nx;
-            if (row_counter) {
-                unsigned long long now;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                if (t_row) {
-                    my_row_ns = (uint32_t)(now - t_row);
-                    atomicMin(row_counter + 1, my_row_ns);
-                }
-                t_row = now;
-                const uint32_t fastest = *reinterpret_cast<volatile uint32_t *>(row_counter + 1);
-                const uint32_t claimed = *reinterpret_cast<volatile uint32_t *>(row_counter);
-                const bool slow = my_row_ns > 2u * fastest;
-                const bool last_round = claimed + gridDim.x / 2 >= num_rows;
-                nx = (slow && last_round) ? num_rows : atomicAdd(row_counter, 1u);
-            } else {
-                nx = row + gridDim.x;
-            }
-            s_next = nx;
-            // pull that row's input into L2 now: one bulk prefetch, no registers, a whole row-time of lead
-            if (nx < num_rows && !evals_copy)  // (a no-op on system memory)
-                prefetch_l2_bulk(evals + (size_t)nx * in_words, in_words * 4u);
+            if (LATE_CLAIM && row_counter) s_next = kPending;
+            else claim_next(row);
         }
         // ---- 1. y1 = widen(row[perm1[i] mod row_len]) ----
         uint32_t v[E][W];
@@ -364,7 +377,6 @@ __global__ void __launch_bounds__(MAXT, MINB)
         if constexpr (EXACT) __syncwarp();
         else __syncthreads();
 
-        const uint32_t next = s_next;  // published before the scans' barriers
         if constexpr (!CACHE) T16::load(tab1, t, T, c1);  // for the next row; in flight during the write-out
 
         // ---- 5. coalesced write-out with sign extension to out32 words: consecutive lanes read consecutive
@@ -480,7 +492,20 @@ __global__ void __launch_bounds__(MAXT, MINB)
                 }
             }
         }
-        // ---- 6. stage the next row (its lines were pulled into L2 a row-time ago); the planes are reused ----
+        if constexpr (LATE_CLAIM) {
+            if (t == 0 && row_counter) {
+                claim_next(row);
+                __threadfence_block();
+            }
+        }
+        // ---- 6. stage the next row (its lines were pulled into L2 at claim time); the planes are reused ----
+        uint32_t next = s_next;  // written before the scans' barriers, or (late claim) by thread 0 just now
+        if constexpr (LATE_CLAIM) {
+            while (next == kPending) {
+                __nanosleep(64);
+                next = s_next;
+            }
+        }
         if constexpr (EXACT) {
             __syncwarp();  // this warp's slots are free once IT has written its share out
             // (issuing these loads before the write-out was measured slower: the 16 extra live registers spill)
@@ -566,7 +591,7 @@ cudaError_t launch_one(const EncodeArgs &a, int T, size_t smem) {
         if (err != cudaSuccess) return err;
     }
     kern<<<grid, T, smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows, a.row_len, a.cw,
-                                      a.out32, a.fuse_layers, 1u, a.evals_copy, a.row_counter);
+                                      a.out32, a.fuse_layers, 1u, a.evals_copy, a.row_counter, getenv("ZIPGPU_ENDGAME_Q") ? (uint32_t)atoi(getenv("ZIPGPU_ENDGAME_Q")) : 1u);
     return cudaGetLastError();
 }
 
