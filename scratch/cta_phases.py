@@ -24,6 +24,18 @@ print("rows per CTA: min %d median %d max %d; histogram:" % (rows_done.min(), np
 end = np.array([t[b, rows_done[b]-1, 4] for b in range(G)])
 print("CTA end times us: min %.0f median %.0f max %.0f" % ((end.min()-t0)/1e3, (np.median(end)-t0)/1e3, (end.max()-t0)/1e3))
 sm = t[:, 0, 6]
+start_last = np.array([t[b, rows_done[b]-1, 0] for b in range(G)])
+order = np.argsort(end)
+print("last 12 CTAs to finish: (cta, rows, last-row start us, end us, last-row duration us)")
+for b in order[-12:]:
+    print("  ", b, rows_done[b], round((start_last[b]-t0)/1e3), round((end[b]-t0)/1e3), round((end[b]-start_last[b])/1e3))
+pct = np.percentile((end - t0)/1e3, [0, 10, 25, 50, 75, 90, 100])
+print("end-time percentiles us:", np.round(pct))
+# per-SM finish = max over its CTAs
+bysm = {}
+for b in range(G): bysm.setdefault(int(sm[b]), []).append(end[b])
+smend = np.array([max(v) for v in bysm.values()])
+print("per-SM finish us: min %.0f median %.0f max %.0f; mean idle before kernel end %.0f us" % ((smend.min()-t0)/1e3, (np.median(smend)-t0)/1e3, (smend.max()-t0)/1e3, (smend.max()-smend.mean())/1e3))
 for s_ in sorted(set(sm))[:3]:
     mates = [b for b in range(G) if sm[b] == s_]
     for b in mates:
