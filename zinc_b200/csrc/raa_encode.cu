@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
     }
     __syncthreads();
 
-    // Rows are claimed dynamically (row_counter starts at gridDim.x): the warp schedulers do not share an SM fairly
+    // Rows are claimed dynamically (the first gridDim.x rows are static): the warp schedulers do not share an SM fairly
     // between its two CTAs -- measured with static rows, one CTA of every pair finished its 14 rows in 1.05 ms and
     // left the other alone for the remaining 0.9 ms, with nobody to hide its encode phases.  Claiming keeps every
     // pair together to the end.  The claim for the row after this one is made early and published through a barrier.
@@ -281,38 +281,39 @@ __global__ void __launch_bounds__(MAXT, MINB)
     constexpr uint32_t kPending = 0xffffffffu;
     unsigned long long t_row = 0;
     uint32_t my_row_ns = 0;
-    auto claim_next = [&](uint32_t cur_row) {  // thread 0 only
-        uint32_t nx;
-        if (row_counter) {
-            unsigned long long now;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (t_row) {
-                my_row_ns = (uint32_t)(now - t_row);
-                atomicMin(row_counter + 1, my_row_ns);
-            }
-            t_row = now;
-            const uint32_t fastest = *reinterpret_cast<volatile uint32_t *>(row_counter + 1);
-            const uint32_t claimed = *reinterpret_cast<volatile uint32_t *>(row_counter);
-            // a starved CTA (its rows take several times the fastest CTA's) starts another row only if that row can be
-            // finished before the fast CTAs have consumed what is left -- otherwise the whole kernel would wait for it
-            const bool slow = my_row_ns > 2u * fastest;
-            const unsigned long long left = claimed < num_rows ? num_rows - claimed : 0;
-            const unsigned long long t_left = left * fastest / (gridDim.x / 2 + 1);  // ns until the rows run out
-            const bool too_late = (unsigned long long)my_row_ns * endgame_q > 4ull * t_left;
-            nx = (slow && too_late) ? num_rows : atomicAdd(row_counter, 1u);
-        } else {
-            nx = cur_row + gridDim.x;
-        }
+    auto publish_next = [&](uint32_t nx) {
         // pull that row's input into L2 now: one bulk prefetch, no registers
         if (nx < num_rows && !evals_copy)  // (a no-op on system memory)
             prefetch_l2_bulk(evals + (size_t)nx * in_words, in_words * 4u);
         s_next = nx;
     };
-    constexpr bool LATE_CLAIM = FUSE;
+    auto claim_late = [&]() {  // thread 0 only, FUSE: with the end-game rule
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t_row) {
+            my_row_ns = (uint32_t)(now - t_row);
+            atomicMin(row_counter + 1, my_row_ns);
+        }
+        t_row = now;
+        const uint32_t fastest = *reinterpret_cast<volatile uint32_t *>(row_counter + 1);
+        // word 0 counts the claims made so far minus one (armed to 0xffffffff by one memset): row = gridDim.x + claims
+        const uint32_t claimed = gridDim.x + *reinterpret_cast<volatile uint32_t *>(row_counter) + 1u;
+        // a starved CTA (its rows take several times the fastest CTA's) starts another row only if that row can be
+        // finished before the fast CTAs have consumed what is left -- otherwise the whole kernel would wait for it
+        const bool slow = my_row_ns > 2u * fastest;
+        const unsigned long long left = claimed < num_rows ? num_rows - claimed : 0;
+        const unsigned long long t_left = left * fastest / (gridDim.x / 2 + 1);  // ns until the rows run out
+        const bool too_late = (unsigned long long)my_row_ns * endgame_q > 4ull * t_left;
+        publish_next((slow && too_late) ? num_rows : gridDim.x + atomicAdd(row_counter, 1u) + 1u);
+    };
+    constexpr bool LATE_CLAIM = FUSE && MINB >= 2;  // with one CTA per SM nobody hides the unprefetched input load
     while (row < num_rows) {
+        // early claim: the atomic is issued here and its result consumed after the first gather, so its latency is
+        // off the critical path of the row
+        uint32_t early = row + gridDim.x;
         if (t == 0) {
             if (LATE_CLAIM && row_counter) s_next = kPending;
-            else claim_next(row);
+            else if (row_counter) early = gridDim.x + atomicAdd(row_counter, 1u) + 1u;
         }
         // ---- 1. y1 = widen(row[perm1[i] mod row_len]) ----
         uint32_t v[E][W];
@@ -338,6 +339,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
             }
         }
 
+        if (t == 0 && !(LATE_CLAIM && row_counter)) publish_next(early);  // before the scan's barriers
         // ---- 2. s1 = prefix sum(y1), parked at the edge-coloured addresses ----
         // (the barriers inside block_scan also order every thread's stage reads before the plane writes)
         uint32_t pre[W];
@@ -494,7 +496,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
         }
         if constexpr (LATE_CLAIM) {
             if (t == 0 && row_counter) {
-                claim_next(row);
+                claim_late();
                 __threadfence_block();
             }
         }
@@ -556,20 +558,6 @@ bool cfg_exact(const EncodeCfg &c, uint32_t row_len, uint32_t cw, int in_limbs, 
            out32 == 8u * (uint32_t)in_limbs;
 }
 
-// a static table of pairs {i, UINT_MAX}: the source of the asynchronous copies that arm the row counters (it must
-// outlive the copy)
-const uint32_t *grid_init_values() {
-    static const std::vector<uint32_t> v = [] {
-        std::vector<uint32_t> x(2 * 4096);  // pairs {i, 0xffffffff}
-        for (uint32_t i = 0; i < 4096; i++) {
-            x[2 * i] = i;
-            x[2 * i + 1] = 0xffffffffu;
-        }
-        return x;
-    }();
-    return v.data();
-}
-
 template <int IN32, int W, int E, int OUT32, bool CACHE, bool EXACT, bool FUSE, int MAXT, int MINB>
 cudaError_t launch_one(const EncodeArgs &a, int T, size_t smem) {
     constexpr bool BULK = EXACT && OUT32 == 8 && W <= 4;
@@ -585,13 +573,14 @@ cudaError_t launch_one(const EncodeArgs &a, int T, size_t smem) {
     if (env_occ > 0 && env_occ < occ) occ = env_occ;
     uint32_t grid = (uint32_t)a.num_sms * (uint32_t)occ;
     if (grid > a.num_rows) grid = a.num_rows;
-    if (a.row_counter) {  // word 0: next row to claim (the first gridDim.x rows are taken statically); word 1: fastest row
-        err = cudaMemcpyAsync(a.row_counter, &grid_init_values()[2 * grid], 2 * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                              a.stream);
+    // few rows per CTA: static rows (arming and claiming cost more than the imbalance they remove; measured at nv = 20)
+    uint32_t *row_counter = a.num_rows >= 6 * grid ? a.row_counter : nullptr;
+    if (row_counter) {  // word 0: claims so far - 1, word 1: fastest row time seen; one fill arms both
+        err = cudaMemsetAsync(row_counter, 0xff, 2 * sizeof(uint32_t), a.stream);
         if (err != cudaSuccess) return err;
     }
     kern<<<grid, T, smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows, a.row_len, a.cw,
-                                      a.out32, a.fuse_layers, 1u, a.evals_copy, a.row_counter, getenv("ZIPGPU_ENDGAME_Q") ? (uint32_t)atoi(getenv("ZIPGPU_ENDGAME_Q")) : 1u);
+                                      a.out32, a.fuse_layers, 1u, a.evals_copy, row_counter, getenv("ZIPGPU_ENDGAME_Q") ? (uint32_t)atoi(getenv("ZIPGPU_ENDGAME_Q")) : 1u);
     return cudaGetLastError();
 }
 
