@@ -928,20 +928,103 @@ extern "C" int zipgpu_commit(zipgpu_code *code, size_t num_rows, const uint64_t 
     return rc ? rc : rc2;
 }
 
+// batch_commit as ONE matrix: rows are independent and the polynomials share the code, so the batch is the commit of a
+// (num_polys * num_rows)-row matrix whose row blocks arrive from different host pointers.  Groups of whole polynomials
+// (~8 MiB of evaluations) form the chunks of the same pipeline as run_host_job: H2D per polynomial, kernels per group
+// on alternating streams, the narrow tree passes once over the whole batch, outputs copied back per polynomial.
+static int run_batch_job(zipgpu_code *code, size_t num_polys, size_t num_rows, const uint64_t *const *evals,
+                         uint64_t *const *rows_out, uint8_t *const *layers_out, uint8_t *const *roots_out) {
+    zipgpu_ctx *ctx = code->ctx;
+    const size_t in_row_bytes = code->row_len * code->in_limbs * 8;
+    const size_t out_row_bytes = code->cw * code->out_limbs * 8;
+    if (code->depth < 0)
+        return fail(ZIPGPU_ERR_INVALID, "leaves.len().is_power_of_two(): codeword_len is not a power of two");
+    const size_t lay_row_bytes = layers_per_row(code->depth) * 32;
+    const size_t total_rows = num_polys * num_rows;
+    const size_t poly_in = num_rows * in_row_bytes, poly_out = num_rows * out_row_bytes, poly_lay = num_rows * lay_row_bytes;
+    bool want_rows = false, want_layers = false;
+    for (size_t p = 0; p < num_polys; p++) {
+        want_rows |= rows_out && rows_out[p];
+        want_layers |= layers_out && layers_out[p];
+    }
+    uint64_t *d_evals = nullptr, *d_rows = nullptr;
+    uint8_t *d_layers = nullptr, *d_roots = nullptr;
+    cudaStream_t s = ctx->stream;
+    DEV_ALLOC(ctx, &d_evals, total_rows * in_row_bytes, s);
+    DEV_ALLOC(ctx, &d_rows, total_rows * out_row_bytes, s);
+    DEV_ALLOC(ctx, &d_layers, std::max<size_t>(total_rows * lay_row_bytes, 32), s);
+    DEV_ALLOC(ctx, &d_roots, total_rows * 32, s);
+    cudaError_t e;
+    if ((e = chain(ctx, s, ctx->h2d)) != cudaSuccess) return cuda_fail(e, "chain");
+    if ((e = chain(ctx, s, ctx->d2h)) != cudaSuccess) return cuda_fail(e, "chain");
+    if ((e = chain(ctx, s, ctx->stream2)) != cudaSuccess) return cuda_fail(e, "chain");
+    cudaStream_t ks[2] = {s, ctx->stream2};
+    const size_t group = std::max<size_t>(1, (8u << 20) / std::max<size_t>(poly_in, 1));
+    const bool defer_top = !want_layers && num_polys > group && code->depth > 7;
+    int split_level = -1;
+    size_t chunk_no = 0;
+    for (size_t p0 = 0; p0 < num_polys; p0 += group) {
+        const size_t np = std::min(group, num_polys - p0);
+        for (size_t p = p0; p < p0 + np; p++)
+            CU(cudaMemcpyAsync((uint8_t *)d_evals + p * poly_in, evals[p], poly_in, cudaMemcpyHostToDevice, ctx->h2d));
+        cudaStream_t k = ks[chunk_no++ & 1];
+        if ((e = chain(ctx, ctx->h2d, k)) != cudaSuccess) return cuda_fail(e, "chain");
+        const size_t r0 = p0 * num_rows;
+        int rc = commit_dev(code, np * num_rows, (const uint64_t *)((uint8_t *)d_evals + r0 * in_row_bytes),
+                            (uint64_t *)((uint8_t *)d_rows + r0 * out_row_bytes), d_layers + r0 * lay_row_bytes,
+                            d_roots + r0 * 32, k, defer_top ? 6 : -1, &split_level);
+        if (rc) return rc;
+        if (want_rows || want_layers) {
+            if ((e = chain(ctx, k, ctx->d2h)) != cudaSuccess) return cuda_fail(e, "chain");
+            for (size_t p = p0; p < p0 + np; p++) {
+                if (rows_out && rows_out[p])
+                    CU(cudaMemcpyAsync(rows_out[p], (uint8_t *)d_rows + p * poly_out, poly_out, cudaMemcpyDeviceToHost, ctx->d2h));
+                if (layers_out && layers_out[p] && poly_lay)
+                    CU(cudaMemcpyAsync(layers_out[p], d_layers + p * poly_lay, poly_lay, cudaMemcpyDeviceToHost, ctx->d2h));
+            }
+        }
+    }
+    if ((e = chain(ctx, ctx->stream2, s)) != cudaSuccess) return cuda_fail(e, "chain");
+    if (defer_top && split_level < code->depth) {
+        int rc = merkle_top_dev(code, total_rows, d_rows, d_layers, d_roots, s, split_level);
+        if (rc) return rc;
+    }
+    if ((e = chain(ctx, s, ctx->d2h)) != cudaSuccess) return cuda_fail(e, "chain");
+    for (size_t p = 0; p < num_polys; p++)
+        CU(cudaMemcpyAsync(roots_out[p], d_roots + p * num_rows * 32, num_rows * 32, cudaMemcpyDeviceToHost, ctx->d2h));
+    if ((e = chain(ctx, ctx->d2h, s)) != cudaSuccess) return cuda_fail(e, "chain");
+    if ((e = chain(ctx, ctx->h2d, s)) != cudaSuccess) return cuda_fail(e, "chain");
+    DEV_FREE(ctx, d_evals, s);
+    DEV_FREE(ctx, d_rows, s);
+    DEV_FREE(ctx, d_layers, s);
+    DEV_FREE(ctx, d_roots, s);
+    return ZIPGPU_OK;
+}
+
 extern "C" int zipgpu_batch_commit(zipgpu_code *code, size_t num_polys, size_t num_rows, const uint64_t *const *evals,
                                    uint64_t *const *rows_out, uint8_t *const *layers_out, uint8_t *const *roots_out) {
     if (!code || (num_polys && (!evals || !roots_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
     API_LOCK(code->ctx);
     CU(cudaSetDevice(code->ctx->device));
+    for (size_t p = 0; p < num_polys; p++)
+        if (num_rows && (!evals[p] || !roots_out[p]))
+            return fail(ZIPGPU_ERR_INVALID, "NULL polynomial or roots pointer in batch");
+    if (num_polys == 0 || num_rows == 0) return ZIPGPU_OK;
     int rc = ZIPGPU_OK;
-    for (size_t p = 0; p < num_polys && rc == 0; p++) {
-        if (num_rows && (!evals[p] || !roots_out[p])) {
-            rc = fail(ZIPGPU_ERR_INVALID, "NULL polynomial or roots pointer in batch");
-            break;
+    // the whole batch as one matrix while its prover data fits comfortably (rows + layers: 192 B per evaluation);
+    // beyond that, polynomial by polynomial (still pipelined: poly p+1's H2D overlaps poly p's kernels)
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t need = num_polys * num_rows * (code->row_len * code->in_limbs * 8 + code->cw * code->out_limbs * 8 +
+                                                (code->depth >= 0 ? layers_per_row(code->depth) * 32 : 0) + 32);
+    if (code->depth >= 0 && need < total_b / 2) {
+        rc = run_batch_job(code, num_polys, num_rows, evals, rows_out, layers_out, roots_out);
+    } else {
+        for (size_t p = 0; p < num_polys && rc == 0; p++) {
+            HostJob job{evals[p], rows_out ? rows_out[p] : nullptr, layers_out ? layers_out[p] : nullptr, roots_out[p], true,
+                        nullptr};
+            rc = run_host_job(code, num_rows, job);
         }
-        HostJob job{evals[p], rows_out ? rows_out[p] : nullptr, layers_out ? layers_out[p] : nullptr, roots_out[p], true,
-                    nullptr};
-        rc = run_host_job(code, num_rows, job);  // no sync: poly p+1's H2D overlaps poly p's kernels
     }
     int rc2 = zipgpu_ctx_sync(code->ctx);
     return rc ? rc : rc2;
