@@ -290,3 +290,23 @@ def test_open_columns_wire_format(oracle, ctx):
     got = res.open_columns_wire(cols)
     assert len(got) == len(expect) and got == expect
     res.free()
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_longest_codeword_shape(fused, oracle, ctx, monkeypatch):
+    """cw = 16384 (row_len 8192: the nv = 25 / 26 shape, one 1024-thread CTA per SM with 16 entries per thread): a few
+    hundred rows through both the two-kernel and the fused commit path against the oracle"""
+    row_len, cw, num_rows = 8192, 16384, 300
+    from zinc_b200 import RaaCode, ZipTypes
+
+    p1, p2 = oracle.perm_from_seed(cw, KECCAK_SEEDS[0]), oracle.perm_from_seed(cw, KECCAK_SEEDS[1])
+    code = RaaCode.with_permutations(ZipTypes(), row_len, 2, p1, p2)
+    evals = np.random.default_rng(26).integers(0, 1 << 64, size=num_rows * row_len, dtype=np.uint64)
+    rc, rows, layers, roots = oracle.commit_mt(evals, num_rows, row_len, 2, 0, 0, p1, p2, threads=16, faithful=False)
+    assert rc == 0
+    if fused:
+        monkeypatch.setenv("ZIPGPU_FUSE_MIN_ROWS", "1")
+    else:
+        monkeypatch.setenv("ZIPGPU_NO_FUSE", "1")
+    g_rows, g_lay, g_roots = _commit_device(ctx, code, num_rows, cw, evals)
+    assert np.array_equal(g_roots, roots) and np.array_equal(g_rows, rows) and np.array_equal(g_lay, layers)
