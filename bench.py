@@ -503,6 +503,12 @@ def main():
                 "note": "what the timed commit steps launch: raa_encode_kernel<FUSE> (encode + BLAKE3 leaves + tree "
                         "levels 1..log2(E) from shared memory) and the batched passes for the levels above",
                 "two_kernel_path_ms": enc_ms_avg + hash_ms_avg,
+                # the fused kernel is INT32-alu-bound: 31/32 of the compressions at 480 alu lane-instructions each, plus
+                # the encoder's own alu work (45 M warp-instructions at nv = 24, ncu source counters)
+                "fused_alu_pipe_util": ((compressions * 31.0 / 32.0) * HASH_ALU_SASS_PER_COMPRESSION +
+                                        (45e6 * 32 if nv == 24 else 0.0)) / (fused_ms * 1e-3) / alu_peak,
+                "step_vs_alu_floor": ((compressions * HASH_ALU_SASS_PER_COMPRESSION + (45e6 * 32 if nv == 24 else 0.0))
+                                      / alu_peak) / (ms_per_step * 1e-3),
             },
             "hasher": {
                 "kernels": "merkle_subtree_kernel x passes (tree-only launches of the same rows)", "bound": "int32_alu",
