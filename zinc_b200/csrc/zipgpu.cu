@@ -581,9 +581,14 @@ static size_t pick_chunk_rows(size_t num_rows, size_t bytes_per_row_in, int num_
         const long v = atol(env);
         if (v > 0) return std::min<size_t>((size_t)v, std::max<size_t>(num_rows, 1));
     }
-    // ~8 MiB of input per chunk (measured best on B200: copies stay back to back, the exposed tail is short)
-    size_t rows = std::max<size_t>((8u << 20) / std::max<size_t>(bytes_per_row_in, 1), (size_t)num_sms);
-    rows = std::max(rows, (num_rows + 31) / 32);
+    // Measured on B200 (scratch/e2e_mid.py, e2e_probe.py): below 4 MiB of input one chunk is best (the launches of a
+    // chunk cost more than the overlap gains); above, chunks of 1/16 of the input clamped to 2..8 MiB and never fewer
+    // than 256 rows keep the copies back to back and the exposed tail short (nv = 20: 0.34 -> 0.29 ms).
+    const size_t total = num_rows * std::max<size_t>(bytes_per_row_in, 1);
+    if (total < (4u << 20)) return std::max<size_t>(num_rows, 1);
+    const size_t target = std::min<size_t>(std::max<size_t>(total / 16, 2u << 20), 8u << 20);
+    size_t rows = std::max<size_t>(target / std::max<size_t>(bytes_per_row_in, 1), 256);
+    (void)num_sms;
     return std::min(rows, std::max<size_t>(num_rows, 1));
 }
 
