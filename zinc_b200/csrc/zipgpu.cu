@@ -690,17 +690,6 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
         DEV_ALLOC(ctx, &d_layers, std::max<size_t>(num_rows * lay_row_bytes, 32), s);
         DEV_ALLOC(ctx, &d_roots, num_rows * 32, s);
     }
-    cudaError_t e;
-    const double t_alloc = now();
-    if ((e = chain(ctx, s, ctx->h2d)) != cudaSuccess) return cuda_fail(e, "chain");
-    if ((e = chain(ctx, s, ctx->d2h)) != cudaSuccess) return cuda_fail(e, "chain");
-    if ((e = chain(ctx, s, ctx->stream2)) != cudaSuccess) return cuda_fail(e, "chain");
-    // consecutive chunks alternate between two kernel streams: the tail of one chunk's kernels (partial waves, the
-    // latency-bound narrow passes) overlaps the head of the next chunk's
-    static const bool one_stream = getenv("ZIPGPU_ONE_STREAM") != nullptr;
-    cudaStream_t ks[2] = {s, one_stream ? s : ctx->stream2};
-    size_t chunk_no = 0;
-
     // Chunk schedule: uniform chunks with a short last one.  The H2D copies run back to back and the kernels of a chunk
     // finish about one chunk-time after its copy, so what stays exposed after the last copy is the kernel work of the
     // LAST chunk -- which cannot take less than the ~50 us latency of its three launches, hence exactly one short chunk.
@@ -717,6 +706,20 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
             sched.emplace_back(last.first + last.second - tail, tail);
         }
     }
+    // one chunk: everything on the kernel stream (no cross-stream events; a small commit is all launch latency)
+    const bool single = sched.size() == 1;
+    cudaStream_t h2d = single ? s : ctx->h2d, d2h = single ? s : ctx->d2h, st2 = single ? s : ctx->stream2;
+    cudaError_t e;
+    const double t_alloc = now();
+    if ((e = chain(ctx, s, h2d)) != cudaSuccess) return cuda_fail(e, "chain");
+    if ((e = chain(ctx, s, d2h)) != cudaSuccess) return cuda_fail(e, "chain");
+    if ((e = chain(ctx, s, st2)) != cudaSuccess) return cuda_fail(e, "chain");
+    // consecutive chunks alternate between two kernel streams: the tail of one chunk's kernels (partial waves, the
+    // latency-bound narrow passes) overlaps the head of the next chunk's
+    static const bool one_stream = getenv("ZIPGPU_ONE_STREAM") != nullptr;
+    cudaStream_t ks[2] = {s, one_stream ? s : st2};
+    size_t chunk_no = 0;
+
     // Per chunk the trees are taken to the first pass boundary >= level 6 (the wide passes); the rest is deferred.
     const bool defer_top = merkle && !job.layers_out && sched.size() > 1 && code->depth > 7;
     int split_level = -1;
@@ -726,20 +729,20 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
     cudaEvent_t tl0 = nullptr;
     if (timeline) {
         cudaEventCreate(&tl0);
-        cudaEventRecord(tl0, ctx->h2d);
+        cudaEventRecord(tl0, h2d);
     }
     for (const auto &ch : sched) {
         const size_t r0 = ch.first, n = ch.second;
         CU(cudaMemcpyAsync((uint8_t *)d_evals + r0 * in_row_bytes, (const uint8_t *)job.evals + r0 * in_row_bytes,
-                           n * in_row_bytes, cudaMemcpyHostToDevice, ctx->h2d));
+                           n * in_row_bytes, cudaMemcpyHostToDevice, h2d));
         if (timeline) {
             cudaEvent_t ev;
             cudaEventCreate(&ev);
-            cudaEventRecord(ev, ctx->h2d);
+            cudaEventRecord(ev, h2d);
             tl_copy.push_back(ev);
         }
         cudaStream_t k = ks[chunk_no++ & 1];
-        if ((e = chain(ctx, ctx->h2d, k)) != cudaSuccess) return cuda_fail(e, "chain");
+        if ((e = chain(ctx, h2d, k)) != cudaSuccess) return cuda_fail(e, "chain");
         int rc = commit_dev(code, n, (const uint64_t *)((uint8_t *)d_evals + r0 * in_row_bytes),
                             (uint64_t *)((uint8_t *)d_rows + r0 * out_row_bytes),
                             merkle ? d_layers + r0 * lay_row_bytes : nullptr, merkle ? d_roots + r0 * 32 : nullptr, k,
@@ -752,16 +755,16 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
             tl_kern.push_back(ev);
         }
         if (job.rows_out || job.layers_out) {
-            if ((e = chain(ctx, k, ctx->d2h)) != cudaSuccess) return cuda_fail(e, "chain");
+            if ((e = chain(ctx, k, d2h)) != cudaSuccess) return cuda_fail(e, "chain");
             if (job.rows_out)
                 CU(cudaMemcpyAsync((uint8_t *)job.rows_out + r0 * out_row_bytes, (uint8_t *)d_rows + r0 * out_row_bytes,
-                                   n * out_row_bytes, cudaMemcpyDeviceToHost, ctx->d2h));
+                                   n * out_row_bytes, cudaMemcpyDeviceToHost, d2h));
             if (job.layers_out && lay_row_bytes)
                 CU(cudaMemcpyAsync(job.layers_out + r0 * lay_row_bytes, d_layers + r0 * lay_row_bytes,
-                                   n * lay_row_bytes, cudaMemcpyDeviceToHost, ctx->d2h));
+                                   n * lay_row_bytes, cudaMemcpyDeviceToHost, d2h));
         }
     }
-    if ((e = chain(ctx, ctx->stream2, s)) != cudaSuccess) return cuda_fail(e, "chain");
+    if ((e = chain(ctx, st2, s)) != cudaSuccess) return cuda_fail(e, "chain");
     if (defer_top && split_level < code->depth) {
         int rc = merkle_top_dev(code, num_rows, d_rows, d_layers, d_roots, s, split_level);
         if (rc) return rc;
@@ -787,12 +790,12 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
         cudaEventDestroy(tl0);
     }
     if (merkle && job.roots_out) {
-        if ((e = chain(ctx, s, ctx->d2h)) != cudaSuccess) return cuda_fail(e, "chain");
-        CU(cudaMemcpyAsync(job.roots_out, d_roots, num_rows * 32, cudaMemcpyDeviceToHost, ctx->d2h));
+        if ((e = chain(ctx, s, d2h)) != cudaSuccess) return cuda_fail(e, "chain");
+        CU(cudaMemcpyAsync(job.roots_out, d_roots, num_rows * 32, cudaMemcpyDeviceToHost, d2h));
     }
     // join the copy streams back into the kernel stream so the frees are ordered after every use
-    if ((e = chain(ctx, ctx->d2h, s)) != cudaSuccess) return cuda_fail(e, "chain");
-    if ((e = chain(ctx, ctx->h2d, s)) != cudaSuccess) return cuda_fail(e, "chain");
+    if ((e = chain(ctx, d2h, s)) != cudaSuccess) return cuda_fail(e, "chain");
+    if ((e = chain(ctx, h2d, s)) != cudaSuccess) return cuda_fail(e, "chain");
     const double t_enq = now();
     if (!job.keep) DEV_FREE(ctx, d_evals, s);
     if (trace) fprintf(stderr, "[zipgpu] host job: alloc %.3f ms, enqueue %.3f ms\n", t_alloc - t_begin, t_enq - t_alloc);
