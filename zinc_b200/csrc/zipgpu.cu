@@ -177,8 +177,43 @@ static cudaError_t dev_free(zipgpu_ctx *c, void *p, cudaStream_t s) {
     }
     return cudaErrorInvalidValue;
 }
-#define DEV_ALLOC(ctx, ptr, bytes, s) CU(dev_alloc((ctx), (void **)(ptr), (bytes), (s)))
-#define DEV_FREE(ctx, ptr, s) CU(dev_free((ctx), (ptr), (s)))
+// Error-path hygiene: every function that takes buffers from the cache declares a DevGuard; buffers it allocated and
+// neither freed nor handed over (release) by the time it returns -- i.e. on an early error return -- go back to the
+// cache instead of staying "live" for the life of the context.
+struct DevGuard {
+    zipgpu_ctx *ctx;
+    cudaStream_t s;
+    std::vector<void *> owned;
+    DevGuard *prev;
+    static thread_local DevGuard *current;
+    DevGuard(zipgpu_ctx *c, cudaStream_t st) : ctx(c), s(st), prev(current) { current = this; }
+    ~DevGuard() {
+        current = prev;
+        for (void *p : owned) dev_free(ctx, p, s);
+    }
+    void add(void *p) { owned.push_back(p); }
+    void drop(void *p) {
+        for (size_t i = 0; i < owned.size(); i++)
+            if (owned[i] == p) {
+                owned.erase(owned.begin() + i);
+                return;
+            }
+    }
+    void release(void *p) { drop(p); }  // ownership moves elsewhere (a zipgpu_data handle)
+};
+thread_local DevGuard *DevGuard::current = nullptr;
+
+static cudaError_t dev_alloc_tracked(zipgpu_ctx *c, void **out, size_t bytes, cudaStream_t s) {
+    cudaError_t e = dev_alloc(c, out, bytes, s);
+    if (e == cudaSuccess && DevGuard::current) DevGuard::current->add(*out);
+    return e;
+}
+static cudaError_t dev_free_tracked(zipgpu_ctx *c, void *p, cudaStream_t s) {
+    for (DevGuard *g = DevGuard::current; g; g = g->prev) g->drop(p);
+    return dev_free(c, p, s);
+}
+#define DEV_ALLOC(ctx, ptr, bytes, s) CU(dev_alloc_tracked((ctx), (void **)(ptr), (bytes), (s)))
+#define DEV_FREE(ctx, ptr, s) CU(dev_free_tracked((ctx), (ptr), (s)))
 
 // ------------------------------------------------------------------------------------------------------
 // library / context
@@ -632,6 +667,7 @@ static int run_zero_copy_job(zipgpu_code *code, size_t num_rows, const HostJob &
     uint64_t *d_evals = nullptr, *d_rows = nullptr;
     uint8_t *d_layers = nullptr, *d_roots = nullptr;
     cudaStream_t s = ctx->stream;
+    DevGuard guard(ctx, s);
     DEV_ALLOC(ctx, &d_evals, num_rows * in_row_bytes, s);
     DEV_ALLOC(ctx, &d_rows, num_rows * out_row_bytes, s);
     DEV_ALLOC(ctx, &d_layers, num_rows * lay_row_bytes, s);
@@ -653,6 +689,10 @@ static int run_zero_copy_job(zipgpu_code *code, size_t num_rows, const HostJob &
         d->d_rows = d_rows;
         d->d_layers = d_layers;
         d->d_roots = d_roots;
+        guard.release(d_evals);
+        guard.release(d_rows);
+        guard.release(d_layers);
+        guard.release(d_roots);
         *job.keep = d;
     } else {
         DEV_FREE(ctx, d_evals, s);
@@ -681,6 +721,7 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
     uint64_t *d_evals = nullptr, *d_rows = nullptr;
     uint8_t *d_layers = nullptr, *d_roots = nullptr;
     cudaStream_t s = ctx->stream;
+    DevGuard guard(ctx, s);
     static const bool trace = getenv("ZIPGPU_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
@@ -813,6 +854,10 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
         d->d_rows = d_rows;
         d->d_layers = d_layers;
         d->d_roots = d_roots;
+        guard.release(d_evals);
+        guard.release(d_rows);
+        guard.release(d_layers);
+        guard.release(d_roots);
         *job.keep = d;
     } else {
         DEV_FREE(ctx, d_rows, s);
@@ -842,6 +887,7 @@ extern "C" int zipgpu_merkle_rows_device(zipgpu_ctx *ctx, size_t num_rows, int d
     API_LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    DevGuard guard(ctx, s);
     int rc;
     if ((rc = check_align16(d_leaves, "leaves")) || (rc = check_align16(d_roots_out, "roots_out")) ||
         (rc = check_align16(d_layers_out, "layers_out")))
@@ -873,6 +919,7 @@ extern "C" int zipgpu_merkle_rows(zipgpu_ctx *ctx, size_t num_rows, int depth, i
     API_LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
+    DevGuard guard(ctx, s);
     const size_t nleaves = num_rows << depth;
     const size_t leaf_bytes = nleaves * leaf_limbs * 8;
     const size_t lay_bytes = num_rows * layers_per_row(depth) * 32;
@@ -907,6 +954,7 @@ extern "C" int zipgpu_commit_device(zipgpu_code *code, size_t num_rows, const ui
     API_LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    DevGuard guard(ctx, s);
     int rc;
     if ((rc = check_align16(d_roots_out, "roots_out")) || (rc = check_align16(d_layers_out, "layers_out"))) return rc;
     uint64_t *rows_scratch = nullptr;
@@ -958,6 +1006,7 @@ static int run_batch_job(zipgpu_code *code, size_t num_polys, size_t num_rows, c
     uint64_t *d_evals = nullptr, *d_rows = nullptr;
     uint8_t *d_layers = nullptr, *d_roots = nullptr;
     cudaStream_t s = ctx->stream;
+    DevGuard guard(ctx, s);
     DEV_ALLOC(ctx, &d_evals, total_rows * in_row_bytes, s);
     DEV_ALLOC(ctx, &d_rows, total_rows * out_row_bytes, s);
     DEV_ALLOC(ctx, &d_layers, std::max<size_t>(total_rows * lay_row_bytes, 32), s);
@@ -1104,6 +1153,7 @@ extern "C" int zipgpu_data_open_columns(const zipgpu_data *d, size_t num_cols, c
     API_LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
+    DevGuard guard(ctx, s);
     const size_t val_bytes = num_cols * d->num_rows * d->out_limbs * 8;
     const size_t path_bytes = num_cols * d->num_rows * (size_t)d->depth * 32;
     uint32_t *d_cols = nullptr, *d_vals = nullptr;
@@ -1150,6 +1200,7 @@ extern "C" int zipgpu_data_open_columns_wire(const zipgpu_data *d, size_t num_co
     API_LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
+    DevGuard guard(ctx, s);
     const size_t bytes = num_cols * zipgpu_data_open_columns_wire_bytes(d);
     uint32_t *d_cols = nullptr;
     uint8_t *d_out = nullptr;
@@ -1190,6 +1241,7 @@ extern "C" int zipgpu_combine_rows_device(zipgpu_ctx *ctx, size_t num_rows, size
     API_LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    DevGuard guard(ctx, s);
     uint64_t *scratch = nullptr;
     DEV_ALLOC(ctx, &scratch, combine_rows_scratch_bytes((uint32_t)num_rows, (uint32_t)row_len), s);
     CombineArgs a;
@@ -1216,6 +1268,7 @@ extern "C" int zipgpu_data_combine_rows(const zipgpu_data *d, const uint64_t *co
     API_LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
+    DevGuard guard(ctx, s);
     uint64_t *d_coeffs = nullptr, *d_out = nullptr;
     DEV_ALLOC(ctx, &d_coeffs, d->num_rows * 8, s);
     DEV_ALLOC(ctx, &d_out, d->row_len * (size_t)out_limbs * 8, s);
