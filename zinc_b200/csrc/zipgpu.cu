@@ -234,6 +234,8 @@ extern "C" int zipgpu_device_count(int *count) {
     return ZIPGPU_OK;
 }
 
+extern "C" void zipgpu_ctx_destroy(zipgpu_ctx *c);
+
 extern "C" int zipgpu_ctx_create(int device, zipgpu_ctx **out) {
     if (!out) return fail(ZIPGPU_ERR_INVALID, "out is NULL");
     *out = nullptr;
@@ -259,19 +261,19 @@ extern "C" int zipgpu_ctx_create(int device, zipgpu_ctx **out) {
         (e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking)) != cudaSuccess) {
-        delete c;
+        zipgpu_ctx_destroy(c);  // releases whatever was created so far
         return cuda_fail(e, "cudaStreamCreate");
     }
-    c->ring.resize(256);
+    c->ring.assign(256, nullptr);
     for (auto &ev : c->ring) {
         if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) {
-            delete c;
+            zipgpu_ctx_destroy(c);
             return cuda_fail(e, "cudaEventCreate");
         }
     }
     if ((e = cudaMalloc(&c->d_row_counters, 2 * 256 * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&c->d_sink, 256)) != cudaSuccess) {
-        delete c;
+        zipgpu_ctx_destroy(c);
         return cuda_fail(e, "cudaMalloc");
     }
     *out = c;
@@ -284,15 +286,17 @@ extern "C" void zipgpu_ctx_destroy(zipgpu_ctx *c) {
     cudaDeviceSynchronize();
     for (auto &r : c->prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); cudaEventDestroy(r.e2); }
     for (auto &r : c->prof_free) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); cudaEventDestroy(r.e2); }
-    for (auto &ev : c->ring) cudaEventDestroy(ev);
+    for (auto &ev : c->ring)
+        if (ev) cudaEventDestroy(ev);
     for (auto &b : c->cache_free) { cudaFree(b.p); cudaEventDestroy(b.ready); }
     for (auto &b : c->cache_live) { cudaFree(b.p); cudaEventDestroy(b.ready); }
     if (c->d_sink) cudaFree(c->d_sink);
     if (c->d_row_counters) cudaFree(c->d_row_counters);
-    cudaStreamDestroy(c->stream);
-    cudaStreamDestroy(c->stream2);
-    cudaStreamDestroy(c->h2d);
-    cudaStreamDestroy(c->d2h);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->h2d) cudaStreamDestroy(c->h2d);
+    if (c->d2h) cudaStreamDestroy(c->d2h);
+    cudaGetLastError();
     delete c;
 }
 
@@ -430,9 +434,15 @@ extern "C" int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t rep, i
     std::vector<uint16_t> t1(padded, 0), t2(padded, 0);
     std::vector<uint8_t> cl(padded, 0);
     build_encode_tables(perm1, perm2, (uint32_t)row_len, (uint32_t)cw, in_limbs, out_limbs, t1.data(), t2.data(), cl.data());
-    CU(cudaMemcpy(c->d_tab1, t1.data(), padded * 2, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->d_tab2, t2.data(), padded * 2, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->d_colw, cl.data(), padded, cudaMemcpyHostToDevice));
+    if ((e = cudaMemcpy(c->d_tab1, t1.data(), padded * 2, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(c->d_tab2, t2.data(), padded * 2, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(c->d_colw, cl.data(), padded, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cudaFree(c->d_tab1);
+        cudaFree(c->d_tab2);
+        cudaFree(c->d_colw);
+        delete c;
+        return cuda_fail(e, "cudaMemcpy(tables)");
+    }
     *out = c;
     return ZIPGPU_OK;
 }
