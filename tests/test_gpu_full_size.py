@@ -310,3 +310,26 @@ def test_longest_codeword_shape(fused, oracle, ctx, monkeypatch):
         monkeypatch.setenv("ZIPGPU_NO_FUSE", "1")
     g_rows, g_lay, g_roots = _commit_device(ctx, code, num_rows, cw, evals)
     assert np.array_equal(g_roots, roots) and np.array_equal(g_rows, rows) and np.array_equal(g_lay, layers)
+
+
+@pytest.mark.parametrize("num_rows", [148, 1000, 1333])
+def test_warp_specialised_commit_kernel(num_rows, oracle, ctx, monkeypatch):
+    """cw = 8192 (the nv = 23 / 24 shape) takes the warp-specialised commit kernel (one 1024-thread CTA per SM: 16 warps
+    encode into alternating plane sets, 16 warps hash): codewords, every layer and the roots against the oracle, for row
+    counts below / above the dynamic-claiming threshold and not a multiple of the grid; and against the other paths"""
+    from zinc_b200 import RaaCode, ZipTypes
+
+    row_len, cw = 4096, 8192
+    p1, p2 = oracle.perm_from_seed(cw, KECCAK_SEEDS[0]), oracle.perm_from_seed(cw, KECCAK_SEEDS[1])
+    code = RaaCode.with_permutations(ZipTypes(), row_len, 2, p1, p2)
+    evals = np.random.default_rng(num_rows).integers(0, 1 << 64, size=num_rows * row_len, dtype=np.uint64)
+    rc, rows, layers, roots = oracle.commit_mt(evals, num_rows, row_len, 2, 0, 0, p1, p2, threads=16, faithful=False)
+    assert rc == 0
+    monkeypatch.setenv("ZIPGPU_FUSE_MIN_ROWS", "1")
+    for knob in (None, "ZIPGPU_NO_WS", "ZIPGPU_NO_FUSE"):
+        if knob:
+            monkeypatch.setenv(knob, "1")
+        g_rows, g_lay, g_roots = _commit_device(ctx, code, num_rows, cw, evals)
+        assert np.array_equal(g_roots, roots), knob
+        assert np.array_equal(g_rows, rows), knob
+        assert np.array_equal(g_lay, layers), knob

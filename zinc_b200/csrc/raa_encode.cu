@@ -44,7 +44,16 @@ __device__ __forceinline__ uint32_t slot_of(uint32_t t, uint32_t k, uint32_t T) 
 // Scan of W-limb values across the CTA in the logical order i = t*E + k.  On return v[k] holds the inclusive scan
 // WITHIN the thread and pre[] the sum of everything owned by lower threads; the caller adds pre to each v[k] at
 // the point where it consumes it (keeps the live register set small).  aux: 2 * 32 * W words of shared memory.
-template <int W, int E>
+struct CtaBarrier {  // all threads of the CTA
+    __device__ __forceinline__ static void sync() { __syncthreads(); }
+};
+template <int ID, int COUNT>
+struct NamedBarrier {  // a subset of the CTA's warps (warp-specialised kernels)
+    __device__ __forceinline__ static void sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+    __device__ __forceinline__ static void arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+};
+
+template <int W, int E, class BAR = CtaBarrier>
 __device__ __forceinline__ void block_scan(uint32_t (&v)[E][W], uint32_t (&pre)[W], uint32_t *aux, uint32_t t,
                                            uint32_t nwarps) {
     const uint32_t lane = t & 31u, warp = t >> 5;
@@ -65,7 +74,7 @@ __device__ __forceinline__ void block_scan(uint32_t (&v)[E][W], uint32_t (&pre)[
 #pragma unroll
         for (int w = 0; w < W; w++) aux[warp * W + w] = inc[w];
     }
-    __syncthreads();
+    BAR::sync();
     if (warp == 0) {
         uint32_t wt[W];
 #pragma unroll
@@ -84,7 +93,7 @@ __device__ __forceinline__ void block_scan(uint32_t (&v)[E][W], uint32_t (&pre)[
             aux[32 * W + lane * W + w] = lane ? e : 0u;
         }
     }
-    __syncthreads();
+    BAR::sync();
     // exclusive prefix of this thread = warp prefix + inclusive scan of the lower lanes of the warp
 #pragma unroll
     for (int w = 0; w < W; w++) {
@@ -530,6 +539,174 @@ __global__ void __launch_bounds__(MAXT, MINB)
 }
 
 // ------------------------------------------------------------------------------------------------------
+// The warp-specialised commit kernel (cw = 8192, Int<1> -> Int<4>): ONE 1024-thread CTA per SM, two plane sets.
+//   warps  0..15 (ENC)  : stage -> gather -> scan -> gather -> scan -> park s2 in plane set `buf` -> write the codeword
+//                         out (record tiles + bulk stores), then straight on to the next row in the other plane set
+//   warps 16..31 (HASH) : BLAKE3 leaves and the four lowest tree levels of the row parked in `buf`, thread t on the 16
+//                         entries ENC thread t produced
+// Two named barriers per plane set hand it back and forth (full: ENC arrives / HASH waits; empty: HASH arrives / ENC
+// waits).  This is what the hardware made of the two-CTA fused kernel anyway -- its warp schedulers let one CTA of
+// every pair run as if alone (75 us per row, 62 of them hashing) and starved the other -- minus the 13 us per row the
+// favoured CTA spent not hashing: here the hash warps never leave the alu pipe.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kWsEnc = 512, kWsAll = 1024;
+constexpr int kBarEnc = 1, kBarFull0 = 2, kBarEmpty0 = 4;  // + buf
+template <int ID>
+__device__ __forceinline__ void ws_sync_all() { asm volatile("bar.sync %0, %1;" ::"r"(ID), "n"(kWsAll) : "memory"); }
+__device__ __forceinline__ void ws_sync(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kWsAll) : "memory"); }
+__device__ __forceinline__ void ws_arrive(uint32_t id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kWsAll) : "memory"); }
+
+__global__ void __launch_bounds__(kWsAll, 1)
+    commit_ws_kernel(const uint32_t *__restrict__ evals, uint32_t *__restrict__ rows_out,
+                     const uint16_t *__restrict__ tab1, const uint16_t *__restrict__ tab2,
+                     const uint8_t *__restrict__ colw, uint32_t num_rows, uint8_t *__restrict__ layers, uint32_t one,
+                     uint32_t *__restrict__ row_counter) {
+    constexpr int IN32 = 2, W = 3, E = 16, OUT32 = 8;
+    constexpr uint32_t T = kWsEnc, P = T * E, cw = P, in_words = (P / 2) * IN32;
+    using T16 = Tab16<E>;
+    using T8 = Tab8<E>;
+    using EncBar = NamedBarrier<kBarEnc, kWsEnc>;
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *planes = smem;                    // [2][W][P]
+    uint32_t *aux = smem + 2 * W * P;           // scan scratch of the ENC group
+    uint32_t *tiles = aux + 64 * W;             // one 1 KiB record tile per ENC warp
+    __shared__ volatile uint32_t s_row[2];      // row parked in each plane set (0xffffffff: no more rows)
+    __shared__ volatile uint32_t s_next;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t t = tid & (kWsEnc - 1);      // index within the group: HASH thread t continues ENC thread t's entries
+
+    if (tid < kWsEnc) {
+        // ============================== ENC ==============================
+        uint32_t c1[T16::NR], c2[T16::NR], cc[T8::NR];
+        T16::load(tab1, t, T, c1);
+        const uint32_t wbase = (t >> 5) * (E * 32);
+        uint32_t *tile = tiles + (t >> 5) * 256;
+        const uint32_t lane = t & 31u, ha = (lane >> 2) & 1u;
+        uint32_t row = blockIdx.x, it = 0;
+        for (; row < num_rows; it++) {
+            const uint32_t buf = it & 1u;
+            uint32_t *pl = planes + buf * (W * P);
+            if (it >= 2) ws_sync(kBarEmpty0 + buf);  // the hash warps are done with this plane set
+            uint32_t early = row + gridDim.x;
+            if (t == 0 && row_counter) early = gridDim.x + atomicAdd(row_counter, 1u) + 1u;
+            {
+                WarpStage<IN32, E> ws;
+                ws.load(evals + (size_t)row * in_words, t);
+                ws.store(pl, P, T, t);
+            }
+            EncBar::sync();
+            uint32_t v[E][W];
+#pragma unroll
+            for (int k = 0; k < E; k++) {
+                const uint32_t so = T16::get(c1, k) * IN32;
+                const uint2 x = *reinterpret_cast<const uint2 *>(pl + so);
+                v[k][0] = x.x;
+                v[k][1] = x.y;
+                v[k][2] = (uint32_t)((int32_t)x.y >> 31);
+            }
+            if (t == 0) {
+                if (early < num_rows) prefetch_l2_bulk(evals + (size_t)early * in_words, in_words * 4u);
+                s_next = early;
+            }
+            uint32_t pre[W];
+            T8::load(colw, t, T, cc);
+            block_scan<W, E, EncBar>(v, pre, aux, t, T >> 5);
+#pragma unroll
+            for (int k = 0; k < E; k++) {
+                add_limbs<W>(v[k], pre);
+                const uint32_t s1 = wbase + k * 32 + T8::get(cc, k);
+#pragma unroll
+                for (int w = 0; w < W; w++) pl[w * P + s1] = v[k][w];
+            }
+            T16::load(tab2, t, T, c2);
+            EncBar::sync();
+#pragma unroll
+            for (int k = 0; k < E; k++) {
+                const uint32_t sl = T16::get(c2, k);
+#pragma unroll
+                for (int w = 0; w < W; w++) v[k][w] = pl[w * P + sl];
+            }
+            block_scan<W, E, EncBar>(v, pre, aux, t, T >> 5);
+#pragma unroll
+            for (int k = 0; k < E; k++) {
+                add_limbs<W>(v[k], pre);
+                const uint32_t s2 = slot_of<E>(t, k, T);
+#pragma unroll
+                for (int w = 0; w < W; w++) pl[w * P + s2] = v[k][w];
+            }
+            if (t == 0) s_row[buf] = row;
+            ws_arrive(kBarFull0 + buf);  // hand the row to the hash warps
+            __syncwarp();
+            T16::load(tab1, t, T, c1);   // for the next row; in flight during the write-out
+            // write-out of this warp's 32E positions: 32-byte records into the warp's tile, one bulk store per KiB
+            uint8_t *dst_w = reinterpret_cast<uint8_t *>(rows_out) + ((size_t)row * cw + (size_t)(t >> 5) * (32 * E)) * 32;
+#pragma unroll
+            for (int j = 0; j < E; j++) {
+                const uint32_t i = (t >> 5) * (32 * E) + j * 32 + lane;
+                const uint32_t s = slot_of<E>(i / E, i % E, T);
+                const uint32_t a0 = pl[s], a1 = pl[P + s], a2 = pl[2 * P + s];
+                const uint32_t sign = (uint32_t)((int32_t)a2 >> 31);
+                const uint4 lo = make_uint4(a0, a1, a2, sign), hi = make_uint4(sign, sign, sign, sign);
+                if (lane == 0) bulk_wait_read_all();
+                __syncwarp();
+                uint4 *rec = reinterpret_cast<uint4 *>(tile) + lane * 2;
+                rec[ha] = ha ? hi : lo;
+                rec[ha ^ 1u] = ha ? lo : hi;
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) bulk_store_s2g(dst_w + (size_t)j * 1024, tile, 1024);
+            }
+            row = s_next;  // published before this iteration's ENC barriers
+        }
+        {   // no more rows: tell the hash warps through the next plane set
+            const uint32_t buf = it & 1u;
+            if (it >= 2) ws_sync(kBarEmpty0 + buf);
+            if (t == 0) s_row[buf] = 0xffffffffu;
+            ws_arrive(kBarFull0 + buf);
+        }
+        if (lane == 0) bulk_wait_all();
+    } else {
+        // ============================== HASH ==============================
+        constexpr int H = 4;
+        for (uint32_t it = 0;; it++) {
+            const uint32_t buf = it & 1u;
+            ws_sync(kBarFull0 + buf);
+            const uint32_t row = s_row[buf];
+            if (row == 0xffffffffu) break;
+            const uint32_t *pl = planes + buf * (W * P);
+            uint8_t *lay_row = layers + (size_t)row * (2 * (size_t)cw - 2) * 32;
+            b3::Digest stack[H];
+#pragma unroll 1
+            for (uint32_t k = 0; k < (uint32_t)E; k++) {
+                const uint32_t s = slot_of<E>(t, k, T);
+                uint32_t x[OUT32];
+#pragma unroll
+                for (int w = 0; w < W; w++) x[w] = pl[w * P + s];
+                const uint32_t sign = (uint32_t)((int32_t)x[W - 1] >> 31);
+#pragma unroll
+                for (int w = W; w < OUT32; w++) x[w] = sign;
+                const uint32_t idx = t * E + k;
+                b3::Digest d;
+                b3::hash_leaf<OUT32>(x, d.w, one);
+                st_global_v8(lay_row + (size_t)idx * 32, d.w);
+#pragma unroll 1
+                for (int l = 0; l < H; l++) {
+                    if ((k >> l) & 1u) {
+                        d = b3::hash_node_call(stack[l], d, one);
+                        const size_t off = 2 * (size_t)cw - ((2 * (size_t)cw) >> (l + 1));
+                        st_global_v8(lay_row + (off + (idx >> (l + 1))) * 32, d.w);
+                    } else {
+                        stack[l] = d;
+                        break;
+                    }
+                }
+            }
+            ws_arrive(kBarEmpty0 + buf);  // the plane set may be overwritten
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
 namespace {
@@ -619,6 +796,23 @@ cudaError_t launch_w(const EncodeArgs &a) {
 #else
     // the hot instantiations (ZipTypes K = 4N limbs, exact power-of-two shapes) get a compile-time output width,
     // no padding predicates and the register prefetch of the next row
+    if (a.fuse_layers && IN32 == 2 && W == 3 && exact && c.E == 16 && c.T == 512 && a.out32 == 8 &&
+        !getenv("ZIPGPU_NO_WS")) {
+        // the warp-specialised commit kernel: one 1024-thread CTA per SM, two plane sets
+        const size_t ws_smem = (2 * 3 * (size_t)8192 + 64 * 3 + 16 * 256) * sizeof(uint32_t);
+        cudaError_t err = cudaFuncSetAttribute(commit_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem);
+        if (err != cudaSuccess) return err;
+        uint32_t grid = (uint32_t)a.num_sms;
+        if (grid > a.num_rows) grid = a.num_rows;
+        uint32_t *row_counter = a.num_rows >= 2 * grid ? a.row_counter : nullptr;
+        if (row_counter) {
+            err = cudaMemsetAsync(row_counter, 0xff, 2 * sizeof(uint32_t), a.stream);
+            if (err != cudaSuccess) return err;
+        }
+        commit_ws_kernel<<<grid, kWsAll, ws_smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows,
+                                                              a.fuse_layers, 1u, row_counter);
+        return cudaGetLastError();
+    }
     if (a.fuse_layers) {
         if (!exact) return cudaErrorInvalidConfiguration;
         return launch_e<IN32, W, 4 * IN32, true, true>(a, c, smem);
