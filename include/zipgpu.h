@@ -9,6 +9,7 @@
  *   MultilinearZip::batch_commit      src/zip/pcs/commit.rs:134-142   -> zipgpu_batch_commit
  *   MultilinearZip::encode_rows       src/zip/pcs/commit.rs:158-183   -> zipgpu_encode_rows
  *   RaaCode::{new,encode_inner}       src/zip/code_raa.rs:35-105      -> zipgpu_code_create (+ zipgpu_perm_from_seed)
+ *   ZipLinearCode::{new,encode_wide}  src/zip/code.rs:100-147,186-201,299-321 -> zipgpu_sparse_code_create
  *   MerkleTree::new                   src/zip/pcs/utils.rs:74-118     -> zipgpu_merkle_rows / zipgpu_merkle_rows_device
  *   MerkleProof::create_proof,
  *   ColumnOpening::open_at_column     src/zip/pcs/utils.rs:163-176,221-233, open_z.rs:124-143 -> zipgpu_data_open_columns
@@ -94,6 +95,20 @@ int zipgpu_raa_codeword_width_bits(int in_limbs, size_t poly_size, size_t repeti
  * not hold for any poly_size with this cw). */
 int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t repetition_factor, int in_limbs, int out_limbs,
                        const uint32_t *perm1, const uint32_t *perm2, zipgpu_code **out);
+/* ZipLinearCode, the sparse code: `ZipLinearCode::new` / `new_multilinear` src/zip/code.rs:100-147 with the two
+ * sampled matrices as INPUTS (like the RAA permutations): cols_x / coef_x are `SparseMatrixZ::cells`
+ * (code.rs:271-296) of matrix a and b in order -- codeword_len/2 matrix rows of cells_per_row (column, coefficient)
+ * cells each.  Coefficients are i64: KeccakTranscript::get_encoding_element draws 0 or 1 (src/transcript.rs:176-181),
+ * the reference tests' MockTranscript a counter (src/zip/pcs/tests.rs:30-33).  The handle is a zipgpu_code: every
+ * entry point below (encode_rows = `ZipLinearCode::encode_wide` code.rs:186-201 per row, commit, batch_commit,
+ * commit_resident, ...) takes it unchanged.  Sums are exact modulo 2^(64*out_limbs) (the reference's checked
+ * arithmetic never wraps at the sizes it is used at). */
+int zipgpu_sparse_code_create(zipgpu_ctx *ctx, size_t row_len, size_t codeword_len, size_t cells_per_row, int in_limbs,
+                              int out_limbs, const uint32_t *cols_a, const int64_t *coef_a, const uint32_t *cols_b,
+                              const int64_t *coef_b, zipgpu_code **out);
+/* -1: an RAA code; 0: sparse code on the generic kernel; 1: sparse code on the tensor-core kernel (all coefficients
+ * in 0..255 and row_len, codeword_len multiples of 128) */
+int zipgpu_code_sparse_kind(const zipgpu_code *code);
 void zipgpu_code_destroy(zipgpu_code *code);
 size_t zipgpu_code_row_len(const zipgpu_code *code);
 size_t zipgpu_code_codeword_len(const zipgpu_code *code);

@@ -43,6 +43,9 @@ def lib():
         L.zo_merkle_verify.argtypes = [sz, u8p, u8p, u64p, i, sz]
         L.zo_commit_perm.argtypes = [u64p, sz, sz, i, sz, u32p, u32p, i, u64p, u8p, u8p]
         L.zo_commit_mt.argtypes = [u64p, sz, sz, i, sz, u64, u64, u32p, u32p, i, u64p, u8p, u8p, i, i]
+        i64p = C.POINTER(C.c_int64)
+        L.zo_sparse_mat_vec.argtypes = [sz, sz, sz, u32p, i64p, u64p, i, u64p, i]
+        L.zo_sparse_commit_mt.argtypes = [u64p, sz, sz, i, sz, sz, u32p, i64p, u32p, i64p, i, u64p, u8p, u8p, i]
         L.zo_raa_row_len.argtypes = [sz]; L.zo_raa_row_len.restype = sz
         L.zo_num_rows.argtypes = [sz, sz]; L.zo_num_rows.restype = sz
         L.zo_raa_width_ok.argtypes = [i, i, sz, sz]
@@ -135,4 +138,24 @@ def commit_mt(evals: np.ndarray, num_rows: int, row_len: int, rep: int, seed1: i
     rc = lib().zo_commit_mt(_p(evals, C.c_uint64), num_rows, row_len, in_limbs, rep, seed1, seed2,
                             _p(perm1, C.c_uint32), _p(perm2, C.c_uint32), out_limbs,
                             _p(rows, C.c_uint64), _p(layers, C.c_uint8), _p(roots, C.c_uint8), threads, int(faithful))
+    return rc, rows, layers, roots
+
+
+def sparse_commit(evals: np.ndarray, num_rows: int, row_len: int, n: int, d: int, cols_a, coef_a, cols_b, coef_b,
+                  in_limbs: int = 1, out_limbs: int = 4, want_layers: bool = True, want_roots: bool = True,
+                  threads: int = 1):
+    """ZipLinearCode as the code (zip/code.rs:77-215): -> (rc, rows, layers or None, roots or None)"""
+    evals = np.ascontiguousarray(evals, dtype=np.uint64)
+    cols_a, cols_b = (np.ascontiguousarray(c, dtype=np.uint32) for c in (cols_a, cols_b))
+    coef_a, coef_b = (np.ascontiguousarray(c, dtype=np.int64) for c in (coef_a, coef_b))
+    cw = 2 * n
+    depth = (cw - 1).bit_length() if cw > 1 else 0
+    rows = np.empty(num_rows * cw * out_limbs, dtype=np.uint64)
+    layers = np.empty(num_rows * ((2 << depth) - 2) * 32, dtype=np.uint8) if want_layers and want_roots else None
+    roots = np.empty(num_rows * 32, dtype=np.uint8) if want_roots else None
+    rc = lib().zo_sparse_commit_mt(_p(evals, C.c_uint64), num_rows, row_len, in_limbs, n, d,
+                                   _p(cols_a, C.c_uint32), _p(coef_a, C.c_int64), _p(cols_b, C.c_uint32),
+                                   _p(coef_b, C.c_int64), out_limbs, _p(rows, C.c_uint64),
+                                   _p(layers, C.c_uint8) if layers is not None and layers.size else None,
+                                   _p(roots, C.c_uint8), threads)
     return rc, rows, layers, roots

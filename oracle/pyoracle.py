@@ -305,3 +305,87 @@ class KeccakTranscript:
         ch = self.get_random_bytes(8)
         self.buf += b"\x12" + ch + b"\x34"
         return int.from_bytes(ch, "little")
+
+    # --- the draws ZipLinearCode::new makes (zip/code.rs:271-296) ---
+    def get_usize_in_range(self, start: int, end: int) -> int:
+        """transcript.rs:161-172"""
+        ch = keccak256(self.buf)
+        self.buf += b"\x88" + ch + b"\x11"
+        return start + int.from_bytes(ch[:8], "little") % (end - start)
+
+    def get_encoding_element(self) -> int:
+        """transcript.rs:176-181: the LSB of one random byte; the state is NOT advanced"""
+        return self.get_random_bytes(1)[0] & 1
+
+    def sample_unique_columns(self, start: int, end: int, columns: set, count: int) -> int:
+        """transcript.rs:187-201"""
+        added = 0
+        while added < count:
+            c = self.get_usize_in_range(start, end)
+            if c not in columns:
+                columns.add(c)
+                added += 1
+        return added
+
+
+class MockTranscript:
+    """zip/pcs/tests.rs:24-56"""
+
+    def __init__(self):
+        self.counter = 0
+
+    def get_encoding_element(self) -> int:
+        self.counter += 1
+        return self.counter
+
+    def get_u64(self) -> int:
+        self.counter += 1
+        return self.counter
+
+    def sample_unique_columns(self, start: int, end: int, columns: set, count: int) -> int:
+        self.counter += 1
+        inserted = 0
+        for i in range(start, end):
+            if i not in columns:
+                columns.add(i)
+                inserted += 1
+                if inserted == count:
+                    break
+        return inserted
+
+
+def sparse_matrix_sample_new(n: int, m: int, d: int, transcript):
+    """SparseMatrixZ::sample_new (code.rs:271-296): per matrix row draw d unique columns into a BTreeSet, then one
+    encoding element per column in ascending column order.  -> (cols[n*d], coef[n*d])"""
+    cols, coef = [], []
+    for _ in range(n):
+        chosen: set = set()
+        transcript.sample_unique_columns(0, m, chosen, d)
+        for c in sorted(chosen):
+            cols.append(c)
+            coef.append(transcript.get_encoding_element())
+    return cols, coef
+
+
+def zip_linear_code_new(poly_size: int, transcript, rep: int = 2):
+    """ZipLinearCode::new / new_multilinear (code.rs:100-147): row_len, codeword_len and the matrices a, b of
+    dimension (codeword_len/2) x row_len with row_len/2 cells per row (code.rs:134)."""
+    assert poly_size & (poly_size - 1) == 0
+    num_vars = poly_size.bit_length() - 1
+    n_0 = min(20, (1 << num_vars) - 1)
+    assert (1 << num_vars) > n_0
+    row_len = raa_row_len(poly_size)  # the same isqrt().next_power_of_two() (code.rs:127)
+    cw = row_len * rep
+    a = sparse_matrix_sample_new(cw // 2, row_len, row_len // 2, transcript)
+    b = sparse_matrix_sample_new(cw // 2, row_len, row_len // 2, transcript)
+    return row_len, cw, a, b
+
+
+def sparse_mat_vec(n: int, d: int, cols, coef, vec: list[int]) -> list[int]:
+    """SparseMatrixZ::mat_vec_mul (code.rs:299-321), exact Python ints"""
+    return [sum(coef[i * d + k] * vec[cols[i * d + k]] for k in range(d)) for i in range(n)]
+
+
+def sparse_encode_row(row: list[int], n: int, d: int, a, b) -> list[int]:
+    """ZipLinearCode::encode_wide (code.rs:186-201)"""
+    return sparse_mat_vec(n, d, a[0], a[1], row) + sparse_mat_vec(n, d, b[0], b[1], row)

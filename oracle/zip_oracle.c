@@ -573,3 +573,112 @@ int zo_commit_mt(const uint64_t *evals, size_t num_rows, size_t row_len, int in_
     free(jobs);
     return rc;
 }
+
+/* ---- ZipLinearCode (zip/code.rs:77-215): the sparse code.  The two sampled matrices are INPUTS here, like the RAA
+ * permutations: `cols`/`coef` are SparseMatrixZ::cells (code.rs:271-296) in order, d cells per matrix row. ---- */
+
+/* acc += coef * sext(v)   (mod 2^(64*out_limbs)); expand::<L,M>(coeff) * expand::<N,M>(value), code.rs:314 */
+static void zo_mul_add(uint64_t *acc, int out_limbs, const uint64_t *v, int in_limbs, int64_t coef) {
+    uint64_t w[16], prod[16];
+    zo_widen(v, in_limbs, w, out_limbs);
+    uint64_t mag = coef < 0 ? (uint64_t)0 - (uint64_t)coef : (uint64_t)coef;
+    unsigned __int128 carry = 0;
+    for (int i = 0; i < out_limbs; i++) {
+        unsigned __int128 t = (unsigned __int128)w[i] * mag + carry;
+        prod[i] = (uint64_t)t;
+        carry = t >> 64;
+    }
+    if (coef < 0) { /* two's complement negate */
+        uint64_t c = 1;
+        for (int i = 0; i < out_limbs; i++) {
+            uint64_t x = ~prod[i] + c;
+            c = (c && x == 0) ? 1 : 0;
+            prod[i] = x;
+        }
+    }
+    uint64_t c = 0;
+    for (int i = 0; i < out_limbs; i++) {
+        unsigned __int128 t = (unsigned __int128)acc[i] + prod[i] + c;
+        acc[i] = (uint64_t)t;
+        c = (uint64_t)(t >> 64);
+    }
+}
+
+/* SparseMatrixZ::mat_vec_mul (code.rs:299-321) */
+int zo_sparse_mat_vec(size_t n, size_t m, size_t d, const uint32_t *cols, const int64_t *coef,
+                      const uint64_t *vec, int in_limbs, uint64_t *out, int out_limbs) {
+    if (out_limbs > 16 || in_limbs > out_limbs) return -2;
+    for (size_t i = 0; i < n; i++) {
+        uint64_t *acc = out + i * out_limbs;
+        memset(acc, 0, 8 * (size_t)out_limbs);
+        for (size_t k = 0; k < d; k++) {
+            uint32_t c = cols[i * d + k];
+            if (c >= m) return -2;
+            zo_mul_add(acc, out_limbs, vec + (size_t)c * in_limbs, in_limbs, coef[i * d + k]);
+        }
+    }
+    return 0;
+}
+
+typedef struct {
+    const uint64_t *evals;
+    size_t row_begin, row_end, row_len, n, d;
+    int in_limbs, out_limbs, rc;
+    const uint32_t *cols_a, *cols_b;
+    const int64_t *coef_a, *coef_b;
+    uint64_t *rows_out;
+    uint8_t *layers_out, *roots_out;
+} zo_sparse_job;
+
+static void *zo_sparse_worker(void *arg) {
+    zo_sparse_job *j = (zo_sparse_job *)arg;
+    size_t cw = 2 * j->n, depth = ilog2_sz(next_pow2_sz(cw));
+    size_t per_row = ((size_t)2 << depth) - 2;
+    uint64_t *rowbuf = j->rows_out ? 0 : (uint64_t *)malloc(cw * j->out_limbs * 8);
+    for (size_t r = j->row_begin; r < j->row_end; r++) {
+        const uint64_t *row = j->evals + r * j->row_len * j->in_limbs;
+        uint64_t *out = j->rows_out ? j->rows_out + r * cw * j->out_limbs : rowbuf;
+        /* encode_wide code.rs:186-201: a.mat_vec_mul(row) then b.mat_vec_mul(row) */
+        if (zo_sparse_mat_vec(j->n, j->row_len, j->d, j->cols_a, j->coef_a, row, j->in_limbs, out, j->out_limbs) ||
+            zo_sparse_mat_vec(j->n, j->row_len, j->d, j->cols_b, j->coef_b, row, j->in_limbs,
+                              out + j->n * j->out_limbs, j->out_limbs))
+            j->rc = -2;
+        if (j->roots_out && cw == ((size_t)1 << depth) &&
+            zo_merkle_tree_new(depth, out, cw, j->out_limbs,
+                               j->layers_out ? j->layers_out + r * per_row * 32 : 0, j->roots_out + 32 * r))
+            j->rc = -2;
+    }
+    free(rowbuf);
+    return 0;
+}
+
+/* encode_rows (commit.rs:158-183) + one MerkleTree per row (commit.rs:71-74) with ZipLinearCode as the code.
+ * n = codeword_len/2 matrix rows, d cells per row; roots_out NULL = encode only. */
+int zo_sparse_commit_mt(const uint64_t *evals, size_t num_rows, size_t row_len, int in_limbs, size_t n, size_t d,
+                        const uint32_t *cols_a, const int64_t *coef_a, const uint32_t *cols_b, const int64_t *coef_b,
+                        int out_limbs, uint64_t *rows_out, uint8_t *layers_out, uint8_t *roots_out, int threads) {
+    if (num_rows == 0) return 0;
+    if (threads < 1) threads = 1;
+    if ((size_t)threads > num_rows) threads = (int)num_rows;
+    size_t rows_per_thread = (num_rows + threads - 1) / threads;
+    pthread_t *tid = (pthread_t *)malloc(sizeof(pthread_t) * threads);
+    zo_sparse_job *jobs = (zo_sparse_job *)calloc(threads, sizeof(zo_sparse_job));
+    int rc = 0, started = 0;
+    for (int t = 0; t < threads; t++) {
+        size_t b = (size_t)t * rows_per_thread, e = b + rows_per_thread;
+        if (b >= num_rows) break;
+        if (e > num_rows) e = num_rows;
+        zo_sparse_job j = {evals, b, e, row_len, n, d, in_limbs, out_limbs, 0, cols_a, cols_b, coef_a, coef_b,
+                           rows_out, layers_out, roots_out};
+        jobs[t] = j;
+        pthread_create(&tid[t], 0, zo_sparse_worker, &jobs[t]);
+        started++;
+    }
+    for (int t = 0; t < started; t++) {
+        pthread_join(tid[t], 0);
+        if (jobs[t].rc) rc = jobs[t].rc;
+    }
+    free(tid);
+    free(jobs);
+    return rc;
+}

@@ -87,6 +87,17 @@ int zo_commit_mt(const uint64_t *evals, size_t num_rows, size_t row_len, int in_
                  uint64_t seed1, uint64_t seed2, const uint32_t *perm1, const uint32_t *perm2, int out_limbs,
                  uint64_t *rows_out, uint8_t *layers_out, uint8_t *roots_out, int threads, int faithful);
 
+/* ---- ZipLinearCode, the sparse code (zip/code.rs:77-215).  The two sampled matrices are inputs:
+ * cols/coef = SparseMatrixZ::cells (code.rs:271-296) in order, d cells per matrix row, n = codeword_len/2 rows.
+ * Coefficients are passed as i64 (KeccakTranscript draws 0/1, transcript.rs:176-181; the tests' MockTranscript
+ * a counter, pcs/tests.rs:30-33).  Arithmetic is mod 2^(64*out_limbs); the reference's checked ops never wrap
+ * for the sizes it is used at. ---- */
+int zo_sparse_mat_vec(size_t n, size_t m, size_t d, const uint32_t *cols, const int64_t *coef,
+                      const uint64_t *vec, int in_limbs, uint64_t *out, int out_limbs);          /* code.rs:299-321 */
+int zo_sparse_commit_mt(const uint64_t *evals, size_t num_rows, size_t row_len, int in_limbs, size_t n, size_t d,
+                        const uint32_t *cols_a, const int64_t *coef_a, const uint32_t *cols_b, const int64_t *coef_b,
+                        int out_limbs, uint64_t *rows_out, uint8_t *layers_out, uint8_t *roots_out, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -157,3 +157,41 @@ def test_shard_range_partitions():
             for (b0, c0), (b1, _) in zip(spans, spans[1:]):
                 assert b0 + c0 == b1
             assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def test_product_transcript_equals_oracle_transcript():
+    """the host mirror's incremental Keccak sponge against the oracle's one-shot Keccak (pinned to hashlib there)"""
+    from oracle import pyoracle as po
+    from zinc_b200 import KeccakTranscript
+    from zinc_b200.transcript import _Sponge, keccak256
+
+    for n in (0, 1, 135, 136, 137, 271, 272, 273, 1000):
+        data = bytes((7 * i + 1) % 256 for i in range(n))
+        sp = _Sponge()
+        sp.update(data[:n // 3])
+        sp.update(data[n // 3:])
+        assert sp.digest() == keccak256(data) == po.keccak256(data), n
+    a, b = KeccakTranscript(), po.KeccakTranscript()
+    a.absorb(b"zinc" * 50)
+    b.absorb(b"zinc" * 50)
+    for _ in range(40):
+        assert a.get_usize_in_range(3, 67) == b.get_usize_in_range(3, 67)
+        assert a.get_encoding_element() == b.get_encoding_element()
+    assert a.get_u64() == b.get_u64()
+
+
+def test_zip_linear_code_new_mirrors_reference():
+    """ZipLinearCode::new (code.rs:100-147) over both transcripts: shapes and sampled cells equal the oracle's"""
+    from oracle import pyoracle as po
+    from zinc_b200 import DefaultLinearCodeSpec, KeccakTranscript, MockTranscript, ZipLinearCode
+
+    for poly_size, T, OT in ((16, MockTranscript, po.MockTranscript), (1 << 7, KeccakTranscript, po.KeccakTranscript)):
+        code = ZipLinearCode.new(DefaultLinearCodeSpec(), poly_size, T())
+        row_len, cw, a, b = po.zip_linear_code_new(poly_size, OT())
+        assert (code.row_len(), code.codeword_len()) == (row_len, cw)
+        assert code.num_column_opening() == 1000 and code.num_proximity_testing() == 1
+        assert code.a.cols.tolist() == a[0] and code.a.coef.tolist() == a[1]
+        assert code.b.cols.tolist() == b[0] and code.b.coef.tolist() == b[1]
+        assert code.a.d == row_len // 2 and code.a.n == cw // 2
+    with pytest.raises(AssertionError):
+        ZipLinearCode.new(DefaultLinearCodeSpec(), 12, MockTranscript())  # code.rs:105 poly_size.is_power_of_two()

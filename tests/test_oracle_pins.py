@@ -308,3 +308,72 @@ def test_linearity_and_zero(oracle):
     ea, eb = po.encode_row_perm(a, 2, p1, p2), po.encode_row_perm(b, 2, p1, p2)
     assert po.encode_row_perm([3 * x + 5 * y for x, y in zip(a, b)], 2, p1, p2) == [3 * x + 5 * y for x, y in zip(ea, eb)]
     assert po.encode_row_perm([0] * 4, 2, p1, p2) == [0] * 8
+
+
+# ---- ZipLinearCode, the sparse code (zip/code.rs:77-215) --------------------------------------------------
+def _random_sparse(rng, n, m, d, lo, hi):
+    cols = np.stack([np.sort(rng.choice(m, size=d, replace=False)) for _ in range(n)]).astype(np.uint32).reshape(-1)
+    coef = rng.integers(lo, hi, size=n * d, endpoint=True).astype(np.int64)
+    return cols, coef
+
+
+@pytest.mark.parametrize("in_limbs,out_limbs", [(1, 4), (2, 8), (1, 2)])
+def test_sparse_python_equals_c(oracle, in_limbs, out_limbs):
+    from oracle import pyoracle as po
+
+    rng = np.random.default_rng(11 + in_limbs)
+    row_len, n, d, num_rows = 16, 16, 8, 3
+    a = _random_sparse(rng, n, row_len, d, -(1 << 40), 1 << 40)
+    b = _random_sparse(rng, n, row_len, d, -3, 3)
+    evals = [int(x) for x in rng.integers(-(1 << 63), (1 << 63) - 1, size=num_rows * row_len)]
+    if in_limbs == 2:
+        evals = [v * ((1 << 62) + 12345) for v in evals]
+    if out_limbs == 2:
+        a = (a[0], (a[1] % 7).astype(np.int64))  # keep the sums inside 128 bits
+    rc, rows, _, roots = oracle.sparse_commit(u64(evals, in_limbs), num_rows, row_len, n, d, a[0], a[1], b[0], b[1],
+                                              in_limbs, out_limbs, want_layers=False, threads=2)
+    assert rc == 0
+    want = []
+    for r in range(num_rows):
+        want += po.sparse_encode_row(evals[r * row_len:(r + 1) * row_len], n, d,
+                                     (a[0].tolist(), a[1].tolist()), (b[0].tolist(), b[1].tolist()))
+    assert np.array_equal(rows, u64(want, out_limbs))
+
+
+def test_sparse_golden_vectors(oracle):
+    blake3 = pytest.importorskip("blake3")
+    with open(os.path.join(GOLD, "sparse_vectors.json")) as f:
+        fixtures = json.load(f)
+    assert len(fixtures) == 9
+    for fx in fixtures:
+        evals = u64([int(v) for v in fx["evals"]])
+        rc, rows, layers, roots = oracle.sparse_commit(evals, fx["num_rows"], fx["row_len"], fx["cw"] // 2, fx["cells_per_row"],
+                                                       fx["cols_a"], fx["coef_a"], fx["cols_b"], fx["coef_b"])
+        assert rc == 0
+        assert blake3.blake3(rows.tobytes()).hexdigest() == fx["rows_blake3"], (fx["nv"], fx["transcript"])
+        assert blake3.blake3(layers.tobytes()).hexdigest() == fx["layers_blake3"]
+        assert roots.tobytes().hex() == "".join(fx["roots"])
+
+
+def test_mock_transcript_sparse_matrix_shape():
+    """pcs/tests.rs:24-56 by hand: every sample_unique_columns bumps the counter once and takes the first d columns;
+    every encoding element is the next counter value."""
+    from oracle import pyoracle as po
+
+    row_len, cw, a, b = po.zip_linear_code_new(16, po.MockTranscript())
+    assert (row_len, cw) == (4, 8)
+    assert a[0] == [0, 1] * 4 and a[1] == [2, 3, 5, 6, 8, 9, 11, 12]
+    assert b[0] == [0, 1] * 4 and b[1] == [14, 15, 17, 18, 20, 21, 23, 24]
+
+
+def test_keccak_encoding_elements_repeat_within_a_row():
+    """transcript.rs:176-181: get_encoding_element does not advance the sponge, so all cells of a matrix row carry
+    the same bit -- restated faithfully, not `fixed`."""
+    from oracle import pyoracle as po
+
+    _, _, a, b = po.zip_linear_code_new(1 << 8, po.KeccakTranscript())
+    d = 8
+    for coef in (a[1], b[1]):
+        for i in range(0, len(coef), d):
+            assert len(set(coef[i:i + d])) == 1
+        assert set(coef) == {0, 1}

@@ -19,6 +19,8 @@ from .zip import (  # noqa: F401
     RaaCode,
     RandomFieldZipTypes,
     ResidentZipData,
+    SparseMatrixZ,
+    ZipLinearCode,
     ZipTypes,
     default_context,
     shuffle_seeded_indices,

@@ -34,6 +34,8 @@ SIGNATURES = {
     "zipgpu_num_rows": (sz, [sz, sz]),
     "zipgpu_raa_codeword_width_bits": (i32, [i32, sz, sz]),
     "zipgpu_code_create": (i32, [vp, sz, sz, i32, i32, vp, vp, C.POINTER(vp)]),
+    "zipgpu_sparse_code_create": (i32, [vp, sz, sz, sz, i32, i32, vp, vp, vp, vp, C.POINTER(vp)]),
+    "zipgpu_code_sparse_kind": (i32, [vp]),
     "zipgpu_code_destroy": (None, [vp]),
     "zipgpu_code_row_len": (sz, [vp]),
     "zipgpu_code_codeword_len": (sz, [vp]),

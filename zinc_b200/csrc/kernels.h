@@ -77,6 +77,28 @@ struct CombineArgs {
 size_t combine_rows_scratch_bytes(uint32_t num_rows, uint32_t row_len);
 cudaError_t launch_combine_rows(const CombineArgs &a, int *launches);
 
+// ---- K6: ZipLinearCode (sparse code) encoder (sparse_encode.cu) ----
+struct SparseEncodeArgs {
+    const uint64_t *evals;   // [num_rows][row_len] Int<in_limbs>
+    uint64_t *rows_out;      // [num_rows][cw] Int<out_limbs>
+    uint32_t num_rows, row_len, cw;
+    int in_limbs, out_limbs;
+    int num_sms;
+    // general coefficients: ELL tables transposed to [d][cw] (cell k of codeword entry j at k*cw + j)
+    const uint32_t *cols_t = nullptr;
+    const int64_t *coef_t = nullptr;
+    uint32_t d = 0;
+    // all coefficients 0/1 and a shape sparse_gemm_supported() accepts: dense [cw][row_len] bytes, cells per entry,
+    // scratch of sparse_planes_bytes()
+    const uint8_t *dense = nullptr;
+    const uint32_t *nnz = nullptr;
+    uint8_t *planes = nullptr;
+    cudaStream_t stream;
+};
+bool sparse_gemm_supported(int in_limbs, int out_limbs, uint32_t row_len, uint32_t cw);
+size_t sparse_planes_bytes(uint32_t num_rows, uint32_t row_len, int in_limbs);
+cudaError_t launch_sparse_encode(const SparseEncodeArgs &a, int *launches);
+
 // ---- INT32 micro-benchmark (microbench.cu) ----
 cudaError_t launch_microbench_int32(int kind, int iters, int num_sms, cudaStream_t stream, uint32_t *d_sink,
                                     double *lane_ops);

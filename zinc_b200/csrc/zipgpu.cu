@@ -80,6 +80,14 @@ struct zipgpu_code {
     int fused_levels;  // Merkle levels the fused commit kernel produces (0: no fused variant for this shape)
     uint16_t *d_tab1, *d_tab2;  // pre-translated gather tables (raa_encode.cu)
     uint8_t *d_colw;
+    // ZipLinearCode (zipgpu_sparse_code_create): either the ELL tables of the generic kernel or the dense 0/1 matrix
+    // of the tensor-core kernel (sparse_encode.cu)
+    bool sparse = false;
+    uint32_t sp_d = 0;
+    uint32_t *d_sp_cols = nullptr;
+    int64_t *d_sp_coef = nullptr;
+    uint8_t *d_sp_dense = nullptr;
+    uint32_t *d_sp_bias = nullptr;
 };
 
 struct zipgpu_data {
@@ -447,6 +455,98 @@ extern "C" int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t rep, i
     return ZIPGPU_OK;
 }
 
+// ZipLinearCode::new's product (zip/code.rs:100-147): the two sampled matrices are inputs, see include/zipgpu.h
+extern "C" int zipgpu_sparse_code_create(zipgpu_ctx *ctx, size_t row_len, size_t codeword_len, size_t cells_per_row,
+                                         int in_limbs, int out_limbs, const uint32_t *cols_a, const int64_t *coef_a,
+                                         const uint32_t *cols_b, const int64_t *coef_b, zipgpu_code **out) {
+    if (!out) return fail(ZIPGPU_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!ctx || !cols_a || !coef_a || !cols_b || !coef_b) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (row_len == 0 || codeword_len == 0 || (codeword_len & 1))
+        return fail(ZIPGPU_ERR_INVALID, "row_len must be positive and codeword_len a positive even number");
+    if (cells_per_row == 0 || cells_per_row > row_len)
+        return fail(ZIPGPU_ERR_INVALID, "cells_per_row must be in [1, row_len]");
+    if (in_limbs < 1 || out_limbs < in_limbs || out_limbs > 8)
+        return fail(ZIPGPU_ERR_INVALID, "need 1 <= in_limbs <= out_limbs <= 8");
+    if (codeword_len > (1u << 24) || row_len > (1u << 24)) return fail(ZIPGPU_ERR_UNSUPPORTED, "codeword longer than 2^24");
+    const size_t n = codeword_len / 2, d = cells_per_row, cw = codeword_len;
+    // the tensor-core kernel takes coefficients 0..cmax with 255*cmax*row_len < 2^31 (exact s32 accumulation)
+    int64_t cmin = 0, cmax = 0;
+    for (size_t i = 0; i < n * d; i++) {
+        if (cols_a[i] >= row_len || cols_b[i] >= row_len)
+            return fail(ZIPGPU_ERR_INVALID, "sparse matrix column index out of range");
+        cmin = std::min(cmin, std::min(coef_a[i], coef_b[i]));
+        cmax = std::max(cmax, std::max(coef_a[i], coef_b[i]));
+    }
+    bool dense = cmin >= 0 && cmax <= 255 && (uint64_t)255 * (uint64_t)std::max<int64_t>(cmax, 1) * row_len < (1ull << 31) &&
+                 sparse_gemm_supported(in_limbs, out_limbs, (uint32_t)row_len, (uint32_t)cw) && !getenv("ZIPGPU_SPARSE_GENERIC");
+    std::vector<uint8_t> hd;
+    std::vector<uint32_t> hbias;
+    if (dense) {
+        hd.assign(cw * row_len, 0);
+        hbias.assign(cw, 0);
+        for (size_t j = 0; j < cw && dense; j++) {
+            const uint32_t *cols = j < n ? cols_a + j * d : cols_b + (j - n) * d;
+            const int64_t *coef = j < n ? coef_a + j * d : coef_b + (j - n) * d;
+            for (size_t k = 0; k < d; k++) {
+                const uint32_t v = hd[j * row_len + cols[k]] + (uint32_t)coef[k];  // repeated columns add up
+                if (v > (uint32_t)std::max<int64_t>(cmax, 1)) { dense = false; break; }
+                hd[j * row_len + cols[k]] = (uint8_t)v;
+                hbias[j] += (uint32_t)coef[k];
+            }
+        }
+    }
+    API_LOCK(ctx);
+    CU(cudaSetDevice(ctx->device));
+    zipgpu_code *c = new (std::nothrow) zipgpu_code();
+    if (!c) return fail(ZIPGPU_ERR_NOMEM, "host allocation failed");
+    c->ctx = ctx;
+    c->row_len = row_len;
+    c->rep = cw / row_len;
+    c->cw = cw;
+    c->in_limbs = in_limbs;
+    c->out_limbs = out_limbs;
+    c->depth = is_pow2(cw) ? ilog2(cw) : -1;
+    c->fused_levels = 0;
+    c->d_tab1 = c->d_tab2 = nullptr;
+    c->d_colw = nullptr;
+    c->sparse = true;
+    c->sp_d = (uint32_t)d;
+    cudaError_t e = cudaSuccess;
+    if (dense) {
+        if ((e = cudaMalloc(&c->d_sp_dense, cw * row_len)) == cudaSuccess && (e = cudaMalloc(&c->d_sp_bias, cw * 4)) == cudaSuccess &&
+            (e = cudaMemcpy(c->d_sp_dense, hd.data(), cw * row_len, cudaMemcpyHostToDevice)) == cudaSuccess)
+            e = cudaMemcpy(c->d_sp_bias, hbias.data(), cw * 4, cudaMemcpyHostToDevice);
+    } else {
+        // ELL, transposed to [d][cw] so that a warp's 32 codeword entries read consecutive words
+        std::vector<uint32_t> tc(d * cw);
+        std::vector<int64_t> tf(d * cw);
+        for (size_t j = 0; j < cw; j++) {
+            const uint32_t *cols = j < n ? cols_a + j * d : cols_b + (j - n) * d;
+            const int64_t *coef = j < n ? coef_a + j * d : coef_b + (j - n) * d;
+            for (size_t k = 0; k < d; k++) {
+                tc[k * cw + j] = cols[k];
+                tf[k * cw + j] = coef[k];
+            }
+        }
+        if ((e = cudaMalloc(&c->d_sp_cols, d * cw * 4)) == cudaSuccess && (e = cudaMalloc(&c->d_sp_coef, d * cw * 8)) == cudaSuccess &&
+            (e = cudaMemcpy(c->d_sp_cols, tc.data(), d * cw * 4, cudaMemcpyHostToDevice)) == cudaSuccess)
+            e = cudaMemcpy(c->d_sp_coef, tf.data(), d * cw * 8, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(c->d_sp_dense);
+        cudaFree(c->d_sp_bias);
+        cudaFree(c->d_sp_cols);
+        cudaFree(c->d_sp_coef);
+        delete c;
+        return cuda_fail(e, "sparse code tables");
+    }
+    *out = c;
+    return ZIPGPU_OK;
+}
+/* 1 when the code runs on the tensor-core kernel (coefficients 0..255 and a tileable shape), 0 generic, -1 not sparse */
+extern "C" int zipgpu_code_sparse_kind(const zipgpu_code *c) { return !c || !c->sparse ? -1 : c->d_sp_dense ? 1 : 0; }
+
 extern "C" void zipgpu_code_destroy(zipgpu_code *c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
@@ -454,6 +554,10 @@ extern "C" void zipgpu_code_destroy(zipgpu_code *c) {
     cudaFree(c->d_tab1);
     cudaFree(c->d_tab2);
     cudaFree(c->d_colw);
+    cudaFree(c->d_sp_dense);
+    cudaFree(c->d_sp_bias);
+    cudaFree(c->d_sp_cols);
+    cudaFree(c->d_sp_coef);
     delete c;
 }
 extern "C" size_t zipgpu_code_row_len(const zipgpu_code *c) { return c ? c->row_len : 0; }
@@ -492,6 +596,33 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     if (num_rows > 0xffffffffull) return fail(ZIPGPU_ERR_UNSUPPORTED, "too many rows");
     int rc;
     if ((rc = check_align16(d_evals, "evals")) || (rc = check_align16(d_rows, "rows_out"))) return rc;
+    if (code->sparse) {
+        if (fuse_layers || evals_copy) return fail(ZIPGPU_ERR_INVALID, "the sparse code has no fused commit kernel");
+        zipgpu_ctx *ctx = code->ctx;
+        SparseEncodeArgs sa;
+        sa.evals = d_evals;
+        sa.rows_out = d_rows;
+        sa.num_rows = (uint32_t)num_rows;
+        sa.row_len = (uint32_t)code->row_len;
+        sa.cw = (uint32_t)code->cw;
+        sa.in_limbs = code->in_limbs;
+        sa.out_limbs = code->out_limbs;
+        sa.num_sms = ctx->num_sms;
+        sa.cols_t = code->d_sp_cols;
+        sa.coef_t = code->d_sp_coef;
+        sa.d = code->sp_d;
+        sa.dense = code->d_sp_dense;
+        sa.nnz = code->d_sp_bias;
+        sa.stream = s;
+        DevGuard guard(ctx, s);
+        if (sa.dense) DEV_ALLOC(ctx, &sa.planes, sparse_planes_bytes(sa.num_rows, sa.row_len, sa.in_limbs), s);
+        int n = 0;
+        cudaError_t e = launch_sparse_encode(sa, &n);
+        if (e != cudaSuccess) return cuda_fail(e, "launch_sparse_encode");
+        ctx->launches += n;
+        if (sa.planes) DEV_FREE(ctx, sa.planes, s);
+        return ZIPGPU_OK;
+    }
     EncodeArgs a;
     a.evals = reinterpret_cast<const uint32_t *>(d_evals);
     a.rows_out = reinterpret_cast<uint32_t *>(d_rows);

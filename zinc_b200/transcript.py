@@ -51,27 +51,82 @@ def keccak256(data: bytes) -> bytes:
     return b"".join(st[i].to_bytes(8, "little") for i in range(4))
 
 
-class KeccakTranscript:
-    """src/transcript.rs:14-55 -- only the part RaaCode::new consumes (absorb / get_u64)."""
+class _Sponge:
+    """Incremental Keccak-256 (rate 136): `update`, `copy`, `digest` -- what the reference does with
+    `hasher.update`, `hasher.clone()` and `finalize()` (transcript.rs:35-55)."""
+
+    RATE = 136
 
     def __init__(self) -> None:
-        self._absorbed = bytearray()
+        self.st = [0] * 25
+        self.buf = bytearray()
+
+    def copy(self) -> "_Sponge":
+        c = _Sponge.__new__(_Sponge)
+        c.st = list(self.st)
+        c.buf = bytearray(self.buf)
+        return c
+
+    def _block(self, blk) -> None:
+        st = self.st
+        for i in range(self.RATE // 8):
+            st[i] ^= int.from_bytes(blk[8 * i:8 * i + 8], "little")
+        _permute(st)
+
+    def update(self, data: bytes) -> None:
+        self.buf += data
+        while len(self.buf) >= self.RATE:
+            self._block(self.buf[:self.RATE])
+            del self.buf[:self.RATE]
+
+    def digest(self) -> bytes:
+        c = self.copy()
+        blk = bytearray(c.buf) + b"\x01" + bytes(self.RATE - len(c.buf) - 1)
+        blk[-1] |= 0x80
+        c._block(blk)
+        return b"".join(c.st[i].to_bytes(8, "little") for i in range(4))
+
+
+class KeccakTranscript:
+    """src/transcript.rs:14-55,142-201 -- the draws RaaCode::new and ZipLinearCode::new make."""
+
+    def __init__(self) -> None:
+        self._hasher = _Sponge()
 
     def absorb(self, v: bytes) -> None:  # transcript.rs:35-37
-        self._absorbed += v
+        self._hasher.update(bytes(v))
 
     def get_random_bytes(self, length: int) -> bytes:  # transcript.rs:41-55
         out = bytearray()
         counter = 0
         while len(out) < length:
-            out += keccak256(bytes(self._absorbed) + counter.to_bytes(4, "big", signed=True))
+            h = self._hasher.copy()
+            h.update(counter.to_bytes(4, "big", signed=True))
+            out += h.digest()
             counter += 1
         return bytes(out[:length])
 
     def get_u64(self) -> int:  # transcript.rs:183-185 via get_integer_challenge::<Int<1>> (142-155)
         challenge = self.get_random_bytes(8)
-        self._absorbed += b"\x12" + challenge + b"\x34"
+        self._hasher.update(b"\x12" + challenge + b"\x34")
         return int.from_bytes(challenge, "little")
+
+    def get_usize_in_range(self, start: int, end: int) -> int:  # transcript.rs:161-172
+        challenge = self._hasher.digest()
+        self._hasher.update(b"\x88" + challenge + b"\x11")
+        return start + int.from_bytes(challenge[:8], "little") % (end - start)
+
+    def get_encoding_element(self) -> int:  # transcript.rs:176-181 (0 or 1; does not advance the state)
+        return self.get_random_bytes(1)[0] & 1
+
+    def sample_unique_columns(self, start: int, end: int, columns: set, count: int) -> int:  # transcript.rs:187-201
+        added = 0
+        while added < count:
+            candidate = self.get_usize_in_range(start, end)
+            if candidate not in columns:
+                columns.add(candidate)
+                added += 1
+        return added
 
 
 class MockTranscript:
@@ -83,3 +138,18 @@ class MockTranscript:
     def get_u64(self) -> int:
         self.counter += 1
         return self.counter
+
+    def get_encoding_element(self) -> int:
+        self.counter += 1
+        return self.counter
+
+    def sample_unique_columns(self, start: int, end: int, columns: set, count: int) -> int:
+        self.counter += 1
+        inserted = 0
+        for i in range(start, end):
+            if i not in columns:
+                columns.add(i)
+                inserted += 1
+                if inserted == count:
+                    break
+        return inserted

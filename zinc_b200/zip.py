@@ -256,6 +256,116 @@ class RaaCode:
         return self.encode_wide(row, self.zt.N, self.zt.M, ctx)
 
 
+class SparseMatrixZ:
+    """zip/code.rs:265-336: `n` rows of `d` (column, coefficient) cells over `m` columns; cells in row order."""
+
+    def __init__(self, n: int, m: int, d: int, cols, coef):
+        self.n, self.m, self.d = n, m, d
+        self.cols = np.ascontiguousarray(cols, dtype=np.uint32).reshape(n * d)
+        self.coef = np.ascontiguousarray(coef, dtype=np.int64).reshape(n * d)
+
+    @staticmethod
+    def sample_new(n: int, m: int, d: int, transcript) -> "SparseMatrixZ":
+        """code.rs:274-296: per row, d unique columns into a BTreeSet, then one encoding element per column in
+        ascending column order."""
+        cols = np.empty(n * d, dtype=np.uint32)
+        coef = np.empty(n * d, dtype=np.int64)
+        for i in range(n):
+            chosen: set = set()
+            transcript.sample_unique_columns(0, m, chosen, d)
+            for k, c in enumerate(sorted(chosen)):
+                cols[i * d + k] = c
+                coef[i * d + k] = transcript.get_encoding_element()
+        return SparseMatrixZ(n, m, d, cols, coef)
+
+    def to_dense(self) -> np.ndarray:
+        out = np.zeros((self.n, self.m), dtype=np.int64)
+        for i in range(self.n):
+            for k in range(self.d):
+                out[i, self.cols[i * self.d + k]] = self.coef[i * self.d + k]
+        return out
+
+
+class ZipLinearCode:
+    """zip/code.rs:77-215, the sparse code: encode_wide(row) = a.mat_vec_mul(row) ‖ b.mat_vec_mul(row).  The two
+    matrices are sampled on the host (they depend only on the transcript and the shape) and uploaded on first use."""
+
+    def __init__(self, zt: ZipTypes, row_len: int, codeword_len: int, num_column_opening: int,
+                 num_proximity_testing: int, a: SparseMatrixZ, b: SparseMatrixZ):
+        assert a.n == b.n == codeword_len // 2 and a.m == b.m == row_len and a.d == b.d
+        self.zt = zt
+        self._row_len = row_len
+        self._codeword_len = codeword_len
+        self.repetition_factor = codeword_len // row_len
+        self._num_column_opening = num_column_opening
+        self._num_proximity_testing = num_proximity_testing
+        self.a, self.b = a, b
+        self._native: dict[tuple[int, int, int], C.c_void_p] = {}
+
+    @staticmethod
+    def new(spec, poly_size: int, transcript, zt: ZipTypes = ZipTypes()) -> "ZipLinearCode":
+        """code.rs:100-147"""
+        assert poly_size & (poly_size - 1) == 0 and poly_size > 0
+        num_vars = poly_size.bit_length() - 1
+        n_0 = min(20, (1 << num_vars) - 1)
+        assert (1 << num_vars) > n_0
+        row_len = int(nat.lib().zipgpu_raa_row_len(1 << num_vars))  # the same isqrt().next_power_of_two(), code.rs:127
+        codeword_len = row_len * spec.repetition_factor()
+        num_proximity_testing = spec.num_proximity_testing(zt.N, row_len, n_0)
+        a = SparseMatrixZ.sample_new(codeword_len // 2, row_len, row_len // 2, transcript)  # code.rs:134,150-161
+        b = SparseMatrixZ.sample_new(codeword_len // 2, row_len, row_len // 2, transcript)
+        return ZipLinearCode(zt, row_len, codeword_len, spec.num_column_opening(), num_proximity_testing, a, b)
+
+    @staticmethod
+    def with_matrices(zt: ZipTypes, row_len: int, codeword_len: int, a: SparseMatrixZ, b: SparseMatrixZ) -> "ZipLinearCode":
+        """What a Rust host does: hand over the cells of the matrices `ZipLinearCode::new` sampled."""
+        return ZipLinearCode(zt, row_len, codeword_len, 1000, 1, a, b)
+
+    def row_len(self) -> int:
+        return self._row_len
+
+    def codeword_len(self) -> int:
+        return self._codeword_len
+
+    def num_column_opening(self) -> int:
+        return self._num_column_opening
+
+    def num_proximity_testing(self) -> int:
+        return self._num_proximity_testing
+
+    def native(self, ctx: Context, in_limbs: int, out_limbs: int) -> C.c_void_p:
+        key = (id(ctx), in_limbs, out_limbs)
+        h = self._native.get(key)
+        if h is None:
+            h = C.c_void_p()
+            nat.check(nat.lib().zipgpu_sparse_code_create(ctx.handle, self._row_len, self._codeword_len, self.a.d, in_limbs,
+                                                          out_limbs, nat.ptr(self.a.cols), nat.ptr(self.a.coef),
+                                                          nat.ptr(self.b.cols), nat.ptr(self.b.coef), C.byref(h)))
+            self._native[key] = h
+        return h
+
+    def kernel_kind(self, ctx: Context | None = None, in_limbs: int | None = None, out_limbs: int | None = None) -> str:
+        ctx = ctx or default_context()
+        k = nat.lib().zipgpu_code_sparse_kind(self.native(ctx, in_limbs or self.zt.N, out_limbs or self.zt.K))
+        return {1: "tensor", 0: "generic"}[k]
+
+    def encode_wide(self, row, in_limbs: int | None = None, out_limbs: int | None = None,
+                    ctx: Context | None = None) -> np.ndarray:
+        """code.rs:186-201 -> [cw, out_limbs] uint64"""
+        in_limbs = in_limbs or self.zt.N
+        out_limbs = out_limbs or self.zt.K
+        r = as_limbs(row, in_limbs)
+        assert r.shape[0] == self._row_len, "Row length must match the code's row length"  # code.rs:191-195
+        ctx = ctx or default_context()
+        out = np.empty((self._codeword_len, out_limbs), dtype=np.uint64)
+        nat.check(nat.lib().zipgpu_encode_rows(self.native(ctx, in_limbs, out_limbs), 1, nat.ptr(r), nat.ptr(out)))
+        return out
+
+    def encode(self, row, ctx: Context | None = None) -> np.ndarray:
+        """code.rs:35-37: encode == encode_wide::<N, M>"""
+        return self.encode_wide(row, self.zt.N, self.zt.M, ctx)
+
+
 @dataclass
 class MultilinearZipParams:
     """pcs/structs.rs:11-29"""
