@@ -36,6 +36,9 @@ def main():
         for w in WANT:
             if w in idx:
                 print(f"  {w:72s} {r[idx[w]]} {units[idx[w]]}")
+        for h in hdr:
+            if "pipe_tensor" in h and h not in WANT and ("pct_of_peak_sustained_active" in h):
+                print(f"  {h:72s} {r[idx[h]]} {units[idx[h]]}")
         stalls = []
         for h in hdr:
             if "issue_stalled" in h and h.endswith("per_issue_active.ratio"):

@@ -108,10 +108,14 @@ def test_generic_kernel_matches_oracle(row_len, num_rows, lo, hi, oracle, ctx, m
     check_against_oracle(code, evals, num_rows, oracle, ctx)
 
 
+@pytest.mark.parametrize("kernel", ["tcgen05", "mma_sync"])
 @pytest.mark.parametrize("row_len,num_rows,cmax", [(128, 16, 1), (128, 37, 1), (256, 100, 1), (512, 64, 255), (1024, 19, 7)])
-def test_tensor_kernel_matches_oracle(row_len, num_rows, cmax, oracle, ctx):
+def test_tensor_kernel_matches_oracle(row_len, num_rows, cmax, kernel, oracle, ctx, monkeypatch):
+    """both tensor-core kernels: tcgen05.mma.kind::i8 (default) and the mma.sync version of the same product"""
     from zinc_b200 import ZipLinearCode, ZipTypes
 
+    if kernel == "mma_sync":
+        monkeypatch.setenv("ZIPGPU_SPARSE_MMA_SYNC", "1")
     rng = np.random.default_rng(1000 + row_len + num_rows)
     cw, d = 2 * row_len, row_len // 2
     code = ZipLinearCode.with_matrices(ZipTypes(), row_len, cw, random_matrix(rng, cw // 2, row_len, d, 0, cmax),

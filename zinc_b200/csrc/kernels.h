@@ -93,8 +93,10 @@ struct SparseEncodeArgs {
     const uint8_t *dense = nullptr;
     const uint32_t *nnz = nullptr;
     uint8_t *planes = nullptr;
+    bool use_umma = true;    // tcgen05 kernel (sparse_umma.cu); false: the mma.sync kernel
     cudaStream_t stream;
 };
+cudaError_t launch_sparse_umma(const SparseEncodeArgs &a);  // GEMM stage only, planes already split
 bool sparse_gemm_supported(int in_limbs, int out_limbs, uint32_t row_len, uint32_t cw);
 size_t sparse_planes_bytes(uint32_t num_rows, uint32_t row_len, int in_limbs);
 cudaError_t launch_sparse_encode(const SparseEncodeArgs &a, int *launches);

@@ -12,7 +12,9 @@
 //    (x + 2^(64·in−1), so all bytes are unsigned); the product runs on the tensor cores as an exact u8×u8→s32 GEMM
 //    (mma.sync.m16n8k32; 255·row_len < 2^31), and the epilogue recombines the 8·in_limbs planes of an entry into the
 //    multi-limb integer, removes the bias (nnz[j]·2^(64·in−1)) and sign-extends to Int<out_limbs>.
-//    Tiles 128×128×128 bytes, 3-stage cp.async pipeline, XOR-swizzled 128-byte rows read with ldmatrix.
+//    Default: the tcgen05 kernel of sparse_umma.cu (TMA → shared memory → tcgen05.mma.kind::i8 → TMEM).  The kernel in
+//    this file is the mma.sync version of the same product (ZIPGPU_SPARSE_MMA_SYNC=1): tiles 128×128×128 bytes,
+//    3-stage cp.async pipeline, XOR-swizzled 128-byte rows read with ldmatrix.
 //  * sparse_generic_kernel -- arbitrary i64 coefficients (the reference tests' MockTranscript draws a counter,
 //    pcs/tests.rs:30-33) and the shapes the GEMM tiling does not cover (row_len or cw below 128): one thread per
 //    codeword entry walking an ELL table transposed so that a warp reads it coalesced.
@@ -295,6 +297,7 @@ static cudaError_t launch_gemm(const SparseEncodeArgs &a) {
     const uint32_t blocks = (uint32_t)((total + 255) / 256 < (size_t)a.num_sms * 16 ? (total + 255) / 256 : (size_t)a.num_sms * 16);
     split_planes_kernel<IN><<<blocks, 256, 0, a.stream>>>(a.evals, a.planes, a.num_rows, a.row_len);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (a.use_umma) return launch_sparse_umma(a);  // tcgen05 + TMA + TMEM (sparse_umma.cu)
     // grid.y is limited to 65535 tiles of GN plane rows: walk very tall matrices in row batches
     const uint32_t rows_per_tile = GN / (8 * IN), max_rows = 65535u * rows_per_tile;
     for (uint32_t r0 = 0; r0 < a.num_rows; r0 += max_rows) {

@@ -613,6 +613,7 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
         sa.d = code->sp_d;
         sa.dense = code->d_sp_dense;
         sa.nnz = code->d_sp_bias;
+        sa.use_umma = !getenv("ZIPGPU_SPARSE_MMA_SYNC");
         sa.stream = s;
         DevGuard guard(ctx, s);
         if (sa.dense) DEV_ALLOC(ctx, &sa.planes, sparse_planes_bytes(sa.num_rows, sa.row_len, sa.in_limbs), s);
