@@ -3,14 +3,15 @@
 //
 // Reference: ZipLinearCode::encode_wide src/zip/code.rs:186-201, SparseMatrixZ::mat_vec_mul code.rs:299-321.
 //
-// One CTA computes a 128 (codeword entries) × 256 (plane rows = 256/(8·in_limbs) evaluation rows) tile:
+// Persistent: one CTA per SM walks 128 (codeword entries) × 256 (plane rows = 256/(8·in_limbs) evaluation rows) tiles:
 //   warp 0   one lane drives TMA: per 128-byte K block, the 128×128 B tile of the coefficient matrix and the 256×128 B
 //            tile of the planes land in a 4-stage shared-memory ring (SWIZZLE_128B, K-major), completion on mbarriers;
-//   warp 1   one lane issues tcgen05.mma.kind::i8 (M128 × N256 × K32, u8·u8→s32) with the accumulator in TMEM
-//            (256 columns), tcgen05.commit releases ring slots and finally signals the epilogue;
+//   warp 1   one lane issues tcgen05.mma.kind::i8 (M128 × N256 × K32, u8·u8→s32) into one of two 256-column TMEM
+//            accumulators, tcgen05.commit releases ring slots and signals the epilogue at the end of a tile;
 //   warps 2-5 epilogue: TMEM lane = codeword entry, 8·in_limbs consecutive columns = the byte planes of one
 //            evaluation row, so a thread reads its planes with tcgen05.ld, recombines them into the multi-limb sum,
-//            removes the bias, sign-extends and stores Int<out_limbs> -- a warp writes 32 consecutive entries.
+//            removes the bias, sign-extends and stores Int<out_limbs> -- a warp writes 32 consecutive entries.  The
+//            epilogue of tile i runs while the MMAs of tile i+1 fill the other accumulator.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -23,12 +24,16 @@ namespace umma {
 constexpr int TM = 128, TN = 256, TK = 128, STAGES = 4;
 constexpr int A_BYTES = TM * TK, B_BYTES = TN * TK, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int THREADS = 192;
-constexpr int TMEM_COLS = 256;
+constexpr int TMEM_COLS = 512;  // two TN-column accumulators
+constexpr int EPI_THREADS = 128;
 constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -91,21 +96,20 @@ template <int IN>
 __global__ void __launch_bounds__(umma::THREADS, 1)
     sparse_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                        const uint32_t *__restrict__ bias, uint64_t *__restrict__ rows_out, uint32_t num_rows, uint32_t K,
-                       uint32_t cw, int out_limbs) {
+                       uint32_t cw, int out_limbs, uint32_t m_blocks, uint32_t num_tiles) {
     using namespace umma;
     constexpr int P = 8 * IN;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
-    const uint32_t bars = tiles + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], accum
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + (bars - raw) + 8 * (2 * STAGES + 1));
+    const uint32_t bars = tiles + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + (bars - raw) + 8 * (2 * STAGES + 4));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t m0 = blockIdx.x * TM;
-    const uint32_t n0 = blockIdx.y * TN;
     const uint32_t KT = K / TK;
     auto full = [&](int s) { return bars + 8 * s; };
     auto empty = [&](int s) { return bars + 8 * (STAGES + s); };
-    const uint32_t accum = bars + 8 * (2 * STAGES);
+    auto acc_full = [&](int b) { return bars + 8 * (2 * STAGES + b); };
+    auto acc_empty = [&](int b) { return bars + 8 * (2 * STAGES + 2 + b); };
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_a)) : "memory");
@@ -117,7 +121,10 @@ __global__ void __launch_bounds__(umma::THREADS, 1)
                 mbar_init(full(s), 1);
                 mbar_init(empty(s), 1);
             }
-            mbar_init(accum, 1);
+            for (int b = 0; b < 2; b++) {
+                mbar_init(acc_full(b), 1);
+                mbar_init(acc_empty(b), EPI_THREADS);
+            }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -130,91 +137,113 @@ __global__ void __launch_bounds__(umma::THREADS, 1)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // persistent: this CTA takes tiles blockIdx.x, blockIdx.x + gridDim.x, ...; consecutive tiles share the plane
+    // rows (n block), so the CTAs running at the same time read the same B tile out of L2
     if (warp == 0) {
         if (lane == 0) {
-            for (uint32_t kb = 0; kb < KT; kb++) {
-                const int s = kb % STAGES;
-                mbar_wait(empty(s), ((kb / STAGES) & 1) ^ 1);
-                mbar_expect_tx(full(s), STAGE_BYTES);
-                tma_load_2d(tiles + s * STAGE_BYTES, &tm_a, full(s), (int)(kb * TK), (int)m0);
-                tma_load_2d(tiles + s * STAGE_BYTES + A_BYTES, &tm_b, full(s), (int)(kb * TK), (int)n0);
+            uint32_t it = 0;
+            for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m0 = (int)((t % m_blocks) * TM), n0 = (int)((t / m_blocks) * TN);
+                for (uint32_t kb = 0; kb < KT; kb++, it++) {
+                    const int s = it % STAGES;
+                    mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(full(s), STAGE_BYTES);
+                    tma_load_2d(tiles + s * STAGE_BYTES, &tm_a, full(s), (int)(kb * TK), m0);
+                    tma_load_2d(tiles + s * STAGE_BYTES + A_BYTES, &tm_b, full(s), (int)(kb * TK), n0);
+                }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            for (uint32_t kb = 0; kb < KT; kb++) {
-                const int s = kb % STAGES;
-                mbar_wait(full(s), (kb / STAGES) & 1);
+            uint32_t it = 0, i = 0;
+            for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, i++) {
+                const uint32_t ab = i & 1;  // two accumulators of TN columns: the epilogue of a tile overlaps the next tile
+                mbar_wait(acc_empty(ab), ((i >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t a = tiles + s * STAGE_BYTES, b = a + A_BYTES;
+                const uint32_t d = tmem_base + ab * TN;
+                for (uint32_t kb = 0; kb < KT; kb++, it++) {
+                    const int s = it % STAGES;
+                    mbar_wait(full(s), (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a = tiles + s * STAGE_BYTES, b = a + A_BYTES;
 #pragma unroll
-                for (int k = 0; k < TK / 32; k++)
-                    mma_i8(tmem_base, smem_desc(a + k * 32), smem_desc(b + k * 32), UMMA_IDESC, (kb | (uint32_t)k) != 0);
-                tc_commit(empty(s));  // the slot is free once these MMAs have read it
+                    for (int k = 0; k < TK / 32; k++)
+                        mma_i8(d, smem_desc(a + k * 32), smem_desc(b + k * 32), UMMA_IDESC, (kb | (uint32_t)k) != 0);
+                    tc_commit(empty(s));  // the slot is free once these MMAs have read it
+                }
+                tc_commit(acc_full(ab));
             }
-            tc_commit(accum);
         }
         __syncwarp();
     } else {
-        mbar_wait(accum, 0);
-        tc_fence_after();
         const int q = warp & 3;  // a warp reads TMEM lanes 32*(warp % 4) ..
-        const uint32_t j = m0 + q * 32 + lane;
-        const uint32_t cnt = bias[j];
-        const uint64_t b_lo = (uint64_t)(cnt & 1) << 63, b_hi = (uint64_t)(cnt >> 1);
         constexpr int ROWS_PER_LD = 32 / P;
+        uint32_t i = 0;
+        for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, i++) {
+            const uint32_t m0 = (t % m_blocks) * TM, n0 = (t / m_blocks) * TN;
+            const uint32_t ab = i & 1;
+            const uint32_t j = m0 + q * 32 + lane;
+            const uint32_t cnt = bias[j];
+            const uint64_t b_lo = (uint64_t)(cnt & 1) << 63, b_hi = (uint64_t)(cnt >> 1);
+            mbar_wait(acc_full(ab), (i >> 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-        for (int g = 0; g < TN / 32; g++) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + g * 32, v);
+            for (int g = 0; g < TN / 32; g++) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * TN + g * 32, v);
+                if (g == TN / 32 - 1) {  // everything of this accumulator is in registers: hand it back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(acc_empty(ab));
+                }
 #pragma unroll
-            for (int e = 0; e < ROWS_PER_LD; e++) {
-                uint64_t limb[IN + 1];
+                for (int e = 0; e < ROWS_PER_LD; e++) {
+                    uint64_t limb[IN + 1];
 #pragma unroll
-                for (int i = 0; i <= IN; i++) limb[i] = 0;
+                    for (int l = 0; l <= IN; l++) limb[l] = 0;
 #pragma unroll
-                for (int ql = 0; ql < IN; ql++) {
-                    uint64_t lo = 0, hi = 0;
+                    for (int ql = 0; ql < IN; ql++) {
+                        uint64_t lo = 0, hi = 0;
 #pragma unroll
-                    for (int p = 0; p < 8; p++) {
-                        const uint64_t t = v[e * P + ql * 8 + p];  // < 2^31
-                        const uint64_t add = t << (8 * p);
-                        const uint64_t s = lo + add;
-                        hi += s < add;
-                        lo = s;
-                        if (8 * p > 32) hi += t >> (64 - 8 * p);
+                        for (int p = 0; p < 8; p++) {
+                            const uint64_t x = v[e * P + ql * 8 + p];  // < 2^31
+                            const uint64_t add = x << (8 * p);
+                            const uint64_t s = lo + add;
+                            hi += s < add;
+                            lo = s;
+                            if (8 * p > 32) hi += x >> (64 - 8 * p);
+                        }
+                        const uint64_t s = limb[ql] + lo;
+                        const uint64_t c = s < lo;
+                        limb[ql] = s;
+                        limb[ql + 1] += hi + c;
                     }
-                    const uint64_t s = limb[ql] + lo;
-                    const uint64_t c = s < lo;
-                    limb[ql] = s;
-                    limb[ql + 1] += hi + c;
-                }
-                {  // minus bias * 2^(64*IN - 1)
-                    const uint64_t d0 = limb[IN - 1] - b_lo;
-                    const uint64_t borrow = limb[IN - 1] < b_lo;
-                    limb[IN - 1] = d0;
-                    limb[IN] = limb[IN] - b_hi - borrow;
-                }
-                const uint64_t sign = (uint64_t)((int64_t)limb[IN] >> 63);
-                const size_t r = (size_t)n0 / P + (size_t)g * ROWS_PER_LD + e;
-                if (r < num_rows) {
-                    uint64_t *o = rows_out + (r * cw + j) * out_limbs;
-                    if (out_limbs == 4) {
-                        const uint64_t l2 = IN >= 2 ? limb[IN >= 2 ? 2 : 0] : sign;
-                        const uint32_t w[8] = {(uint32_t)limb[0], (uint32_t)(limb[0] >> 32), (uint32_t)limb[1],
-                                               (uint32_t)(limb[1] >> 32), (uint32_t)l2, (uint32_t)(l2 >> 32),
-                                               (uint32_t)sign, (uint32_t)sign};
-                        st_stream_v8(o, w);
-                    } else {
+                    {  // minus bias * 2^(64*IN - 1)
+                        const uint64_t d0 = limb[IN - 1] - b_lo;
+                        const uint64_t borrow = limb[IN - 1] < b_lo;
+                        limb[IN - 1] = d0;
+                        limb[IN] = limb[IN] - b_hi - borrow;
+                    }
+                    const uint64_t sign = (uint64_t)((int64_t)limb[IN] >> 63);
+                    const size_t r = (size_t)n0 / P + (size_t)g * ROWS_PER_LD + e;
+                    if (r < num_rows) {
+                        uint64_t *o = rows_out + (r * cw + j) * out_limbs;
+                        if (out_limbs == 4) {
+                            const uint64_t l2 = IN >= 2 ? limb[IN >= 2 ? 2 : 0] : sign;
+                            const uint32_t w[8] = {(uint32_t)limb[0], (uint32_t)(limb[0] >> 32), (uint32_t)limb[1],
+                                                   (uint32_t)(limb[1] >> 32), (uint32_t)l2, (uint32_t)(l2 >> 32),
+                                                   (uint32_t)sign, (uint32_t)sign};
+                            st_stream_v8(o, w);
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            if (i < out_limbs) {
-                                uint64_t x = sign;
+                            for (int l8 = 0; l8 < 8; l8++) {
+                                if (l8 < out_limbs) {
+                                    uint64_t x = sign;
 #pragma unroll
-                                for (int l = 0; l <= IN; l++)
-                                    if (l == i) x = limb[l];
-                                o[i] = x;
+                                    for (int l = 0; l <= IN; l++)
+                                        if (l == l8) x = limb[l];
+                                    o[l8] = x;
+                                }
                             }
                         }
                     }
@@ -258,7 +287,7 @@ template <int IN>
 static cudaError_t launch_umma_t(const SparseEncodeArgs &a) {
     cudaError_t e = cudaFuncSetAttribute(sparse_umma_kernel<IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::SMEM);
     if (e != cudaSuccess) return e;
-    const uint32_t rows_per_tile = umma::TN / (8 * IN), max_rows = 65535u * rows_per_tile;
+    const uint32_t rows_per_tile = umma::TN / (8 * IN), max_rows = 8192u * rows_per_tile;  // keeps num_tiles far below 2^32
     CUtensorMap tm_a;
     if (!make_map(&tm_a, a.dense, a.cw, a.row_len, umma::TM)) return cudaErrorNotSupported;
     for (uint32_t r0 = 0; r0 < a.num_rows; r0 += max_rows) {
@@ -266,9 +295,12 @@ static cudaError_t launch_umma_t(const SparseEncodeArgs &a) {
         CUtensorMap tm_b;
         if (!make_map(&tm_b, a.planes + (size_t)r0 * 8 * IN * a.row_len, (uint64_t)nr * 8 * IN, a.row_len, umma::TN))
             return cudaErrorNotSupported;
-        dim3 grid(a.cw / umma::TM, (nr + rows_per_tile - 1) / rows_per_tile);
+        const uint32_t m_blocks = a.cw / umma::TM, n_blocks = (nr + rows_per_tile - 1) / rows_per_tile;
+        const uint32_t num_tiles = m_blocks * n_blocks;
+        const uint32_t grid = num_tiles < (uint32_t)a.num_sms ? num_tiles : (uint32_t)a.num_sms;
         sparse_umma_kernel<IN><<<grid, umma::THREADS, umma::SMEM, a.stream>>>(
-            tm_a, tm_b, a.nnz, a.rows_out + (size_t)r0 * a.cw * a.out_limbs, nr, a.row_len, a.cw, a.out_limbs);
+            tm_a, tm_b, a.nnz, a.rows_out + (size_t)r0 * a.cw * a.out_limbs, nr, a.row_len, a.cw, a.out_limbs, m_blocks,
+            num_tiles);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     return cudaSuccess;
