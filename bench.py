@@ -429,6 +429,70 @@ def main():
             except Exception as ex:  # e.g. not enough memory for nv=26 next to the main buffers
                 sizes[f"nv{snv}"] = {"error": str(ex)[:200]}
 
+    # ---- the other LinearCode of the reference, ZipLinearCode (sparse code, zip/code.rs:77-215), same nv, same
+    #      buffers: 0/1 matrices with row_len/2 cells per row (every coefficient 1, the densest the reference samples),
+    #      tensor-core roofline for its GEMM and the CPU port on a bounded sample (rank 0, N = 1) ----
+    sparse_code = None
+    if rank == 0 and world == 1 and not args.no_sweep:
+        try:
+            from zinc_b200 import SparseMatrixZ, ZipLinearCode, ZipTypes
+            srng = np.random.default_rng(0x5A00 + nv)
+
+            def sample_matrix():
+                d_ = row_len // 2
+                cols = np.empty((cw // 2, d_), dtype=np.uint32)
+                for i_ in range(cw // 2):
+                    cols[i_] = np.sort(srng.permutation(row_len)[:d_])
+                return SparseMatrixZ(cw // 2, row_len, d_, cols, np.ones(cw // 2 * d_, dtype=np.int64))
+
+            scode = ZipLinearCode.with_matrices(ZipTypes(), row_len, cw, sample_matrix(), sample_matrix())
+            sh = scode.native(ctx, 1, 4)
+            s_run = lambda: nat.check(L.zipgpu_commit_device(sh, num_rows, d_evals.data_ptr(), d_rows.data_ptr(),
+                                                             d_layers.data_ptr(), d_roots.data_ptr(), sptr))
+            s_enc = lambda: nat.check(L.zipgpu_encode_rows_device(sh, num_rows, d_evals.data_ptr(), d_rows.data_ptr(), sptr))
+            res = {}
+            for name, fn in (("commit_ms", s_run), ("encode_ms", s_enc)):
+                for _ in range(3):
+                    fn()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a.record(stream)
+                for _ in range(10):
+                    fn()
+                b.record(stream)
+                torch.cuda.synchronize()
+                res[name] = a.elapsed_time(b) / 10
+            s_run()
+            torch.cuda.synchronize()
+            sparse_roots = d_roots.cpu().numpy().copy()
+            sparse_rows_head = d_rows[: 64 * cw * 4].cpu().numpy().view(np.uint64).copy()
+            ops = 2.0 * cw * row_len * num_rows * 8  # u8 x u8 multiply-adds x 2, 8 byte planes per evaluation
+            tops = ops / (res["encode_ms"] * 1e-3) / 1e12
+            sparse_code = {
+                "workload": f"ZipLinearCode commit, 2^{nv} Int<1> evals, two {cw // 2}x{row_len} 0/1 matrices, "
+                            f"{row_len // 2} cells per row", "kernel": scode.kernel_kind(ctx),
+                "commit_ms": res["commit_ms"], "encode_ms": res["encode_ms"],
+                "evals_per_s": n_evals / (res["commit_ms"] * 1e-3),
+                "roofline": {"kernel": "split_planes_kernel + sparse_umma_kernel", "bound": "tensor", "achieved": tops,
+                             "unit": "TOP/s", "ops_per_launch": ops},
+            }
+            if not args.no_cpu:
+                from oracle import cbind
+                threads = os.cpu_count() or 1
+                nr = min(num_rows, 64)
+                ma, mb = scode.a, scode.b
+                t0 = time.perf_counter()
+                rc, orows, _, oroots = cbind.sparse_commit(evals_h[: nr * row_len], nr, row_len, ma.n, ma.d, ma.cols, ma.coef,
+                                                           mb.cols, mb.coef, threads=threads)
+                dt = time.perf_counter() - t0
+                sparse_code["cpu_baseline"] = {
+                    "value": nr * row_len / dt, "unit": "evals/s", "cores": threads, "kind": "port",
+                    "sample": f"rows 0..{nr} of {num_rows} ({dt:.1f} s)",
+                    "rows_and_roots_match_gpu": bool(rc == 0 and np.array_equal(orows, sparse_rows_head[: nr * cw * 4]) and
+                                                     np.array_equal(oroots, sparse_roots[: nr * 32]))}
+        except Exception as ex:
+            sparse_code = {"error": str(ex)[:300]}
+
     # ---- CPU baseline on a bounded sample (rank 0, N = 1) ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -457,6 +521,11 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        if sparse_code and "roofline" in sparse_code:
+            # no measured int8 number exists: 2 x the measured dense bf16 rate (tcgen05 kind::i8 : kind::f16 = 2 : 1)
+            i8_peak = 2.0 * float(peaks.get("bf16_tflops", 1631.7))
+            sparse_code["roofline"].update({"peak": i8_peak, "frac": sparse_code["roofline"]["achieved"] / i8_peak,
+                                            "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (burst)"})
         enc_ms_avg = enc_ms.value / max(calls.value, 1)
         hash_ms_avg = hash_ms.value / max(calls.value, 1)
         enc_gbs = ENC_BYTES_PER_EVAL * n_evals / (enc_ms_avg * 1e-3) / 1e9
@@ -524,6 +593,7 @@ def main():
                 "share_of_step": hash_ms_avg / (hash_ms_avg + enc_ms_avg) if hash_ms_avg + enc_ms_avg > 0 else None,
             },
             "cpu_baseline": cpu_baseline,
+            "sparse_code": sparse_code,
             "sizes": sizes,
         }
         emit(line)
