@@ -465,7 +465,7 @@ def main():
             s_run()
             torch.cuda.synchronize()
             sparse_roots = d_roots.cpu().numpy().copy()
-            sparse_rows_head = d_rows[: 64 * cw * 4].cpu().numpy().view(np.uint64).copy()
+            sparse_rows_head = d_rows[: 256 * cw * 4].cpu().numpy().view(np.uint64).copy()
             ops = 2.0 * cw * row_len * num_rows * 8  # u8 x u8 multiply-adds x 2, 8 byte planes per evaluation
             tops = ops / (res["encode_ms"] * 1e-3) / 1e12
             sparse_code = {
@@ -479,7 +479,7 @@ def main():
             if not args.no_cpu:
                 from oracle import cbind
                 threads = os.cpu_count() or 1
-                nr = min(num_rows, 64)
+                nr = min(num_rows, 256)
                 ma, mb = scode.a, scode.b
                 t0 = time.perf_counter()
                 rc, orows, _, oroots = cbind.sparse_commit(evals_h[: nr * row_len], nr, row_len, ma.n, ma.d, ma.cols, ma.coef,
