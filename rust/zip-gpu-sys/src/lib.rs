@@ -29,6 +29,11 @@ unsafe extern "C" {
     pub fn zipgpu_code_create(ctx: *mut zipgpu_ctx, row_len: usize, repetition_factor: usize, in_limbs: c_int,
                               out_limbs: c_int, perm1: *const u32, perm2: *const u32,
                               out: *mut *mut zipgpu_code) -> c_int;
+    // ZipLinearCode (code.rs:100-147): cells of the two sampled sparse matrices in, same handle type out
+    pub fn zipgpu_sparse_code_create(ctx: *mut zipgpu_ctx, row_len: usize, codeword_len: usize, cells_per_row: usize,
+                                     in_limbs: c_int, out_limbs: c_int, cols_a: *const u32, coef_a: *const i64,
+                                     cols_b: *const u32, coef_b: *const i64, out: *mut *mut zipgpu_code) -> c_int;
+    pub fn zipgpu_code_sparse_kind(code: *const zipgpu_code) -> c_int;
     pub fn zipgpu_code_destroy(code: *mut zipgpu_code);
     // encode_rows / commit_no_merkle (commit.rs:104-119,158-183)
     pub fn zipgpu_encode_rows(code: *mut zipgpu_code, num_rows: usize, evals: *const u64, rows_out: *mut u64) -> c_int;
