@@ -92,11 +92,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = u8, both K-major, N = 256, M = 128
 constexpr uint32_t UMMA_IDESC = (2u << 4) | ((uint32_t)(umma::TN >> 3) << 17) | ((uint32_t)(umma::TM >> 4) << 24);
 
+// Tile order: bands of BAND m-blocks; inside a band the m-block runs fastest, then the n-block.  The ~148 tiles in
+// flight then cover BAND slices of the coefficient matrix and ~148/BAND plane tiles, both L2-resident, instead of one
+// sweep over the whole matrix per plane tile (which at nv = 26 is 128 MiB > L2 and made the kernel DRAM-bound).
+// A matrix that fits L2 with room to spare is not banded (BAND = m_blocks): all its m-blocks then share each plane tile.
+__device__ __forceinline__ void tile_coords(uint32_t t, uint32_t m_blocks, uint32_t n_blocks, uint32_t BAND, uint32_t &m_blk,
+                                            uint32_t &n_blk) {
+    const uint32_t per_band = BAND * n_blocks;
+    const uint32_t band = t / per_band, r = t - band * per_band;
+    const uint32_t width = m_blocks - band * BAND < BAND ? m_blocks - band * BAND : BAND;
+    n_blk = r / width;
+    m_blk = band * BAND + (r - n_blk * width);
+}
+
 template <int IN>
 __global__ void __launch_bounds__(umma::THREADS, 1)
     sparse_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                        const uint32_t *__restrict__ bias, uint64_t *__restrict__ rows_out, uint32_t num_rows, uint32_t K,
-                       uint32_t cw, int out_limbs, uint32_t m_blocks, uint32_t num_tiles) {
+                       uint32_t cw, int out_limbs, uint32_t m_blocks, uint32_t n_blocks, uint32_t band) {
     using namespace umma;
     constexpr int P = 8 * IN;
     extern __shared__ uint8_t smem_raw[];
@@ -106,6 +119,7 @@ __global__ void __launch_bounds__(umma::THREADS, 1)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + (bars - raw) + 8 * (2 * STAGES + 4));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t KT = K / TK;
+    const uint32_t num_tiles = m_blocks * n_blocks;
     auto full = [&](int s) { return bars + 8 * s; };
     auto empty = [&](int s) { return bars + 8 * (STAGES + s); };
     auto acc_full = [&](int b) { return bars + 8 * (2 * STAGES + b); };
@@ -137,13 +151,14 @@ __global__ void __launch_bounds__(umma::THREADS, 1)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // persistent: this CTA takes tiles blockIdx.x, blockIdx.x + gridDim.x, ...; consecutive tiles share the plane
-    // rows (n block), so the CTAs running at the same time read the same B tile out of L2
+    // persistent: this CTA takes tiles blockIdx.x, blockIdx.x + gridDim.x, ... in the banded order of tile_coords()
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
             for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m0 = (int)((t % m_blocks) * TM), n0 = (int)((t / m_blocks) * TN);
+                uint32_t m_blk, n_blk;
+                tile_coords(t, m_blocks, n_blocks, band, m_blk, n_blk);
+                const int m0 = (int)(m_blk * TM), n0 = (int)(n_blk * TN);
                 for (uint32_t kb = 0; kb < KT; kb++, it++) {
                     const int s = it % STAGES;
                     mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
@@ -181,7 +196,9 @@ __global__ void __launch_bounds__(umma::THREADS, 1)
         constexpr int ROWS_PER_LD = 32 / P;
         uint32_t i = 0;
         for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, i++) {
-            const uint32_t m0 = (t % m_blocks) * TM, n0 = (t / m_blocks) * TN;
+            uint32_t m_blk, n_blk;
+            tile_coords(t, m_blocks, n_blocks, band, m_blk, n_blk);
+            const uint32_t m0 = m_blk * TM, n0 = n_blk * TN;
             const uint32_t ab = i & 1;
             const uint32_t j = m0 + q * 32 + lane;
             const uint32_t cnt = bias[j];
@@ -300,7 +317,7 @@ static cudaError_t launch_umma_t(const SparseEncodeArgs &a) {
         const uint32_t grid = num_tiles < (uint32_t)a.num_sms ? num_tiles : (uint32_t)a.num_sms;
         sparse_umma_kernel<IN><<<grid, umma::THREADS, umma::SMEM, a.stream>>>(
             tm_a, tm_b, a.nnz, a.rows_out + (size_t)r0 * a.cw * a.out_limbs, nr, a.row_len, a.cw, a.out_limbs, m_blocks,
-            num_tiles);
+            n_blocks, (size_t)a.cw * a.row_len <= ((size_t)48 << 20) ? m_blocks : 16u);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     return cudaSuccess;
