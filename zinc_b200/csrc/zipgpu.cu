@@ -52,6 +52,8 @@ struct zipgpu_ctx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;  // kernels
     cudaStream_t stream2 = nullptr; // kernels of every other chunk of a host job (tails overlap the next chunk)
+    cudaStream_t stream_hi = nullptr;  // high priority: the sparse code's tensor-core GEMM, so that its one CTA per SM is
+                                       // placed as soon as hash CTAs of the previous row chunk retire
     cudaStream_t h2d = nullptr;
     cudaStream_t d2h = nullptr;
     std::vector<cudaEvent_t> ring;  // timing-disabled events for cross-stream ordering
@@ -267,6 +269,7 @@ extern "C" int zipgpu_ctx_create(int device, zipgpu_ctx **out) {
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&c->stream_hi, cudaStreamNonBlocking, -5)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking)) != cudaSuccess) {
         zipgpu_ctx_destroy(c);  // releases whatever was created so far
@@ -302,6 +305,7 @@ extern "C" void zipgpu_ctx_destroy(zipgpu_ctx *c) {
     if (c->d_row_counters) cudaFree(c->d_row_counters);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->stream_hi) cudaStreamDestroy(c->stream_hi);
     if (c->h2d) cudaStreamDestroy(c->h2d);
     if (c->d2h) cudaStreamDestroy(c->d2h);
     cudaGetLastError();
@@ -479,7 +483,9 @@ extern "C" int zipgpu_sparse_code_create(zipgpu_ctx *ctx, size_t row_len, size_t
         cmax = std::max(cmax, std::max(coef_a[i], coef_b[i]));
     }
     bool dense = cmin >= 0 && cmax <= 255 && (uint64_t)255 * (uint64_t)std::max<int64_t>(cmax, 1) * row_len < (1ull << 31) &&
-                 sparse_gemm_supported(in_limbs, out_limbs, (uint32_t)row_len, (uint32_t)cw) && !getenv("ZIPGPU_SPARSE_GENERIC");
+                 sparse_gemm_supported(in_limbs, out_limbs, (uint32_t)row_len, (uint32_t)cw) &&
+                 (uint64_t)cw * row_len <= (1ull << 31) &&  // the dense byte matrix must stay a sane size
+                 !getenv("ZIPGPU_SPARSE_GENERIC");
     std::vector<uint8_t> hd;
     std::vector<uint32_t> hbias;
     if (dense) {
@@ -699,6 +705,48 @@ static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     const bool fuse = d_roots && d_layers && code->fused_levels > 0 && code->fused_levels <= code->depth &&
                       num_rows >= fuse_min_rows(ctx, code->cw) && fusion_enabled();
     if (evals_copy && !fuse) return fail(ZIPGPU_ERR_INVALID, "zero-copy input needs the fused commit kernel");
+    // Sparse code on the tensor cores: the GEMM (TMA + tcgen05, 6 warps per SM, hardly any INT32 work) and the BLAKE3
+    // passes (INT32-alu-bound, no shared memory) use different parts of an SM.  Row chunks are encoded back to back on
+    // the high-priority stream while the trees of the chunks already encoded are hashed on `s`; the narrow top passes
+    // run once over all rows at the end.  Everything is joined back into `s`.  Measured: the hash warps take issue
+    // slots from the MMA-issuing and epilogue warps, so the gain is small -- +7 % at nv = 26, +2 % at nv = 24, a loss
+    // at nv = 22 (8 x 4 short launches) -- hence only for >= 2^26 codeword entries (ZIPGPU_SPARSE_OVERLAP=1/0 forces).
+    const char *ov = getenv("ZIPGPU_SPARSE_OVERLAP");
+    const bool overlap = ov ? ov[0] == '1' : num_rows * code->cw >= ((size_t)1 << 26);
+    if (code->sparse && code->d_sp_dense && d_roots && d_layers && code->depth > 7 && num_rows >= 1024 && overlap) {
+        const size_t chunks = 8;
+        const size_t per = ((num_rows + chunks - 1) / chunks + 31) & ~(size_t)31;
+        const size_t per_row_layers = (((size_t)2 << code->depth) - 2) * 32;
+        cudaStream_t hi = ctx->stream_hi;
+        CU(chain(ctx, s, hi));
+        int split_level = 0;
+        for (size_t r0 = 0; r0 < num_rows; r0 += per) {
+            const size_t nr = std::min(per, num_rows - r0);
+            int rc = encode_dev(code, nr, d_evals + r0 * code->row_len * code->in_limbs,
+                                d_rows + r0 * code->cw * code->out_limbs, hi);
+            if (rc) return rc;
+            CU(chain(ctx, hi, s));
+            rc = merkle_dev(ctx, nr, code->depth, code->out_limbs, d_rows + r0 * code->cw * code->out_limbs,
+                            d_layers + r0 * per_row_layers, d_roots + r0 * 32, s, 0, until_level >= 0 ? until_level : 6,
+                            &split_level);
+            if (rc) return rc;
+        }
+        if (until_level < 0 && split_level < code->depth) {
+            int rc = merkle_dev(ctx, num_rows, code->depth, code->out_limbs, d_rows, d_layers, d_roots, s, split_level, -1);
+            if (rc) return rc;
+            split_level = code->depth;
+        }
+        if (reached) *reached = split_level;
+        if (prof) {
+            cudaEventRecord(r.e1, s);  // the two phases overlap: the whole commit is reported as one interval
+            cudaEventRecord(r.e2, s);
+            r.has_enc = true;
+            r.has_hash = true;
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            ctx->prof_pending.push_back(r);
+        }
+        return ZIPGPU_OK;
+    }
     int rc = encode_dev(code, num_rows, d_evals, d_rows, s, fuse ? d_layers : nullptr, evals_copy);
     if (rc) return rc;
     if (prof) {
