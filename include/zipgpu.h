@@ -175,6 +175,28 @@ int zipgpu_data_combine_rows(const zipgpu_data *data, const uint64_t *coeffs, in
 int zipgpu_combine_rows_device(zipgpu_ctx *ctx, size_t num_rows, size_t row_len, const uint64_t *d_evals,
                                const uint64_t *d_coeffs, int out_limbs, uint64_t *d_combined_out, void *stream);
 
+/* ---- multi-GPU: all-gather of the row roots over NVLink peer memory ---------------------------------------
+ * A commit sharded by row range over G GPUs of one node (one process and one context per GPU) has
+ * one exchange step: the list of roots, MultilinearZipCommitment::roots (structs.rs:40-45), must be complete on every
+ * GPU.  These calls do it with ONE kernel per GPU and step that stores the local roots into every peer's buffer
+ * through peer memory, signals and waits -- no NCCL.  All ranks must call zipgpu_peer_roots_allgather the same number
+ * of times.
+ *   create : allocates this rank's result buffers (2 x total_rows*32 bytes, double-buffered) and flag words, and fills
+ *            ipc_out (ZIPGPU_IPC_BYTES bytes) for the other ranks;
+ *   connect: ipc_all = the ZIPGPU_IPC_BYTES-byte blocks of ALL ranks in rank order (exchanged by the host, e.g.
+ *            torch.distributed.all_gather); opens the peers' buffers (cudaIpcOpenMemHandle, enables peer access);
+ *   allgather: d_local_roots (device, count*32 bytes; 16-byte aligned) = the roots of rows
+ *            [row_begin, row_begin+count); enqueued on `stream`; when it completes, *d_all_out (returned
+ *            immediately, valid until the call after next) holds all total_rows roots. */
+#define ZIPGPU_IPC_BYTES 64
+typedef struct zipgpu_peer_roots zipgpu_peer_roots;
+int zipgpu_peer_roots_create(zipgpu_ctx *ctx, size_t total_rows, int rank, int world, zipgpu_peer_roots **out,
+                             uint8_t *ipc_out);
+int zipgpu_peer_roots_connect(zipgpu_peer_roots *pr, const uint8_t *ipc_all);
+int zipgpu_peer_roots_allgather(zipgpu_peer_roots *pr, size_t row_begin, size_t count, const uint8_t *d_local_roots,
+                                void *stream, uint8_t **d_all_out);
+void zipgpu_peer_roots_destroy(zipgpu_peer_roots *pr);
+
 /* ---- measurement helpers (used by bench.py; no reference counterpart) -------------------------------- */
 /* When enabled, every commit/encode/merkle call records CUDA events around its kernels on the launch stream. */
 int zipgpu_profile_enable(zipgpu_ctx *ctx, int on);

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--nv", type=int, default=24)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--p2p", action="store_true",
+                    help="gather the roots with the peer-memory kernel (zipgpu_peer_roots_allgather) instead of NCCL")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -33,7 +35,7 @@ def main():
     from helpers import KECCAK_SEEDS, shape_for
     from zinc_b200 import Context, RaaCode, ZipTypes, shuffle_seeded_indices
     from zinc_b200 import _native as nat
-    from zinc_b200.dist import shard_range
+    from zinc_b200.dist import PeerRoots, shard_range
 
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local)
@@ -60,10 +62,15 @@ def main():
     torch.cuda.set_stream(stream)
     sptr = C.c_void_p(stream.cuda_stream)
 
+    peer = PeerRoots(ctx, num_rows) if (args.p2p and world > 1) else None
+    gathered = [0]
+
     def step():
         nat.check(L.zipgpu_commit_device(h, count, d_ev.data_ptr(), d_rows.data_ptr(), d_lay.data_ptr(),
                                          mine.data_ptr(), sptr))
-        if world > 1:
+        if peer is not None:
+            gathered[0] = peer.allgather(begin, count, mine.data_ptr(), sptr)
+        elif world > 1:
             dist.all_gather_into_tensor(d_roots_all, mine)  # equal shards (power-of-two rows and ranks)
 
     assert num_rows % world == 0, "strong-scaling script expects the rows to divide evenly"
@@ -84,6 +91,9 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / args.steps
+    if peer is not None:  # bring the peer-gathered roots where the check below looks
+        d_roots_all.copy_(peer.tensor(gathered[0]))
+        torch.cuda.synchronize()
     # every rank holds all roots: compare with a single-GPU commit of the whole polynomial on rank 0
     ok = None
     if rank == 0:
@@ -94,8 +104,12 @@ def main():
         ok = bool(torch.equal(r_all, d_roots_all))
         print(json.dumps({"metric": "zip_commit_evals_per_sec", "scaling": "strong", "n_gpus": world, "nv": nv,
                           "ms_per_commit": ms, "value": (1 << nv) / (ms * 1e-3), "unit": "evals/s",
-                          "rows_per_gpu": count, "collective": "ncclAllGather of 32-byte roots inside the timed region",
+                          "rows_per_gpu": count, "collective": ("peer-memory kernel (zipgpu_peer_roots_allgather)" if peer is not None else "ncclAllGather") +
+                                        " of the 32-byte roots inside the timed region",
                           "roots_equal_single_gpu_commit": ok}), flush=True)
+    if peer is not None:
+        dist.barrier()
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -333,3 +333,69 @@ def test_warp_specialised_commit_kernel(num_rows, oracle, ctx, monkeypatch):
         assert np.array_equal(g_roots, roots), knob
         assert np.array_equal(g_rows, rows), knob
         assert np.array_equal(g_lay, layers), knob
+
+
+def test_peer_roots_allgather_single_rank(ctx):
+    """the peer-memory roots exchange degenerates to a copy + self-signal on one GPU (N > 1: scripts/strong_scaling.py
+    --p2p and test_peer_roots_two_gpus below); two steps exercise the double buffering"""
+    import torch
+
+    from zinc_b200.dist import PeerRoots
+
+    dev = torch.device("cuda:0")
+    pr = PeerRoots(ctx, 512)
+    for step in range(3):
+        local = torch.randint(0, 256, (512 * 32,), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        ptr = pr.allgather(0, 512, local.data_ptr())
+        ctx.sync()
+        assert torch.equal(pr.tensor(ptr), local), step
+    pr.close()
+
+
+def _peer_worker(rank, world, port, q):
+    import os
+
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world)})
+    import torch
+    import torch.distributed as dist
+
+    from zinc_b200 import Context
+    from zinc_b200.dist import PeerRoots, shard_range
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = Context(rank)
+    total = 1024
+    pr = PeerRoots(ctx, total)
+    begin, count = shard_range(total, rank, world)
+    ok = True
+    for step in range(4):
+        gen = torch.Generator().manual_seed(100 + step)
+        everything = torch.randint(0, 256, (total * 32,), dtype=torch.uint8, generator=gen)
+        local = everything[begin * 32:(begin + count) * 32].cuda()
+        torch.cuda.synchronize()
+        ptr = pr.allgather(begin, count, local.data_ptr())
+        ctx.sync()
+        ok = ok and bool(torch.equal(pr.tensor(ptr).cpu(), everything))
+    dist.barrier()
+    pr.close()
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_peer_roots_two_gpus():
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs of one node")
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_peer_worker, args=(r, 2, 29731, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    res = sorted(q.get(timeout=5) for _ in range(2))
+    assert res == [(0, True), (1, True)], res

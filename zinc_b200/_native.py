@@ -37,6 +37,10 @@ SIGNATURES = {
     "zipgpu_sparse_code_create": (i32, [vp, sz, sz, sz, i32, i32, vp, vp, vp, vp, C.POINTER(vp)]),
     "zipgpu_code_sparse_kind": (i32, [vp]),
     "zipgpu_code_destroy": (None, [vp]),
+    "zipgpu_peer_roots_create": (i32, [vp, sz, i32, i32, C.POINTER(vp), vp]),
+    "zipgpu_peer_roots_connect": (i32, [vp, vp]),
+    "zipgpu_peer_roots_allgather": (i32, [vp, sz, sz, vp, vp, C.POINTER(vp)]),
+    "zipgpu_peer_roots_destroy": (None, [vp]),
     "zipgpu_code_row_len": (sz, [vp]),
     "zipgpu_code_codeword_len": (sz, [vp]),
     "zipgpu_code_merkle_depth": (i32, [vp]),

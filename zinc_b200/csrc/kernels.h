@@ -101,6 +101,18 @@ bool sparse_gemm_supported(int in_limbs, int out_limbs, uint32_t row_len, uint32
 size_t sparse_planes_bytes(uint32_t num_rows, uint32_t row_len, int in_limbs);
 cudaError_t launch_sparse_encode(const SparseEncodeArgs &a, int *launches);
 
+// ---- multi-GPU: roots all-gather over peer memory (peer_roots.cu) ----
+constexpr int PEER_MAX = 16;
+struct PeerRootsArgs {
+    uint8_t *peer_roots[PEER_MAX];            // every rank's result buffer of this step's parity (own included)
+    unsigned long long *peer_flags[PEER_MAX]; // every rank's `world` step counters
+    const uint8_t *src;                       // this rank's roots (device)
+    size_t offset, nbytes;                    // byte range of this rank inside a result buffer (multiples of 16)
+    int rank, world;
+    unsigned long long step;
+};
+cudaError_t launch_peer_roots_allgather(const PeerRootsArgs &a, cudaStream_t stream);
+
 // ---- INT32 micro-benchmark (microbench.cu) ----
 cudaError_t launch_microbench_int32(int kind, int iters, int num_sms, cudaStream_t stream, uint32_t *d_sink,
                                     double *lane_ops);

@@ -571,6 +571,108 @@ extern "C" size_t zipgpu_code_codeword_len(const zipgpu_code *c) { return c ? c-
 extern "C" int zipgpu_code_merkle_depth(const zipgpu_code *c) { return c ? ilog2(next_pow2(c->cw)) : -1; }
 
 // ------------------------------------------------------------------------------------------------------
+// multi-GPU: roots all-gather over peer memory (peer_roots.cu)
+// ------------------------------------------------------------------------------------------------------
+struct zipgpu_peer_roots {
+    zipgpu_ctx *ctx;
+    size_t total_rows, buf_bytes;
+    int rank, world;
+    uint8_t *base = nullptr;                 // own allocation: [buffer 0 | buffer 1 | flags (PEER_MAX u64)]
+    uint8_t *peer_base[PEER_MAX] = {};       // every rank's allocation as mapped here (own = base)
+    bool connected = false;
+    unsigned long long step = 0;
+};
+
+extern "C" int zipgpu_peer_roots_create(zipgpu_ctx *ctx, size_t total_rows, int rank, int world, zipgpu_peer_roots **out,
+                                        uint8_t *ipc_out) {
+    if (!out) return fail(ZIPGPU_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!ctx || !ipc_out) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (world < 1 || world > PEER_MAX || rank < 0 || rank >= world) return fail(ZIPGPU_ERR_INVALID, "bad rank / world");
+    static_assert(sizeof(cudaIpcMemHandle_t) <= ZIPGPU_IPC_BYTES, "IPC handle size");
+    API_LOCK(ctx);
+    CU(cudaSetDevice(ctx->device));
+    zipgpu_peer_roots *p = new (std::nothrow) zipgpu_peer_roots();
+    if (!p) return fail(ZIPGPU_ERR_NOMEM, "host allocation failed");
+    p->ctx = ctx;
+    p->total_rows = total_rows;
+    p->buf_bytes = (total_rows * 32 + 255) & ~(size_t)255;
+    p->rank = rank;
+    p->world = world;
+    const size_t bytes = 2 * p->buf_bytes + PEER_MAX * sizeof(unsigned long long);
+    cudaError_t e = cudaMalloc(&p->base, bytes);  // IPC needs a cudaMalloc allocation of its own
+    if (e == cudaSuccess) e = cudaMemset(p->base, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p->base);
+    if (e != cudaSuccess) {
+        cudaFree(p->base);
+        delete p;
+        return cuda_fail(e, "peer roots buffer");
+    }
+    memset(ipc_out, 0, ZIPGPU_IPC_BYTES);
+    memcpy(ipc_out, &h, sizeof(h));
+    p->peer_base[rank] = p->base;
+    *out = p;
+    return ZIPGPU_OK;
+}
+
+extern "C" int zipgpu_peer_roots_connect(zipgpu_peer_roots *p, const uint8_t *ipc_all) {
+    if (!p || !ipc_all) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    API_LOCK(p->ctx);
+    CU(cudaSetDevice(p->ctx->device));
+    for (int r = 0; r < p->world; r++) {
+        if (r == p->rank || p->peer_base[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, ipc_all + (size_t)r * ZIPGPU_IPC_BYTES, sizeof(h));
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle (peer roots)");
+        p->peer_base[r] = static_cast<uint8_t *>(ptr);
+    }
+    p->connected = true;
+    return ZIPGPU_OK;
+}
+
+extern "C" int zipgpu_peer_roots_allgather(zipgpu_peer_roots *p, size_t row_begin, size_t count, const uint8_t *d_local_roots,
+                                           void *stream, uint8_t **d_all_out) {
+    if (!p || !d_all_out || (count && !d_local_roots)) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (!p->connected && p->world > 1) return fail(ZIPGPU_ERR_INVALID, "zipgpu_peer_roots_connect has not been called");
+    if (row_begin + count > p->total_rows) return fail(ZIPGPU_ERR_INVALID, "row range outside the commitment");
+    if (((row_begin * 32) | (uintptr_t)d_local_roots) & 15) return fail(ZIPGPU_ERR_INVALID, "roots must be 16-byte aligned");
+    API_LOCK(p->ctx);
+    CU(cudaSetDevice(p->ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->ctx->stream;
+    p->step++;
+    const size_t parity_off = (p->step & 1) * p->buf_bytes;
+    PeerRootsArgs a;
+    for (int r = 0; r < PEER_MAX; r++) {
+        a.peer_roots[r] = r < p->world ? p->peer_base[r] + parity_off : nullptr;
+        a.peer_flags[r] = r < p->world ? reinterpret_cast<unsigned long long *>(p->peer_base[r] + 2 * p->buf_bytes) : nullptr;
+    }
+    a.src = d_local_roots;
+    a.offset = row_begin * 32;
+    a.nbytes = count * 32;
+    a.rank = p->rank;
+    a.world = p->world;
+    a.step = p->step;
+    cudaError_t e = launch_peer_roots_allgather(a, s);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_peer_roots_allgather");
+    p->ctx->launches++;
+    *d_all_out = p->base + parity_off;
+    return ZIPGPU_OK;
+}
+
+extern "C" void zipgpu_peer_roots_destroy(zipgpu_peer_roots *p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < p->world; r++)
+        if (r != p->rank && p->peer_base[r]) cudaIpcCloseMemHandle(p->peer_base[r]);
+    cudaFree(p->base);
+    delete p;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // profiling records
 // ------------------------------------------------------------------------------------------------------
 static bool prof_begin(zipgpu_ctx *c, ProfRec *r) {

@@ -161,3 +161,61 @@ def sharded_batch_commit(pp, polys, ctx=None, group=None, commit_poly: Callable 
         comms = [MultilinearZipCommitment([b.reshape(-1, 32)[i].tobytes() for i in range(pp.num_rows)])
                  for b in blocks]
     return local, comms
+
+
+class PeerRoots:
+    """All-gather of the row roots over NVLink peer memory (include/zipgpu.h, csrc/peer_roots.cu): one kernel per GPU
+    and step stores the local roots into every peer's buffer, signals and waits -- the only exchange step of a
+    row-sharded commit without NCCL on the data path.  One process per GPU on one node; construction exchanges the IPC
+    descriptors once through torch.distributed (any backend)."""
+
+    def __init__(self, ctx, total_rows: int, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _native as nat
+
+        self._nat, self._C = nat, C
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.total_rows = total_rows
+        self.handle = C.c_void_p()
+        mine = np.zeros(64, dtype=np.uint8)
+        nat.check(nat.lib().zipgpu_peer_roots_create(ctx.handle, total_rows, self.rank, self.world, C.byref(self.handle),
+                                                     nat.ptr(mine)))
+        if self.world > 1:
+            backend = dist.get_backend(group)
+            dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+            t = torch.from_numpy(mine).to(dev)
+            out = torch.empty(64 * self.world, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(out, t, group=group)
+            everyone = np.ascontiguousarray(out.cpu().numpy())
+            nat.check(nat.lib().zipgpu_peer_roots_connect(self.handle, nat.ptr(everyone)))
+            dist.barrier(group)  # nobody stores into a peer before that peer's buffers exist and are mapped
+
+    def allgather(self, row_begin: int, count: int, d_local_roots: int, stream=None) -> int:
+        """d_local_roots: device pointer to count*32 bytes.  Enqueues on `stream` (None = the context's stream) and
+        returns the device pointer that holds all total_rows*32 bytes once the stream has passed this point."""
+        C = self._C
+        out = C.c_void_p()
+        self._nat.check(self._nat.lib().zipgpu_peer_roots_allgather(self.handle, row_begin, count, C.c_void_p(d_local_roots),
+                                                                    stream, C.byref(out)))
+        return out.value
+
+    def tensor(self, ptr: int):
+        """a torch uint8 view of the gathered roots behind the pointer `allgather` returned"""
+        import torch
+
+        class _Raw:
+            pass
+
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (self.total_rows * 32,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(raw, device=torch.device("cuda", torch.cuda.current_device()))
+
+    def close(self) -> None:
+        if self.handle:
+            self._nat.lib().zipgpu_peer_roots_destroy(self.handle)
+            self.handle = None
