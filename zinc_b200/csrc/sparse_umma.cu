@@ -21,12 +21,18 @@
 namespace zipgpu {
 
 namespace umma {
-constexpr int TM = 128, TN = 256, TK = 128, STAGES = 4;
+// K block per ring stage.  64 (SWIZZLE_64B, 9 stages of 24 KB: more loads in flight) was measured slower: 0.99 ms
+// against 0.75 ms at nv = 24, so the feed limit is not the number of outstanding TMA loads.
+#ifndef ZIPGPU_UMMA_TK
+#define ZIPGPU_UMMA_TK 128
+#endif
+constexpr int TM = 128, TN = 256, TK = ZIPGPU_UMMA_TK, STAGES = TK == 128 ? 4 : 9;
+static_assert(TK == 128 || TK == 64, "K block = one swizzle atom row: 128 (SWIZZLE_128B) or 64 bytes (SWIZZLE_64B)");
 constexpr int A_BYTES = TM * TK, B_BYTES = TN * TK, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 512;  // two TN-column accumulators
 constexpr int EPI_THREADS = 128;
-constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 128;
+constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -64,7 +70,9 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 }
 // K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
-    return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+    // stride between 8-row groups = 8 * TK bytes; layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(8 * TK / 16) << 32) | (1ull << 46) |
+           ((TK == 128 ? 2ull : 4ull) << 61);
 }
 __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -296,7 +304,8 @@ static bool make_map(CUtensorMap *tm, const void *base, uint64_t rows, uint64_t 
     cuuint32_t box[2] = {(cuuint32_t)umma::TK, box_rows};
     cuuint32_t estr[2] = {1, 1};
     return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, umma::TK == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
