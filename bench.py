@@ -429,6 +429,85 @@ def main():
             except Exception as ex:  # e.g. not enough memory for nv=26 next to the main buffers
                 sizes[f"nv{snv}"] = {"error": str(ex)[:200]}
 
+    # ---- the reference's own criterion shapes (benches/zip_benches.rs:225-262): EncodeRows / Commit at 2^12..2^16,
+    #      EncodeMessage (one row, row_len 128..4096), MerkleRoot (one tree, 2^12..2^16 leaves); device-resident GPU
+    #      time per call next to the CPU port on all host threads (these are latency-bound on a GPU: one row = one CTA) ----
+    ref_shapes = None
+    if rank == 0 and world == 1 and not args.no_sweep:
+        try:
+            def gpu_ms(fn, reps=50):
+                for _ in range(5):
+                    fn()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a.record(stream)
+                for _ in range(reps):
+                    fn()
+                b.record(stream)
+                torch.cuda.synchronize()
+                return a.elapsed_time(b) / reps
+
+            def cpu_ms(fn, reps=3):
+                best = None
+                for _ in range(reps):
+                    t0 = time.perf_counter()
+                    fn()
+                    dt = time.perf_counter() - t0
+                    best = dt if best is None else min(best, dt)
+                return best * 1e3
+
+            cb = None
+            if not args.no_cpu:
+                from oracle import cbind as cb
+                cb.build()
+            threads = os.cpu_count() or 1
+            ref_shapes = {"EncodeRows": {}, "Commit": {}, "EncodeMessage": {}, "MerkleRoot": {},
+                          "note": "ms per call; gpu = device-resident buffers, CUDA events; cpu = oracle port, "
+                                  f"{threads} threads (one thread for the single-row / single-tree cases)"}
+            for P_ in (12, 13, 14, 15, 16):
+                rl, nr, cw_ = shape_for(P_)
+                dp = cw_.bit_length() - 1
+                _, hc = make_code(cw_, rl)
+                ev_h = gen_evals(P_, 0)
+                ev = torch.from_numpy(ev_h.view(np.int64)).to(dev)
+                rows_ = torch.empty(nr * cw_ * 4, dtype=torch.int64, device=dev)
+                lay_ = torch.empty(nr * ((2 << dp) - 2) * 32, dtype=torch.uint8, device=dev)
+                roots_ = torch.empty(nr * 32, dtype=torch.uint8, device=dev)
+                g_enc = gpu_ms(lambda: nat.check(L.zipgpu_encode_rows_device(hc, nr, ev.data_ptr(), rows_.data_ptr(), sptr)))
+                g_com = gpu_ms(lambda: nat.check(L.zipgpu_commit_device(hc, nr, ev.data_ptr(), rows_.data_ptr(),
+                                                                        lay_.data_ptr(), roots_.data_ptr(), sptr)))
+                ref_shapes["EncodeRows"][f"2^{P_}"] = {"gpu_ms": g_enc}
+                ref_shapes["Commit"][f"2^{P_}"] = {"gpu_ms": g_com}
+                if cb is not None:
+                    p1, p2 = cb.perm_from_seed(cw_, KECCAK_SEEDS[0]), cb.perm_from_seed(cw_, KECCAK_SEEDS[1])
+                    ref_shapes["EncodeRows"][f"2^{P_}"]["cpu_ms_one_thread_tuned"] = cpu_ms(
+                        lambda: cb.encode_rows(ev_h, nr, rl, 2, p1, p2))
+                    ref_shapes["Commit"][f"2^{P_}"]["cpu_ms"] = cpu_ms(lambda: cb.commit_mt(
+                        ev_h, nr, rl, 2, KECCAK_SEEDS[0], KECCAK_SEEDS[1], p1, p2, threads=threads, faithful=True))
+                # MerkleRoot: ONE tree over 2^P random Int<4> leaves (zip_benches.rs:80-98)
+                leaves_h = np.random.Generator(np.random.PCG64(P_)).integers(0, 1 << 64, size=(1 << P_) * 4, dtype=np.uint64)
+                leaves = torch.from_numpy(leaves_h.view(np.int64)).to(dev)
+                tl = torch.empty(((2 << P_) - 2) * 32, dtype=torch.uint8, device=dev)
+                tr = torch.empty(32, dtype=torch.uint8, device=dev)
+                ref_shapes["MerkleRoot"][f"2^{P_}"] = {"gpu_ms": gpu_ms(lambda: nat.check(L.zipgpu_merkle_rows_device(
+                    ctx.handle, 1, P_, 4, leaves.data_ptr(), tl.data_ptr(), tr.data_ptr(), sptr)))}
+                if cb is not None:
+                    ref_shapes["MerkleRoot"][f"2^{P_}"]["cpu_ms"] = cpu_ms(lambda: cb.merkle_tree(P_, leaves_h, 4))
+            for rl in (128, 256, 512, 1024, 2048, 4096):  # EncodeMessage: encode_wide of one row (zip_benches.rs:61-78)
+                cw_ = 2 * rl
+                _, hc = make_code(cw_, rl)
+                msg_h = gen_evals(12, 0)[:rl].copy()
+                msg = torch.from_numpy(msg_h.view(np.int64)).to(dev)
+                out_ = torch.empty(cw_ * 4, dtype=torch.int64, device=dev)
+                ent = {"gpu_ms": gpu_ms(lambda: nat.check(L.zipgpu_encode_rows_device(hc, 1, msg.data_ptr(), out_.data_ptr(), sptr)))}
+                if cb is not None:
+                    p1, p2 = cb.perm_from_seed(cw_, KECCAK_SEEDS[0]), cb.perm_from_seed(cw_, KECCAK_SEEDS[1])
+                    ent["cpu_ms_faithful"] = cpu_ms(lambda: cb.encode_row_seeded(msg_h, 2, KECCAK_SEEDS[0], KECCAK_SEEDS[1]))
+                    ent["cpu_ms_tuned"] = cpu_ms(lambda: cb.encode_rows(msg_h, 1, rl, 2, p1, p2))
+                ref_shapes["EncodeMessage"][f"row_len={rl}"] = ent
+        except Exception as ex:
+            ref_shapes = {"error": str(ex)[:300]}
+
     # ---- the other LinearCode of the reference, ZipLinearCode (sparse code, zip/code.rs:77-215), same nv, same
     #      buffers: 0/1 matrices with row_len/2 cells per row (every coefficient 1, the densest the reference samples),
     #      tensor-core roofline for its GEMM and the CPU port on a bounded sample (rank 0, N = 1) ----
@@ -594,6 +673,7 @@ def main():
             },
             "cpu_baseline": cpu_baseline,
             "sparse_code": sparse_code,
+            "reference_bench_shapes": ref_shapes,
             "sizes": sizes,
         }
         emit(line)

@@ -162,6 +162,7 @@ def test_fused_commit_kernel_forced_at_small_shapes(nv, oracle, ctx, monkeypatch
     f_rows, f_lay, f_roots = _commit_device(ctx, code, num_rows, cw, evals)
     fused_launches = ctx.launch_count - launches0
     monkeypatch.setenv("ZIPGPU_NO_FUSE", "1")
+    monkeypatch.setenv("ZIPGPU_NO_CTA_TREE", "1")  # compare with the subtree-pass kernels (small trees default to the CTA-tree path)
     launches0 = ctx.launch_count
     u_rows, u_lay, u_roots = _commit_device(ctx, code, num_rows, cw, evals)
     assert fused_launches <= ctx.launch_count - launches0  # the leaf pass is folded into the encoder launch

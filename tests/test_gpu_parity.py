@@ -74,3 +74,33 @@ def test_merkle_tree_int3_proofs(oracle, ctx):
         assert L.zo_merkle_verify(10, path.ctypes.data_as(C.POINTER(C.c_uint8)),
                                   rootb.ctypes.data_as(C.POINTER(C.c_uint8)),
                                   leaf.ctypes.data_as(C.POINTER(C.c_uint64)), 3, i) == 0
+
+
+@pytest.mark.parametrize("num_rows,depth,limbs", [(1, 16, 4), (1, 12, 4), (37, 9, 4), (256, 10, 4), (3, 13, 8), (5, 1, 4),
+                                                   (2, 11, 3), (64, 7, 2)])
+def test_cta_tree_latency_path_matches_oracle_and_pass_path(num_rows, depth, limbs, oracle, ctx, monkeypatch):
+    """small whole trees (<= 2^18 leaves) take the CTA-per-subtree kernel; same layers and roots as the oracle
+    (pcs/utils.rs:74-118, the MerkleRoot shapes of zip_benches.rs:80-98) and as the subtree-pass kernels"""
+    from zinc_b200 import _native as nat
+
+    rng = np.random.default_rng(depth * 100 + num_rows)
+    leaves = rng.integers(0, 1 << 64, size=num_rows * (1 << depth) * limbs, dtype=np.uint64)
+    per_row = ((2 << depth) - 2) * 32
+
+    def run():
+        layers = np.zeros(num_rows * per_row, dtype=np.uint8)
+        roots = np.zeros(num_rows * 32, dtype=np.uint8)
+        n0 = ctx.launch_count
+        nat.check(nat.lib().zipgpu_merkle_rows(ctx.handle, num_rows, depth, limbs, nat.ptr(leaves), nat.ptr(layers), nat.ptr(roots)))
+        return layers, roots, ctx.launch_count - n0
+
+    lay_c, roots_c, n_cta = run()
+    monkeypatch.setenv("ZIPGPU_NO_CTA_TREE", "1")
+    lay_p, roots_p, n_pass = run()
+    assert n_cta == -(-depth // 10) and n_cta <= n_pass
+    assert np.array_equal(lay_c, lay_p) and np.array_equal(roots_c, roots_p)
+    for r in range(num_rows):
+        rc, olay, oroot = oracle.merkle_tree(depth, leaves[r * (1 << depth) * limbs:(r + 1) * (1 << depth) * limbs], limbs)
+        assert rc == 0
+        assert np.array_equal(lay_c[r * per_row:(r + 1) * per_row], olay), r
+        assert np.array_equal(roots_c[r * 32:(r + 1) * 32], oroot), r

@@ -14,6 +14,9 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace zipgpu {
 
 namespace {
@@ -112,6 +115,69 @@ __global__ void __launch_bounds__(128, MINB)
     }
 }
 
+// Latency path for small jobs (a prover's 2^12..2^16 commits, the reference's own criterion shapes): ONE CTA walks a
+// whole subtree of up to 2^10 inputs level by level through shared memory, one compression of latency per level,
+// instead of a chain of subtree passes whose launches and per-thread sequential subtrees dominate when the GPU is
+// not full.  Digests live transposed in shared memory ([word][node]) so that the (2t, 2t+1) reads are conflict-free.
+constexpr int CTA_TREE_MAX_LEVELS = 10;
+template <int LEAF32>
+__global__ void __launch_bounds__(512)
+    merkle_cta_tree_kernel(const uint32_t *__restrict__ leaves, uint8_t *layers, uint8_t *roots, uint32_t num_rows, TreeGeom g,
+                           uint32_t level_in, uint32_t S, uint32_t one) {
+    __shared__ uint32_t buf[8][1 << CTA_TREE_MAX_LEVELS];
+    const uint32_t subtrees_per_row = (g.cw >> level_in) >> S;
+    const uint32_t row = blockIdx.x / subtrees_per_row, b = blockIdx.x % subtrees_per_row;
+    const uint32_t t = threadIdx.x, width = 1u << S;
+    for (uint32_t e = t; e < width; e += blockDim.x) {
+        const uint32_t idx = (b << S) | e;
+        uint32_t d[8];
+        if constexpr (LEAF32 > 0) {
+            uint32_t x[LEAF32];
+            load_leaf<LEAF32>(leaves + ((size_t)row * g.cw + idx) * LEAF32, x);
+            b3::hash_leaf<LEAF32>(x, d, one);
+            store_digest(node_ptr(layers, roots, g, row, 0, idx), d);
+        } else {
+            load_digest(node_ptr(layers, roots, g, row, level_in, idx), d);
+        }
+#pragma unroll
+        for (int w = 0; w < 8; w++) buf[w][e] = d[w];
+    }
+    __syncthreads();
+    for (uint32_t l = 1; l <= S; l++) {
+        const uint32_t n = width >> l;
+        const bool act = t < n;
+        b3::Digest o;
+        if (act) {
+            b3::Digest lft, rgt;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                const uint2 v = *reinterpret_cast<const uint2 *>(&buf[w][2 * t]);
+                lft.w[w] = v.x;
+                rgt.w[w] = v.y;
+            }
+            o = b3::hash_node_call(lft, rgt, one);
+        }
+        __syncthreads();
+        if (act) {
+#pragma unroll
+            for (int w = 0; w < 8; w++) buf[w][t] = o.w[w];
+            store_digest(node_ptr(layers, roots, g, row, level_in + l, (b << (S - l)) | t), o.w);
+        }
+        __syncthreads();
+    }
+}
+
+template <int LEAF32>
+cudaError_t launch_cta_tree(const MerkleArgs &a, const TreeGeom &g, uint32_t level_in, uint32_t S) {
+    const size_t grid = (size_t)a.num_rows * ((g.cw >> level_in) >> S);
+    if (grid == 0) return cudaSuccess;
+    if (grid > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    const uint32_t half = (1u << S) / 2, block = half < 32 ? 32 : half;
+    merkle_cta_tree_kernel<LEAF32><<<(uint32_t)grid, block, 0, a.stream>>>(a.leaves, a.layers, a.roots, a.num_rows, g, level_in,
+                                                                     S, 1u);
+    return cudaGetLastError();
+}
+
 // MINB = 5: ptxas then keeps the whole working set in 92 registers without spills; measured on B200 the leaf pass
 // runs 2 % faster at 5 resident blocks/SM than squeezed into 80 registers for 6 (1.837 vs 1.880 ms at nv = 24)
 template <int LEAF32, int H, int MINB = 5>
@@ -159,6 +225,31 @@ cudaError_t launch_merkle_levels(const MerkleArgs &a, int from_level, int until_
     if (until_level < 0 || until_level > a.depth) until_level = a.depth;
     int n = 0, level = from_level;
     cudaError_t err = cudaSuccess;
+    // small whole trees: the CTA-per-subtree latency path (at most 2^18 leaves in total, i.e. <= 256 CTAs of work)
+    if (from_level == 0 && until_level == a.depth && a.depth >= 1 && ((size_t)a.num_rows << a.depth) <= ((size_t)1 << 18) &&
+        !getenv("ZIPGPU_NO_CTA_TREE")) {
+        while (level < a.depth) {
+            const uint32_t S = (uint32_t)std::min(CTA_TREE_MAX_LEVELS, a.depth - level);
+            if (level == 0) {
+                switch (a.leaf32) {
+                    case 2: err = launch_cta_tree<2>(a, g, 0, S); break;
+                    case 4: err = launch_cta_tree<4>(a, g, 0, S); break;
+                    case 6: err = launch_cta_tree<6>(a, g, 0, S); break;
+                    case 8: err = launch_cta_tree<8>(a, g, 0, S); break;
+                    case 16: err = launch_cta_tree<16>(a, g, 0, S); break;
+                    default: return cudaErrorInvalidValue;
+                }
+            } else {
+                err = launch_cta_tree<0>(a, g, (uint32_t)level, S);
+            }
+            if (err != cudaSuccess) return err;
+            n++;
+            level += (int)S;
+        }
+        if (reached) *reached = level;
+        if (launches) *launches = n;
+        return cudaSuccess;
+    }
     if (level == 0 && (until_level > 0 || a.depth == 0)) {
         // the leaf pass covers levels 0..min(3, depth) (15/16 of all compressions)
         const int h = a.depth < 3 ? a.depth : 3;
