@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(1024) peer_roots_allgather_kernel(PeerRootsArg
         volatile unsigned long long *mine = a.peer_flags[a.rank] + tid;
         unsigned long long spins = 0;
         while (*mine < a.step) {
-            if (++spins > (1ull << 31)) __trap();
+            if (++spins > (1ull << 27)) __trap();  // tens of seconds
         }
     }
     __threadfence_system();
