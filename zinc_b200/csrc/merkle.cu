@@ -120,16 +120,23 @@ __global__ void __launch_bounds__(128, MINB)
 // instead of a chain of subtree passes whose launches and per-thread sequential subtrees dominate when the GPU is
 // not full.  Digests live transposed in shared memory ([word][node]) so that the (2t, 2t+1) reads are conflict-free.
 constexpr int CTA_TREE_MAX_LEVELS = 10;
+constexpr int CTA_TREE_MAX_ROWS = 32;  // narrow subtrees: up to 32 rows share a CTA so that the warps stay full
+constexpr int CTA_TREE_BUF = (1 << CTA_TREE_MAX_LEVELS) + 2 * CTA_TREE_MAX_ROWS;
+// RL > 0: the CTA takes 2^RL whole rows (the subtree is everything that is left of a row); every row owns a region of
+// 2^S + 2 words per digest word (the +2 keeps pair reads 8-byte aligned and spreads the rows over the banks).
 template <int LEAF32>
 __global__ void __launch_bounds__(512)
     merkle_cta_tree_kernel(const uint32_t *__restrict__ leaves, uint8_t *layers, uint8_t *roots, uint32_t num_rows, TreeGeom g,
-                           uint32_t level_in, uint32_t S, uint32_t one) {
-    __shared__ uint32_t buf[8][1 << CTA_TREE_MAX_LEVELS];
+                           uint32_t level_in, uint32_t S, uint32_t RL, uint32_t one) {
+    __shared__ __align__(8) uint32_t buf[8][CTA_TREE_BUF];
     const uint32_t subtrees_per_row = (g.cw >> level_in) >> S;
-    const uint32_t row = blockIdx.x / subtrees_per_row, b = blockIdx.x % subtrees_per_row;
-    const uint32_t t = threadIdx.x, width = 1u << S;
-    for (uint32_t e = t; e < width; e += blockDim.x) {
-        const uint32_t idx = (b << S) | e;
+    const uint32_t row0 = RL ? blockIdx.x << RL : blockIdx.x / subtrees_per_row;
+    const uint32_t b = RL ? 0u : blockIdx.x % subtrees_per_row;
+    const uint32_t t = threadIdx.x, width = 1u << S, stride = width + 2;
+    for (uint32_t e = t; e < (width << RL); e += blockDim.x) {
+        const uint32_t rl = e >> S, i = e & (width - 1), row = row0 + rl;
+        if (row >= num_rows) continue;
+        const uint32_t idx = (b << S) | i;
         uint32_t d[8];
         if constexpr (LEAF32 > 0) {
             uint32_t x[LEAF32];
@@ -140,18 +147,19 @@ __global__ void __launch_bounds__(512)
             load_digest(node_ptr(layers, roots, g, row, level_in, idx), d);
         }
 #pragma unroll
-        for (int w = 0; w < 8; w++) buf[w][e] = d[w];
+        for (int w = 0; w < 8; w++) buf[w][rl * stride + i] = d[w];
     }
     __syncthreads();
     for (uint32_t l = 1; l <= S; l++) {
-        const uint32_t n = width >> l;
-        const bool act = t < n;
+        const uint32_t nlog = S - l, n = 1u << nlog;  // nodes per row at this level
+        const uint32_t rl = t >> nlog, i = t & (n - 1), row = row0 + rl;
+        const bool act = t < (n << RL) && row < num_rows;
         b3::Digest o;
         if (act) {
             b3::Digest lft, rgt;
 #pragma unroll
             for (int w = 0; w < 8; w++) {
-                const uint2 v = *reinterpret_cast<const uint2 *>(&buf[w][2 * t]);
+                const uint2 v = *reinterpret_cast<const uint2 *>(&buf[w][rl * stride + 2 * i]);
                 lft.w[w] = v.x;
                 rgt.w[w] = v.y;
             }
@@ -160,8 +168,8 @@ __global__ void __launch_bounds__(512)
         __syncthreads();
         if (act) {
 #pragma unroll
-            for (int w = 0; w < 8; w++) buf[w][t] = o.w[w];
-            store_digest(node_ptr(layers, roots, g, row, level_in + l, (b << (S - l)) | t), o.w);
+            for (int w = 0; w < 8; w++) buf[w][rl * stride + i] = o.w[w];
+            store_digest(node_ptr(layers, roots, g, row, level_in + l, (b << nlog) | i), o.w);
         }
         __syncthreads();
     }
@@ -169,12 +177,18 @@ __global__ void __launch_bounds__(512)
 
 template <int LEAF32>
 cudaError_t launch_cta_tree(const MerkleArgs &a, const TreeGeom &g, uint32_t level_in, uint32_t S) {
-    const size_t grid = (size_t)a.num_rows * ((g.cw >> level_in) >> S);
+    const uint32_t subtrees_per_row = (g.cw >> level_in) >> S;
+    uint32_t RL = 0;
+    // whole rows: pack rows while the CTA stays within 2^10 inputs and 32 rows -- but only as long as two CTAs per SM
+    // remain (a tiny job is faster spread over many SMs than packed into full warps: commit of 2^12, 14.5 vs 19.6 us)
+    if (subtrees_per_row == 1)
+        while (RL < 5 && (S + RL + 1) <= (uint32_t)CTA_TREE_MAX_LEVELS && (a.num_rows >> (RL + 1)) >= 2u * 148u) RL++;
+    const size_t grid = RL ? ((size_t)a.num_rows + (1u << RL) - 1) >> RL : (size_t)a.num_rows * subtrees_per_row;
     if (grid == 0) return cudaSuccess;
     if (grid > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    const uint32_t half = (1u << S) / 2, block = half < 32 ? 32 : half;
+    const uint32_t half = (1u << (S + RL)) / 2, block = half < 32 ? 32 : half;
     merkle_cta_tree_kernel<LEAF32><<<(uint32_t)grid, block, 0, a.stream>>>(a.leaves, a.layers, a.roots, a.num_rows, g, level_in,
-                                                                     S, 1u);
+                                                                     S, RL, 1u);
     return cudaGetLastError();
 }
 
@@ -265,7 +279,18 @@ cudaError_t launch_merkle_levels(const MerkleArgs &a, int from_level, int until_
         n++;
         level = h;
     }
+    const bool cta_top_ok = until_level == a.depth && !getenv("ZIPGPU_NO_CTA_TREE");
     while (level < until_level) {  // every further pass 3 levels, the last one up to 4
+        // once the trees have narrowed to <= 2^18 nodes in total the remaining passes are latency-bound: finish with
+        // the CTA-per-subtree kernel (one launch per 10 levels, one compression of latency per level)
+        if (cta_top_ok && level > 0 && ((size_t)a.num_rows << (a.depth - level)) <= ((size_t)1 << 18)) {
+            const uint32_t S = (uint32_t)std::min(CTA_TREE_MAX_LEVELS, a.depth - level);
+            err = launch_cta_tree<0>(a, g, (uint32_t)level, S);
+            if (err != cudaSuccess) return err;
+            n++;
+            level += (int)S;
+            continue;
+        }
         const int remaining = a.depth - level;
         const int h = remaining <= 4 ? remaining : 3;
         err = launch_node_pass(a, g, (uint32_t)level, h);
