@@ -478,6 +478,21 @@ def main():
                                                                         lay_.data_ptr(), roots_.data_ptr(), sptr)))
                 ref_shapes["EncodeRows"][f"2^{P_}"] = {"gpu_ms": g_enc}
                 ref_shapes["Commit"][f"2^{P_}"] = {"gpu_ms": g_com}
+                # the call a host makes: pinned host evaluations in, host roots out, prover data resident
+                ev_pin = torch.from_numpy(ev_h.view(np.int64)).pin_memory()
+                roots_pin = torch.empty(nr * 32, dtype=torch.uint8).pin_memory()
+
+                def host_call():
+                    hd = C.c_void_p()
+                    nat.check(L.zipgpu_commit_resident(hc, nr, ev_pin.data_ptr(), roots_pin.data_ptr(), C.byref(hd)))
+                    L.zipgpu_data_free(hd)
+
+                for _ in range(5):
+                    host_call()
+                t0 = time.perf_counter()
+                for _ in range(50):
+                    host_call()
+                ref_shapes["Commit"][f"2^{P_}"]["e2e_host_ms"] = (time.perf_counter() - t0) / 50 * 1e3
                 if cb is not None:
                     p1, p2 = cb.perm_from_seed(cw_, KECCAK_SEEDS[0]), cb.perm_from_seed(cw_, KECCAK_SEEDS[1])
                     ref_shapes["EncodeRows"][f"2^{P_}"]["cpu_ms_one_thread_tuned"] = cpu_ms(
