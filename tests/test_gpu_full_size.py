@@ -381,6 +381,22 @@ def _peer_worker(rank, world, port, q):
         ok = ok and bool(torch.equal(pr.tensor(ptr).cpu(), everything))
     dist.barrier()
     pr.close()
+    # a row-sharded commit whose roots are gathered by the peer-memory kernel == the single-GPU commit
+    import numpy as np
+
+    from zinc_b200 import DenseMultilinearExtension, MultilinearZip, RaaCode, ZipTypes, shuffle_seeded_indices
+    from zinc_b200.dist import sharded_commit
+
+    nv, row_len, num_rows, cw = 14, 128, 128, 256
+    code = RaaCode.with_permutations(ZipTypes(), row_len, 2, shuffle_seeded_indices(cw, 1), shuffle_seeded_indices(cw, 2))
+    pp = MultilinearZip.setup(1 << nv, code)
+    poly = DenseMultilinearExtension.rand(nv, np.random.default_rng(14))
+    pr2 = PeerRoots(ctx, pp.num_rows)
+    _, begin, count, comm = sharded_commit(pp, poly, ctx, peer=pr2)
+    _, full = MultilinearZip.commit(pp, poly, ctx)
+    ok = ok and comm.roots == full.roots and (begin, count) == shard_range(pp.num_rows, rank, world)
+    dist.barrier()
+    pr2.close()
     q.put((rank, ok))
     dist.destroy_process_group()
 

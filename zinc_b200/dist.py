@@ -35,8 +35,11 @@ def _all_gather_bytes(local: np.ndarray, counts: list[int], group=None) -> np.nd
     return np.concatenate([o[:c].cpu().numpy() for o, c in zip(out, counts)])
 
 
-def sharded_commit(pp, poly, ctx=None, group=None, commit_rows: Callable | None = None):
+def sharded_commit(pp, poly, ctx=None, group=None, commit_rows: Callable | None = None, peer=None):
     """Row-range sharded MultilinearZip::commit.
+
+    `peer` (a PeerRoots built for pp.num_rows rows): gather the roots with the peer-memory kernel straight from the
+    resident commit's device buffer instead of a torch.distributed all-gather of host bytes.
 
     Returns (local_data, begin, count, MultilinearZipCommitment with ALL roots).  `commit_rows(pp, evals_slice,
     num_rows_local)` -> (local_data, roots uint8[num_rows_local, 32]) defaults to the GPU path; the CPU tests
@@ -68,7 +71,14 @@ def sharded_commit(pp, poly, ctx=None, group=None, commit_rows: Callable | None 
         local_data, local_roots = commit_rows(pp, local_evals, count)
     else:
         local_data, local_roots = None, np.empty((0, 32), dtype=np.uint8)
-    if world > 1:
+    if world > 1 and peer is not None:
+        from . import _native as nat
+
+        d_local = nat.lib().zipgpu_data_roots_device(local_data.handle) if count else None
+        ptr = peer.allgather(begin, count, d_local)
+        peer.sync()
+        roots = peer.tensor(ptr).cpu().numpy().reshape(pp.num_rows, 32).copy()
+    elif world > 1:
         counts = [shard_range(pp.num_rows, r, world)[1] * 32 for r in range(world)]
         roots = _all_gather_bytes(local_roots.reshape(-1), counts, group).reshape(pp.num_rows, 32)
     else:
@@ -178,6 +188,7 @@ class PeerRoots:
         from . import _native as nat
 
         self._nat, self._C = nat, C
+        self._ctx = ctx
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.total_rows = total_rows
@@ -203,6 +214,10 @@ class PeerRoots:
         self._nat.check(self._nat.lib().zipgpu_peer_roots_allgather(self.handle, row_begin, count, C.c_void_p(d_local_roots),
                                                                     stream, C.byref(out)))
         return out.value
+
+    def sync(self) -> None:
+        """wait for the context's stream (where `allgather` enqueues by default)"""
+        self._ctx.sync()
 
     def tensor(self, ptr: int):
         """a torch uint8 view of the gathered roots behind the pointer `allgather` returned"""
