@@ -618,8 +618,17 @@ def main():
         if sparse_code and "roofline" in sparse_code:
             # no measured int8 number exists: 2 x the measured dense bf16 rate (tcgen05 kind::i8 : kind::f16 = 2 : 1)
             i8_peak = 2.0 * float(peaks.get("bf16_tflops", 1631.7))
+            sp_traffic = None
+            try:
+                with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                    tr = json.load(f).get("sparse_umma_kernel", {})
+                if tr.get("nv") == nv:
+                    sp_traffic = tr.get("dram_bytes")
+            except Exception:
+                pass
             sparse_code["roofline"].update({"peak": i8_peak, "frac": sparse_code["roofline"]["achieved"] / i8_peak,
-                                            "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (burst)"})
+                                            "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (burst)",
+                                            "traffic": sp_traffic})
         enc_ms_avg = enc_ms.value / max(calls.value, 1)
         hash_ms_avg = hash_ms.value / max(calls.value, 1)
         enc_gbs = ENC_BYTES_PER_EVAL * n_evals / (enc_ms_avg * 1e-3) / 1e9
