@@ -7,7 +7,9 @@
 use core::ffi::{c_char, c_int, c_void};
 
 #[repr(C)] pub struct zipgpu_ctx { _p: [u8; 0] }
-#[repr(C)] pub struct zipgpu_code { _p: [u8; 0] }
+#[repr(C)] pub struct zipgpu_peer_roots { _private: [u8; 0] }
+#[repr(C)]
+pub struct zipgpu_code { _p: [u8; 0] }
 #[repr(C)] pub struct zipgpu_data { _p: [u8; 0] }
 
 pub const ZIPGPU_OK: c_int = 0;
@@ -34,6 +36,13 @@ unsafe extern "C" {
                                      in_limbs: c_int, out_limbs: c_int, cols_a: *const u32, coef_a: *const i64,
                                      cols_b: *const u32, coef_b: *const i64, out: *mut *mut zipgpu_code) -> c_int;
     pub fn zipgpu_code_sparse_kind(code: *const zipgpu_code) -> c_int;
+    // multi-GPU: all-gather of the row roots over NVLink peer memory (one process per GPU, one node)
+    pub fn zipgpu_peer_roots_create(ctx: *mut zipgpu_ctx, total_rows: usize, rank: c_int, world: c_int,
+                                    out: *mut *mut zipgpu_peer_roots, ipc_out: *mut u8) -> c_int;
+    pub fn zipgpu_peer_roots_connect(pr: *mut zipgpu_peer_roots, ipc_all: *const u8) -> c_int;
+    pub fn zipgpu_peer_roots_allgather(pr: *mut zipgpu_peer_roots, row_begin: usize, count: usize,
+                                       d_local_roots: *const u8, stream: *mut c_void, d_all_out: *mut *mut u8) -> c_int;
+    pub fn zipgpu_peer_roots_destroy(pr: *mut zipgpu_peer_roots);
     pub fn zipgpu_code_destroy(code: *mut zipgpu_code);
     // encode_rows / commit_no_merkle (commit.rs:104-119,158-183)
     pub fn zipgpu_encode_rows(code: *mut zipgpu_code, num_rows: usize, evals: *const u64, rows_out: *mut u64) -> c_int;
