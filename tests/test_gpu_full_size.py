@@ -198,7 +198,8 @@ def test_encode_wide_to_M_matches_oracle(row_len, oracle, ctx):
     assert np.array_equal(code.encode(row, ctx).reshape(-1), exp)
 
 
-def test_zero_copy_commit_opt_in(oracle, ctx, monkeypatch):
+@pytest.mark.parametrize("nv", [22, 23])
+def test_zero_copy_commit_opt_in(nv, oracle, ctx, monkeypatch):
     """ZIPGPU_ZEROCOPY=1: the fused commit kernel reads pinned host evaluations in place over PCIe and keeps a copy in
     HBM for the opening phase; same roots, rows, layers, and the proximity row combination sees the copied evals"""
     import torch
@@ -206,7 +207,6 @@ def test_zero_copy_commit_opt_in(oracle, ctx, monkeypatch):
     from oracle import pyoracle as po
     from zinc_b200 import DenseMultilinearExtension, MultilinearZip, MultilinearZipParams
 
-    nv = 22
     code, row_len, num_rows, cw, p1, p2 = _code(nv, KECCAK_SEEDS, oracle)
     pp = MultilinearZipParams.new(nv, num_rows, code)
     pinned = torch.empty((1 << nv, 1), dtype=torch.int64).pin_memory()
@@ -313,14 +313,15 @@ def test_longest_codeword_shape(fused, oracle, ctx, monkeypatch):
     assert np.array_equal(g_roots, roots) and np.array_equal(g_rows, rows) and np.array_equal(g_lay, layers)
 
 
-@pytest.mark.parametrize("num_rows", [148, 1000, 1333])
-def test_warp_specialised_commit_kernel(num_rows, oracle, ctx, monkeypatch):
-    """cw = 8192 (the nv = 23 / 24 shape) takes the warp-specialised commit kernel (one 1024-thread CTA per SM: 16 warps
-    encode into alternating plane sets, 16 warps hash): codewords, every layer and the roots against the oracle, for row
+@pytest.mark.parametrize("row_len,num_rows", [(4096, 148), (4096, 1000), (4096, 1333), (2048, 100), (2048, 777), (2048, 2048),
+                                              (1024, 200), (1024, 1025), (1024, 3000)])
+def test_warp_specialised_commit_kernel(row_len, num_rows, oracle, ctx, monkeypatch):
+    """cw = 8192 / 4096 / 2048 (nv = 19 .. 24) take the warp-specialised commit kernel (per CTA one thread group encodes
+    into alternating plane sets while the other hashes): codewords, every layer and the roots against the oracle, for row
     counts below / above the dynamic-claiming threshold and not a multiple of the grid; and against the other paths"""
     from zinc_b200 import RaaCode, ZipTypes
 
-    row_len, cw = 4096, 8192
+    cw = 2 * row_len
     p1, p2 = oracle.perm_from_seed(cw, KECCAK_SEEDS[0]), oracle.perm_from_seed(cw, KECCAK_SEEDS[1])
     code = RaaCode.with_permutations(ZipTypes(), row_len, 2, p1, p2)
     evals = np.random.default_rng(num_rows).integers(0, 1 << 64, size=num_rows * row_len, dtype=np.uint64)

@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
 }
 
 // ------------------------------------------------------------------------------------------------------
-// The warp-specialised commit kernel (cw = 8192, Int<1> -> Int<4>): ONE 1024-thread CTA per SM, two plane sets.
+// The warp-specialised commit kernel (cw = 2048 / 4096 / 8192, Int<1> -> Int<4>): two thread groups per CTA, two plane sets.
 //   warps  0..15 (ENC)  : stage -> gather -> scan -> gather -> scan -> park s2 in plane set `buf` -> write the codeword
 //                         out (record tiles + bulk stores), then straight on to the next row in the other plane set
 //   warps 16..31 (HASH) : BLAKE3 leaves and the four lowest tree levels of the row parked in `buf`, thread t on the 16
@@ -549,19 +549,22 @@ __global__ void __launch_bounds__(MAXT, MINB)
 // every pair run as if alone (75 us per row, 62 of them hashing) and starved the other -- minus the 13 us per row the
 // favoured CTA spent not hashing: here the hash warps never leave the alu pipe.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kWsEnc = 512, kWsAll = 1024;
 constexpr int kBarEnc = 1, kBarFull0 = 2, kBarEmpty0 = 4;  // + buf
-template <int ID>
-__device__ __forceinline__ void ws_sync_all() { asm volatile("bar.sync %0, %1;" ::"r"(ID), "n"(kWsAll) : "memory"); }
-__device__ __forceinline__ void ws_sync(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kWsAll) : "memory"); }
-__device__ __forceinline__ void ws_arrive(uint32_t id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kWsAll) : "memory"); }
+template <int ALL>
+__device__ __forceinline__ void ws_sync(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(ALL) : "memory"); }
+template <int ALL>
+__device__ __forceinline__ void ws_arrive(uint32_t id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(ALL) : "memory"); }
 
-__global__ void __launch_bounds__(kWsAll, 1)
+// E entries per thread, kWsEnc threads per group: (16, 512) = cw 8192, (8, 512) = cw 4096, (8, 256) = cw 2048 -- the
+// (E, T) of the plain encoder for those shapes, so the same pre-translated tables serve both kernels.  The 512-thread
+// CTA of cw = 2048 leaves room for two CTAs per SM.
+template <int E, int kWsEnc>
+__global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
     commit_ws_kernel(const uint32_t *__restrict__ evals, uint32_t *__restrict__ rows_out,
                      const uint16_t *__restrict__ tab1, const uint16_t *__restrict__ tab2,
                      const uint8_t *__restrict__ colw, uint32_t num_rows, uint8_t *__restrict__ layers, uint32_t one,
                      uint32_t *__restrict__ row_counter) {
-    constexpr int IN32 = 2, W = 3, E = 16, OUT32 = 8;
+    constexpr int IN32 = 2, W = 3, OUT32 = 8, kWsAll = 2 * kWsEnc;
     constexpr uint32_t T = kWsEnc, P = T * E, cw = P, in_words = (P / 2) * IN32;
     using T16 = Tab16<E>;
     using T8 = Tab8<E>;
@@ -586,7 +589,7 @@ __global__ void __launch_bounds__(kWsAll, 1)
         for (; row < num_rows; it++) {
             const uint32_t buf = it & 1u;
             uint32_t *pl = planes + buf * (W * P);
-            if (it >= 2) ws_sync(kBarEmpty0 + buf);  // the hash warps are done with this plane set
+            if (it >= 2) ws_sync<kWsAll>(kBarEmpty0 + buf);  // the hash warps are done with this plane set
             uint32_t early = row + gridDim.x;
             if (t == 0 && row_counter) early = gridDim.x + atomicAdd(row_counter, 1u) + 1u;
             {
@@ -635,7 +638,7 @@ __global__ void __launch_bounds__(kWsAll, 1)
                 for (int w = 0; w < W; w++) pl[w * P + s2] = v[k][w];
             }
             if (t == 0) s_row[buf] = row;
-            ws_arrive(kBarFull0 + buf);  // hand the row to the hash warps
+            ws_arrive<kWsAll>(kBarFull0 + buf);  // hand the row to the hash warps
             __syncwarp();
             T16::load(tab1, t, T, c1);   // for the next row; in flight during the write-out
             // write-out of this warp's 32E positions: 32-byte records into the warp's tile, one bulk store per KiB
@@ -660,17 +663,17 @@ __global__ void __launch_bounds__(kWsAll, 1)
         }
         {   // no more rows: tell the hash warps through the next plane set
             const uint32_t buf = it & 1u;
-            if (it >= 2) ws_sync(kBarEmpty0 + buf);
+            if (it >= 2) ws_sync<kWsAll>(kBarEmpty0 + buf);
             if (t == 0) s_row[buf] = 0xffffffffu;
-            ws_arrive(kBarFull0 + buf);
+            ws_arrive<kWsAll>(kBarFull0 + buf);
         }
         if (lane == 0) bulk_wait_all();
     } else {
         // ============================== HASH ==============================
-        constexpr int H = 4;
+        constexpr int H = E == 16 ? 4 : E == 8 ? 3 : E == 4 ? 2 : 1;
         for (uint32_t it = 0;; it++) {
             const uint32_t buf = it & 1u;
-            ws_sync(kBarFull0 + buf);
+            ws_sync<kWsAll>(kBarFull0 + buf);
             const uint32_t row = s_row[buf];
             if (row == 0xffffffffu) break;
             const uint32_t *pl = planes + buf * (W * P);
@@ -701,7 +704,7 @@ __global__ void __launch_bounds__(kWsAll, 1)
                     }
                 }
             }
-            ws_arrive(kBarEmpty0 + buf);  // the plane set may be overwritten
+            ws_arrive<kWsAll>(kBarEmpty0 + buf);  // the plane set may be overwritten
         }
     }
 }
@@ -783,6 +786,23 @@ cudaError_t launch_e(const EncodeArgs &a, const EncodeCfg &c, size_t smem) {
     }
 }
 
+template <int E, int TENC>
+cudaError_t launch_ws(const EncodeArgs &a) {
+    const size_t ws_smem = (2 * 3 * (size_t)(E * TENC) + 64 * 3 + (TENC / 32) * 256) * sizeof(uint32_t);
+    cudaError_t err = cudaFuncSetAttribute(commit_ws_kernel<E, TENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem);
+    if (err != cudaSuccess) return err;
+    uint32_t grid = (uint32_t)a.num_sms * (TENC == 512 ? 1u : 2u);
+    if (grid > a.num_rows) grid = a.num_rows;
+    uint32_t *row_counter = a.num_rows >= 2 * grid ? a.row_counter : nullptr;
+    if (row_counter) {
+        err = cudaMemsetAsync(row_counter, 0xff, 2 * sizeof(uint32_t), a.stream);
+        if (err != cudaSuccess) return err;
+    }
+    commit_ws_kernel<E, TENC><<<grid, 2 * TENC, ws_smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows,
+                                                                     a.fuse_layers, 1u, row_counter);
+    return cudaGetLastError();
+}
+
 template <int IN32, int W>
 cudaError_t launch_w(const EncodeArgs &a) {
     const EncodeCfg c = pick_cfg(a.cw);
@@ -796,22 +816,12 @@ cudaError_t launch_w(const EncodeArgs &a) {
 #else
     // the hot instantiations (ZipTypes K = 4N limbs, exact power-of-two shapes) get a compile-time output width,
     // no padding predicates and the register prefetch of the next row
-    if (a.fuse_layers && IN32 == 2 && W == 3 && exact && c.E == 16 && c.T == 512 && a.out32 == 8 &&
-        !getenv("ZIPGPU_NO_WS")) {
-        // the warp-specialised commit kernel: one 1024-thread CTA per SM, two plane sets
-        const size_t ws_smem = (2 * 3 * (size_t)8192 + 64 * 3 + 16 * 256) * sizeof(uint32_t);
-        cudaError_t err = cudaFuncSetAttribute(commit_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem);
-        if (err != cudaSuccess) return err;
-        uint32_t grid = (uint32_t)a.num_sms;
-        if (grid > a.num_rows) grid = a.num_rows;
-        uint32_t *row_counter = a.num_rows >= 2 * grid ? a.row_counter : nullptr;
-        if (row_counter) {
-            err = cudaMemsetAsync(row_counter, 0xff, 2 * sizeof(uint32_t), a.stream);
-            if (err != cudaSuccess) return err;
-        }
-        commit_ws_kernel<<<grid, kWsAll, ws_smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows,
-                                                              a.fuse_layers, 1u, row_counter);
-        return cudaGetLastError();
+    // (zero-copy input, evals_copy != NULL, stays on the two-CTA fused kernel, which also writes the HBM copy)
+    if (a.fuse_layers && !a.evals_copy && IN32 == 2 && W == 3 && exact && a.out32 == 8 && !getenv("ZIPGPU_NO_WS")) {
+        // the warp-specialised commit kernel: an encode group and a hash group per CTA, two plane sets
+        if (c.E == 16 && c.T == 512) return launch_ws<16, 512>(a);
+        if (c.E == 8 && c.T == 512) return launch_ws<8, 512>(a);
+        if (c.E == 8 && c.T == 256) return launch_ws<8, 256>(a);
     }
     if (a.fuse_layers) {
         if (!exact) return cudaErrorInvalidConfiguration;

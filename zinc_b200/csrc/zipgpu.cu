@@ -785,10 +785,13 @@ static bool fusion_enabled() {
     return getenv("ZIPGPU_NO_FUSE") == nullptr;  // A/B knob: the two-kernel path (encode, then hash)
 }
 // rows from which commit_dev takes the fused kernel (ZIPGPU_FUSE_MIN_ROWS overrides: tests force it at small shapes)
-static size_t fuse_min_rows(const zipgpu_ctx *ctx, size_t cw) {
+static size_t fuse_min_rows(const zipgpu_ctx *ctx, const zipgpu_code *code) {
     if (const char *env = getenv("ZIPGPU_FUSE_MIN_ROWS")) return (size_t)atol(env);
-    // measured break-even (scratch/fuse_threshold_probe.py): 1024 rows at cw = 8192, 2048 rows at cw = 4096
-    return (size_t)(cw >= 8192 ? 6 : 10) * ctx->num_sms;
+    // measured break-even (scratch/fuse_threshold_probe.py, scripts/size_sweep.py): the warp-specialised kernel
+    // (Int<1> -> Int<4>, cw = 2048 / 4096 / 8192) wins from ~1000 rows (nv = 20: 0.144 vs 0.151 ms, nv = 21: 0.266 vs
+    // 0.285, nv = 22: 0.506 vs 0.538) and ties at 512; the two-CTA fused kernel of the other shapes from 2048 rows
+    const bool ws = code->in_limbs == 1 && code->out_limbs == 4 && (code->cw == 2048 || code->cw == 4096 || code->cw == 8192);
+    return (size_t)(ws || code->cw >= 8192 ? 6 : 10) * ctx->num_sms;
 }
 
 // Encode + Merkle of a row range on stream s, with optional profiling events.  until_level >= 0 stops the trees at the
@@ -805,7 +808,7 @@ static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     // run under the other's hashing; below that the two-kernel path, whose hash passes balance at subtree granularity,
     // is faster.
     const bool fuse = d_roots && d_layers && code->fused_levels > 0 && code->fused_levels <= code->depth &&
-                      num_rows >= fuse_min_rows(ctx, code->cw) && fusion_enabled();
+                      num_rows >= fuse_min_rows(ctx, code) && fusion_enabled();
     if (evals_copy && !fuse) return fail(ZIPGPU_ERR_INVALID, "zero-copy input needs the fused commit kernel");
     // Sparse code on the tensor cores: the GEMM (TMA + tcgen05, 6 warps per SM, hardly any INT32 work) and the BLAKE3
     // passes (INT32-alu-bound, no shared memory) use different parts of an SM.  Row chunks are encoded back to back on
@@ -937,7 +940,7 @@ struct HostJob {
 // and an L2 prefetch of system memory is a no-op), so the DMA pipeline stays the default.
 static bool zero_copy_eligible(zipgpu_code *code, size_t num_rows, const HostJob &job, const uint64_t **dev_alias) {
     if (!job.want_roots || job.rows_out || job.layers_out) return false;
-    if (code->fused_levels <= 0 || code->depth < code->fused_levels || num_rows < fuse_min_rows(code->ctx, code->cw)) return false;
+    if (code->fused_levels <= 0 || code->depth < code->fused_levels || num_rows < fuse_min_rows(code->ctx, code)) return false;
     if (!fusion_enabled() || !getenv("ZIPGPU_ZEROCOPY")) return false;
     if (((uintptr_t)job.evals & 31) != 0) return false;
     cudaPointerAttributes attr;
