@@ -790,7 +790,10 @@ static size_t fuse_min_rows(const zipgpu_ctx *ctx, const zipgpu_code *code) {
     // measured break-even (scratch/fuse_threshold_probe.py, scripts/size_sweep.py): the warp-specialised kernel
     // (Int<1> -> Int<4>, cw = 2048 / 4096 / 8192) wins from ~1000 rows (nv = 20: 0.144 vs 0.151 ms, nv = 21: 0.266 vs
     // 0.285, nv = 22: 0.506 vs 0.538) and ties at 512; the two-CTA fused kernel of the other shapes from 2048 rows
-    const bool ws = code->in_limbs == 1 && code->out_limbs == 4 && (code->cw == 2048 || code->cw == 4096 || code->cw == 8192);
+    // cw = 1024: already from 256 rows (nv = 17: 0.031 vs 0.035 ms, nv = 18: 0.052 vs 0.057; 32768 rows: 1.96 vs 2.04)
+    const bool ws = code->in_limbs == 1 && code->out_limbs == 4 &&
+                    (code->cw == 1024 || code->cw == 2048 || code->cw == 4096 || code->cw == 8192);
+    if (ws && code->cw == 1024) return 256;
     return (size_t)(ws || code->cw >= 8192 ? 6 : 10) * ctx->num_sms;
 }
 
