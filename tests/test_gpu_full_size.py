@@ -314,7 +314,7 @@ def test_longest_codeword_shape(fused, oracle, ctx, monkeypatch):
 
 
 @pytest.mark.parametrize("row_len,num_rows", [(4096, 148), (4096, 1000), (4096, 1333), (2048, 100), (2048, 777), (2048, 2048),
-                                              (1024, 200), (1024, 1025), (1024, 3000), (512, 300), (512, 4097)])
+                                              (1024, 200), (1024, 1025), (1024, 3000), (512, 300), (512, 4097), (256, 256), (256, 1000)])
 def test_warp_specialised_commit_kernel(row_len, num_rows, oracle, ctx, monkeypatch):
     """cw = 8192 / 4096 / 2048 (nv = 19 .. 24) take the warp-specialised commit kernel (per CTA one thread group encodes
     into alternating plane sets while the other hashes): codewords, every layer and the roots against the oracle, for row

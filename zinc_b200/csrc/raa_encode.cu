@@ -556,7 +556,7 @@ template <int ALL>
 __device__ __forceinline__ void ws_arrive(uint32_t id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(ALL) : "memory"); }
 
 // E entries per thread, kWsEnc threads per group: (16, 512) = cw 8192, (8, 512) = cw 4096, (8, 256) = cw 2048,
-// (4, 256) = cw 1024 -- the
+// (4, 256) = cw 1024, (4, 128) = cw 512 -- the
 // (E, T) of the plain encoder for those shapes, so the same pre-translated tables serve both kernels.  The 512-thread
 // CTA of cw = 2048 leaves room for two CTAs per SM.
 template <int E, int kWsEnc>
@@ -824,6 +824,7 @@ cudaError_t launch_w(const EncodeArgs &a) {
         if (c.E == 8 && c.T == 512) return launch_ws<8, 512>(a);
         if (c.E == 8 && c.T == 256) return launch_ws<8, 256>(a);
         if (c.E == 4 && c.T == 256) return launch_ws<4, 256>(a);
+        if (c.E == 4 && c.T == 128) return launch_ws<4, 128>(a);
     }
     if (a.fuse_layers) {
         if (!exact) return cudaErrorInvalidConfiguration;
