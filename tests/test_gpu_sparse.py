@@ -243,3 +243,33 @@ def test_device_commit_overlapped_equals_serial(num_rows, ctx, monkeypatch):
     nat.check(nat.lib().zipgpu_commit(h, nr, nat.ptr(ev_h), nat.ptr(rows_h), None, nat.ptr(roots_h)))
     assert np.array_equal(rows_h, serial[0][: nr * cw * 4].view(np.uint64))
     assert np.array_equal(roots_h, serial[2][: nr * 32])
+
+
+def test_sparse_code_create_rejects_bad_input(ctx):
+    """error behaviour of zipgpu_sparse_code_create: negative status + message, never a crash"""
+    import ctypes as C
+
+    from zinc_b200 import _native as nat
+
+    L = nat.lib()
+    cols = np.array([0, 1, 0, 1], dtype=np.uint32)
+    coef = np.ones(4, dtype=np.int64)
+
+    def create(row_len, cw, d, in_limbs, out_limbs, ca=cols, fa=coef):
+        h = C.c_void_p()
+        rc = L.zipgpu_sparse_code_create(ctx.handle, row_len, cw, d, in_limbs, out_limbs, nat.ptr(ca), nat.ptr(fa),
+                                         nat.ptr(ca), nat.ptr(fa), C.byref(h))
+        if rc == 0:
+            L.zipgpu_code_destroy(h)
+        return rc, L.zipgpu_last_error().decode()
+
+    assert create(2, 4, 2, 1, 4)[0] == 0
+    rc, msg = create(2, 5, 2, 1, 4)
+    assert rc < 0 and "even" in msg
+    rc, msg = create(2, 4, 3, 1, 4)
+    assert rc < 0 and "cells_per_row" in msg
+    rc, msg = create(2, 4, 2, 2, 1)
+    assert rc < 0 and "in_limbs" in msg
+    bad = np.array([0, 2, 0, 1], dtype=np.uint32)  # column 2 of a 2-column matrix
+    rc, msg = create(2, 4, 2, 1, 4, ca=bad)
+    assert rc < 0 and "out of range" in msg
