@@ -580,7 +580,17 @@ int zo_commit_mt(const uint64_t *evals, size_t num_rows, size_t row_len, int in_
 /* acc += coef * sext(v)   (mod 2^(64*out_limbs)); expand::<L,M>(coeff) * expand::<N,M>(value), code.rs:314 */
 static void zo_mul_add(uint64_t *acc, int out_limbs, const uint64_t *v, int in_limbs, int64_t coef) {
     uint64_t w[16], prod[16];
+    if (coef == 0) return; /* the product is zero; the reference still multiplies (code.rs:314) */
     zo_widen(v, in_limbs, w, out_limbs);
+    if (coef == 1) { /* the only non-zero value KeccakTranscript draws: a plain widening add ("tuned" CPU baseline) */
+        uint64_t c1 = 0;
+        for (int i = 0; i < out_limbs; i++) {
+            unsigned __int128 t = (unsigned __int128)acc[i] + w[i] + c1;
+            acc[i] = (uint64_t)t;
+            c1 = (uint64_t)(t >> 64);
+        }
+        return;
+    }
     uint64_t mag = coef < 0 ? (uint64_t)0 - (uint64_t)coef : (uint64_t)coef;
     unsigned __int128 carry = 0;
     for (int i = 0; i < out_limbs; i++) {
