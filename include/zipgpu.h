@@ -35,8 +35,13 @@
  *     order itself against the legacy default stream, so a caller that prepares buffers on another stream passes
  *     that stream here or synchronises first (zipgpu_ctx_sync waits for the context's streams).  The others take HOST pointers, perform the
  *     host<->device copies themselves (pipelined with the kernels) and return when the outputs are valid.
- *   - A context is bound to one GPU.  Multi-GPU = one context (and one process/thread) per GPU, each working on a
- *     contiguous row range (commit) or on a subset of the polynomials (batch_commit); see INTEGRATION.md.
+ *   - A context (zipgpu_ctx) is bound to one GPU.  Multi-GPU comes in two forms, both sharding a commit by contiguous
+ *     row range and a batch_commit by polynomial (rows are independent through encode AND hash, commit.rs:71-81):
+ *       zipgpu_mgpu_*                ONE process drives n GPUs (what `ZincProver` needs, zinc/prover.rs:313-315): a worker
+ *                                    thread and a context per device, slices copied over all PCIe links at once;
+ *       zipgpu_*_sharded + zipgpu_peer_roots_*   one process (or thread) per GPU, e.g. under torch.distributed.
+ *     In both the only exchange step -- every GPU receives every other GPU's 32-byte roots -- is part of the kernel
+ *     that produces the roots (P2P stores over NVLink), not a separate collective.  See INTEGRATION.md 4.
  */
 #ifndef ZIPGPU_H
 #define ZIPGPU_H
@@ -59,7 +64,8 @@ typedef enum {
     ZIPGPU_ERR_NOMEM = -3,       /* device or pinned-host allocation failed */
     ZIPGPU_ERR_UNSUPPORTED = -4, /* shape outside what the kernels implement */
     ZIPGPU_ERR_NO_DEVICE = -5,   /* no CUDA device / wrong architecture */
-    ZIPGPU_ERR_WIDTH = -6        /* code_raa.rs:68-72: out type too narrow for the codeword entries */
+    ZIPGPU_ERR_WIDTH = -6,       /* code_raa.rs:68-72: out type too narrow for the codeword entries */
+    ZIPGPU_ERR_PEER_TIMEOUT = -7 /* multi-GPU roots exchange: a peer GPU did not publish its roots in time */
 } zipgpu_status;
 
 /* ---- library / context ------------------------------------------------------------------------------- */
@@ -148,6 +154,8 @@ size_t zipgpu_data_num_rows(const zipgpu_data *data);
 const uint64_t *zipgpu_data_rows_device(const zipgpu_data *data);
 const uint8_t *zipgpu_data_layers_device(const zipgpu_data *data);
 const uint8_t *zipgpu_data_roots_device(const zipgpu_data *data);
+/* row-sharded commits (zipgpu_commit_resident_sharded): ALL roots of the commitment, total_rows*32 bytes; else NULL */
+const uint8_t *zipgpu_data_all_roots_device(const zipgpu_data *data);
 /* copy a row range of `rows` / `layers` back to the host */
 int zipgpu_data_read_rows(const zipgpu_data *data, size_t row_begin, size_t row_count, uint64_t *rows_out);
 int zipgpu_data_read_layers(const zipgpu_data *data, size_t row_begin, size_t row_count, uint8_t *layers_out);
@@ -157,6 +165,10 @@ int zipgpu_data_read_layers(const zipgpu_data *data, size_t row_begin, size_t ro
  *   col_values_out: num_cols * num_rows * out_limbs u64;  paths_out: num_cols * num_rows * depth * 32 bytes */
 int zipgpu_data_open_columns(const zipgpu_data *data, size_t num_cols, const uint32_t *columns,
                              uint64_t *col_values_out, uint8_t *paths_out);
+/* The same for a shard of a larger commitment: the outputs are laid out for `total_rows` rows per column and this
+ * data's rows land at rows [row_offset, row_offset + num_rows) of every column (multi-GPU openings in row order). */
+int zipgpu_data_open_columns_strided(const zipgpu_data *data, size_t num_cols, const uint32_t *columns,
+                                     uint64_t *col_values_out, uint8_t *paths_out, size_t total_rows, size_t row_offset);
 
 /* The same openings as the exact byte stream `open` appends to the proof for these columns (open_z.rs:124-143 over
  * PcsTranscript::write_integers / write_merkle_proof, pcs_transcript.rs:115-135,198-211): per column the num_rows
@@ -175,27 +187,96 @@ int zipgpu_data_combine_rows(const zipgpu_data *data, const uint64_t *coeffs, in
 int zipgpu_combine_rows_device(zipgpu_ctx *ctx, size_t num_rows, size_t row_len, const uint64_t *d_evals,
                                const uint64_t *d_coeffs, int out_limbs, uint64_t *d_combined_out, void *stream);
 
-/* ---- multi-GPU: all-gather of the row roots over NVLink peer memory ---------------------------------------
- * A commit sharded by row range over G GPUs of one node (one process and one context per GPU) has
- * one exchange step: the list of roots, MultilinearZipCommitment::roots (structs.rs:40-45), must be complete on every
- * GPU.  These calls do it with ONE kernel per GPU and step that stores the local roots into every peer's buffer
- * through peer memory, signals and waits -- no NCCL.  All ranks must call zipgpu_peer_roots_allgather the same number
- * of times.
- *   create : allocates this rank's result buffers (2 x total_rows*32 bytes, double-buffered) and flag words, and fills
- *            ipc_out (ZIPGPU_IPC_BYTES bytes) for the other ranks;
+/* ---- multi-GPU, one process (or thread) per GPU: the roots exchange of a row-sharded commit ------------------
+ * A commit sharded by row range over G GPUs of one node has one exchange step: the list of roots,
+ * MultilinearZipCommitment::roots (structs.rs:40-45), must be complete on every GPU.  A zipgpu_peer_roots object holds
+ * this rank's result buffers (2 x total_rows*32 bytes, double-buffered by step) and flag words, and the peers' as
+ * mapped over NVLink.  Every exchange is one "step"; all ranks must run the same number of steps.
+ *   create : allocates the buffers; fills ipc_out (ZIPGPU_IPC_BYTES bytes, nullable) for ranks in other processes;
  *   connect: ipc_all = the ZIPGPU_IPC_BYTES-byte blocks of ALL ranks in rank order (exchanged by the host, e.g.
- *            torch.distributed.all_gather); opens the peers' buffers (cudaIpcOpenMemHandle, enables peer access);
- *   allgather: d_local_roots (device, count*32 bytes; 16-byte aligned) = the roots of rows
- *            [row_begin, row_begin+count); enqueued on `stream`; when it completes, *d_all_out (returned
- *            immediately, valid until the call after next) holds all total_rows roots. */
+ *            torch.distributed.all_gather); opens the peers' buffers (cudaIpcOpenMemHandle);
+ *   connect_local: all = the objects of ranks 0..n-1, created in THIS process on different contexts; uses direct peer
+ *            access (cudaDeviceEnablePeerAccess), no IPC;
+ *   zipgpu_commit_device_sharded: commit of rows [row_begin, row_begin+count) of the commitment from device-resident
+ *            evaluations; the kernel that produces the roots stores each one into every peer's result buffer and its
+ *            last CTA publishes this rank's step counter and waits for the peers' (st.release.sys / ld.acquire.sys).
+ *            Enqueued on `stream`; when the stream has passed this point *d_all_roots_out (returned immediately, valid
+ *            until the call after next) holds all total_rows roots.  d_rows_out / d_layers_out nullable (scratch);
+ *   zipgpu_commit_resident_sharded: the same from HOST evaluations of the row range (pinned or pageable), prover data
+ *            kept behind *handle (nullable; NULL is returned for count == 0), all roots copied to roots_all_out
+ *            (host, total_rows*32 bytes, nullable).  Synchronises and reports ZIPGPU_ERR_PEER_TIMEOUT;
+ *   allgather: the stand-alone exchange for roots that already sit in device memory (d_local_roots: count*32 bytes,
+ *            16-byte aligned);
+ *   status : 0, or ZIPGPU_ERR_PEER_TIMEOUT if a kernel gave up waiting for a peer (bounded wait, default 20 s,
+ *            ZIPGPU_PEER_TIMEOUT_MS); check after synchronising.  After a timeout recreate the object on all ranks. */
 #define ZIPGPU_IPC_BYTES 64
 typedef struct zipgpu_peer_roots zipgpu_peer_roots;
 int zipgpu_peer_roots_create(zipgpu_ctx *ctx, size_t total_rows, int rank, int world, zipgpu_peer_roots **out,
                              uint8_t *ipc_out);
 int zipgpu_peer_roots_connect(zipgpu_peer_roots *pr, const uint8_t *ipc_all);
+int zipgpu_peer_roots_connect_local(zipgpu_peer_roots *const *all, int n);
 int zipgpu_peer_roots_allgather(zipgpu_peer_roots *pr, size_t row_begin, size_t count, const uint8_t *d_local_roots,
                                 void *stream, uint8_t **d_all_out);
+int zipgpu_peer_roots_status(zipgpu_peer_roots *pr);
 void zipgpu_peer_roots_destroy(zipgpu_peer_roots *pr);
+int zipgpu_commit_device_sharded(zipgpu_code *code, zipgpu_peer_roots *pr, size_t row_begin, size_t count,
+                                 const uint64_t *d_evals, uint64_t *d_rows_out, uint8_t *d_layers_out, void *stream,
+                                 uint8_t **d_all_roots_out);
+int zipgpu_commit_resident_sharded(zipgpu_code *code, zipgpu_peer_roots *pr, size_t row_begin, size_t count,
+                                   const uint64_t *evals, uint8_t *roots_all_out, zipgpu_data **handle);
+
+/* ---- multi-GPU, ONE process: a multi-device context behind the same commit API ---------------------------------
+ * What the reference's caller needs (one process: zinc/prover.rs:313-315 calls RaaCode::new, setup, commit): the
+ * device list is given once, every call below shards its work over those GPUs (a worker thread and a zipgpu_ctx per
+ * device; host slices go over all PCIe links concurrently) and returns results in the reference's order.
+ *   commit / commit_resident / encode_rows: GPU g of n takes rows [g*R/n, (g+1)*R/n) (balanced);
+ *   batch_commit: polynomial p goes to device p mod n (commit.rs:134-142 has no cross-polynomial dependency);
+ *   roots: exchanged between the GPUs inside the roots-producing kernel (see zipgpu_peer_roots above), so every
+ *          device holds the complete commitment; the host copy is ONE D2H from device 0;
+ *   data_open_columns / open_columns_wire: every GPU extracts its rows' entries and paths, output in row order
+ *          (the row -> column redistribution of `open`, open_z.rs:124-143: only the opened columns ever move);
+ *   data_combine_rows: per-GPU partial sums over its rows, added exactly on the host. */
+typedef struct zipgpu_mgpu zipgpu_mgpu;
+typedef struct zipgpu_mgpu_code zipgpu_mgpu_code;
+typedef struct zipgpu_mgpu_data zipgpu_mgpu_data;
+/* devices == NULL: the first n visible devices (n <= 0: all of them) */
+int zipgpu_mgpu_create(const int *devices, int n, zipgpu_mgpu **out);
+void zipgpu_mgpu_destroy(zipgpu_mgpu *m);
+int zipgpu_mgpu_num_devices(const zipgpu_mgpu *m);
+zipgpu_ctx *zipgpu_mgpu_ctx(zipgpu_mgpu *m, int index);
+/* kernels launched so far by all of its contexts */
+uint64_t zipgpu_mgpu_launch_count(const zipgpu_mgpu *m);
+/* same arguments and errors as zipgpu_code_create; the tables are uploaded to every device */
+int zipgpu_mgpu_code_create(zipgpu_mgpu *m, size_t row_len, size_t repetition_factor, int in_limbs, int out_limbs,
+                            const uint32_t *perm1, const uint32_t *perm2, zipgpu_mgpu_code **out);
+void zipgpu_mgpu_code_destroy(zipgpu_mgpu_code *code);
+zipgpu_code *zipgpu_mgpu_code_device(zipgpu_mgpu_code *code, int index);
+/* commit_no_merkle / encode_rows (commit.rs:104-119,158-183), host buffers */
+int zipgpu_mgpu_encode_rows(zipgpu_mgpu_code *code, size_t num_rows, const uint64_t *evals, uint64_t *rows_out);
+/* commit (commit.rs:50-87), host buffers; rows_out / layers_out nullable */
+int zipgpu_mgpu_commit(zipgpu_mgpu_code *code, size_t num_rows, const uint64_t *evals, uint64_t *rows_out,
+                       uint8_t *layers_out, uint8_t *roots_out);
+/* batch_commit (commit.rs:134-142); arrays as in zipgpu_batch_commit */
+int zipgpu_mgpu_batch_commit(zipgpu_mgpu_code *code, size_t num_polys, size_t num_rows, const uint64_t *const *evals,
+                             uint64_t *const *rows_out, uint8_t *const *layers_out, uint8_t *const *roots_out);
+/* commit with the prover data left on the GPUs that produced it */
+int zipgpu_mgpu_commit_resident(zipgpu_mgpu_code *code, size_t num_rows, const uint64_t *evals, uint8_t *roots_out,
+                                zipgpu_mgpu_data **handle);
+void zipgpu_mgpu_data_free(zipgpu_mgpu_data *data);
+size_t zipgpu_mgpu_data_num_rows(const zipgpu_mgpu_data *data);
+/* the shard held by device `index`: its zipgpu_data (NULL if it owns no rows) and row range */
+zipgpu_data *zipgpu_mgpu_data_shard(const zipgpu_mgpu_data *data, int index, size_t *row_begin, size_t *row_count);
+/* ALL roots of the commitment as they sit on device `index` after the exchange (num_rows*32 bytes; NULL if that
+ * device owns no rows) */
+const uint8_t *zipgpu_mgpu_data_roots_device(const zipgpu_mgpu_data *data, int index);
+/* as zipgpu_data_open_columns / _wire / _combine_rows, over all shards, outputs in row order */
+int zipgpu_mgpu_data_open_columns(const zipgpu_mgpu_data *data, size_t num_cols, const uint32_t *columns,
+                                  uint64_t *col_values_out, uint8_t *paths_out);
+size_t zipgpu_mgpu_data_open_columns_wire_bytes(const zipgpu_mgpu_data *data);
+int zipgpu_mgpu_data_open_columns_wire(const zipgpu_mgpu_data *data, size_t num_cols, const uint32_t *columns,
+                                       uint8_t *stream_out);
+int zipgpu_mgpu_data_combine_rows(const zipgpu_mgpu_data *data, const uint64_t *coeffs, int out_limbs,
+                                  uint64_t *combined_out);
 
 /* ---- measurement helpers (used by bench.py; no reference counterpart) -------------------------------- */
 /* When enabled, every commit/encode/merkle call records CUDA events around its kernels on the launch stream. */

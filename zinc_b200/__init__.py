@@ -11,6 +11,7 @@ from .zip import (  # noqa: F401
     Error,
     InvalidPcsParam,
     MerkleProof,
+    MultiContext,
     MerkleTree,
     MultilinearZip,
     MultilinearZipCommitment,

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libzipgpu.so")
 
-OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_WIDTH = 0, -1, -2, -3, -4, -5, -6
+OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_WIDTH, ERR_PEER_TIMEOUT = 0, -1, -2, -3, -4, -5, -6, -7
 
 u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
 vp, sz, i32, u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
@@ -41,6 +41,32 @@ SIGNATURES = {
     "zipgpu_peer_roots_connect": (i32, [vp, vp]),
     "zipgpu_peer_roots_allgather": (i32, [vp, sz, sz, vp, vp, C.POINTER(vp)]),
     "zipgpu_peer_roots_destroy": (None, [vp]),
+    "zipgpu_peer_roots_connect_local": (i32, [C.POINTER(vp), i32]),
+    "zipgpu_peer_roots_status": (i32, [vp]),
+    "zipgpu_commit_device_sharded": (i32, [vp, vp, sz, sz, vp, vp, vp, vp, C.POINTER(vp)]),
+    "zipgpu_commit_resident_sharded": (i32, [vp, vp, sz, sz, vp, vp, C.POINTER(vp)]),
+    "zipgpu_mgpu_create": (i32, [C.POINTER(i32), i32, C.POINTER(vp)]),
+    "zipgpu_mgpu_destroy": (None, [vp]),
+    "zipgpu_mgpu_num_devices": (i32, [vp]),
+    "zipgpu_mgpu_ctx": (vp, [vp, i32]),
+    "zipgpu_mgpu_launch_count": (u64, [vp]),
+    "zipgpu_mgpu_code_create": (i32, [vp, sz, sz, i32, i32, vp, vp, C.POINTER(vp)]),
+    "zipgpu_mgpu_code_destroy": (None, [vp]),
+    "zipgpu_mgpu_code_device": (vp, [vp, i32]),
+    "zipgpu_mgpu_encode_rows": (i32, [vp, sz, vp, vp]),
+    "zipgpu_mgpu_commit": (i32, [vp, sz, vp, vp, vp, vp]),
+    "zipgpu_mgpu_batch_commit": (i32, [vp, sz, sz, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "zipgpu_mgpu_commit_resident": (i32, [vp, sz, vp, vp, C.POINTER(vp)]),
+    "zipgpu_mgpu_data_free": (None, [vp]),
+    "zipgpu_mgpu_data_num_rows": (sz, [vp]),
+    "zipgpu_mgpu_data_shard": (vp, [vp, i32, C.POINTER(sz), C.POINTER(sz)]),
+    "zipgpu_mgpu_data_roots_device": (vp, [vp, i32]),
+    "zipgpu_mgpu_data_open_columns": (i32, [vp, sz, vp, vp, vp]),
+    "zipgpu_mgpu_data_open_columns_wire_bytes": (sz, [vp]),
+    "zipgpu_mgpu_data_open_columns_wire": (i32, [vp, sz, vp, vp]),
+    "zipgpu_mgpu_data_combine_rows": (i32, [vp, vp, i32, vp]),
+    "zipgpu_data_all_roots_device": (vp, [vp]),
+    "zipgpu_data_open_columns_strided": (i32, [vp, sz, vp, vp, vp, sz, sz]),
     "zipgpu_code_row_len": (sz, [vp]),
     "zipgpu_code_codeword_len": (sz, [vp]),
     "zipgpu_code_merkle_depth": (i32, [vp]),

@@ -30,6 +30,20 @@ int encode_compute_limbs(int in_limbs, uint32_t cw);
 bool encode_supported(int in_limbs, uint32_t cw, uint32_t row_len);
 cudaError_t launch_raa_encode(const EncodeArgs &a);
 
+// ---- multi-GPU: the roots exchange of a row-sharded commit (peer_roots.cu, merkle.cu) ----
+// One per zipgpu_peer_roots object, in device memory, written once when the peers are connected.  The kernel that
+// produces the roots of this GPU's row range stores every root straight into every peer's result buffer (P2P stores
+// over NVLink); its last CTA then publishes this rank's step counter in every peer's flag words and waits for theirs.
+constexpr int PEER_MAX = 16;
+struct RootsFanout {
+    uint8_t *bufs[2][PEER_MAX];            // [step parity][rank]: that rank's result buffer (total_rows * 32 bytes)
+    unsigned long long *flags[PEER_MAX];   // rank p's PEER_MAX flag words: flags[p][r] = last step rank r published to p
+    unsigned int *done;                    // local: CTAs of the publishing kernel that have finished their stores
+    unsigned int *status;                  // mapped host word: set to 1 + rank of a peer that did not show up in time
+    unsigned long long timeout_ns;         // bound on the wait (the kernel gives up and reports instead of hanging)
+    int rank, world;
+};
+
 // ---- K2/K3: BLAKE3 leaves + per-row Merkle levels (merkle.cu) ----
 struct MerkleArgs {
     const uint32_t *leaves;  // [num_rows][1<<depth][leaf32]
@@ -39,6 +53,14 @@ struct MerkleArgs {
     int depth;
     int leaf32;
     cudaStream_t stream;
+    int num_sms = 148;
+    // row-sharded commit: the launch that produces the roots also stores them at row `fan_row_begin + row` of every
+    // peer's result buffer and its last CTA runs the publish/wait handshake of step `fan_step` (see RootsFanout).
+    // Only honoured when one launch_merkle_levels call reaches the roots; *fan_fused reports whether it was.
+    const RootsFanout *fan = nullptr;
+    unsigned long long fan_step = 0;
+    uint32_t fan_row_begin = 0;
+    bool *fan_fused = nullptr;
 };
 bool merkle_supported(int leaf32);
 // returns the number of kernel launches through *launches
@@ -101,17 +123,11 @@ bool sparse_gemm_supported(int in_limbs, int out_limbs, uint32_t row_len, uint32
 size_t sparse_planes_bytes(uint32_t num_rows, uint32_t row_len, int in_limbs);
 cudaError_t launch_sparse_encode(const SparseEncodeArgs &a, int *launches);
 
-// ---- multi-GPU: roots all-gather over peer memory (peer_roots.cu) ----
-constexpr int PEER_MAX = 16;
-struct PeerRootsArgs {
-    uint8_t *peer_roots[PEER_MAX];            // every rank's result buffer of this step's parity (own included)
-    unsigned long long *peer_flags[PEER_MAX]; // every rank's `world` step counters
-    const uint8_t *src;                       // this rank's roots (device)
-    size_t offset, nbytes;                    // byte range of this rank inside a result buffer (multiples of 16)
-    int rank, world;
-    unsigned long long step;
-};
-cudaError_t launch_peer_roots_allgather(const PeerRootsArgs &a, cudaStream_t stream);
+// ---- multi-GPU: stand-alone form of the roots exchange (peer_roots.cu): copies `nbytes` of local roots into every
+// peer's buffer at `offset` and runs the same handshake; used when the roots were not produced by one launch (chunked
+// host pipelines that return the layers, ranks without rows) ----
+cudaError_t launch_peer_roots_allgather(const RootsFanout *fan, unsigned long long step, const uint8_t *src, size_t offset,
+                                        size_t nbytes, cudaStream_t stream);
 
 // ---- INT32 micro-benchmark (microbench.cu) ----
 cudaError_t launch_microbench_int32(int kind, int iters, int num_sms, cudaStream_t stream, uint32_t *d_sink,

@@ -13,6 +13,7 @@
 #include "blake3_dev.cuh"
 #include "common.cuh"
 #include "kernels.h"
+#include "peer_sync.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -70,16 +71,18 @@ __device__ __forceinline__ void load_leaf(const uint32_t *p, uint32_t (&x)[LEAF3
 template <int LEAF32, int H, int MINB>
 __global__ void __launch_bounds__(128, MINB)
     merkle_subtree_kernel(const uint32_t *__restrict__ leaves, uint8_t *layers, uint8_t *roots, uint32_t num_rows,
-                          TreeGeom g, uint32_t level_in, uint32_t one) {
+                          TreeGeom g, uint32_t level_in, uint32_t one, const RootsFanout *__restrict__ fan,
+                          unsigned long long fan_step, uint32_t fan_row_begin) {
     const uint32_t chunks_per_row = (g.cw >> level_in) >> H;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)num_rows * chunks_per_row) return;
-    const uint32_t row = (uint32_t)(gid / chunks_per_row);
+    const bool active = gid < (size_t)num_rows * chunks_per_row;
+    if (!active && !fan) return;
+    const uint32_t row = active ? (uint32_t)(gid / chunks_per_row) : 0u;
     const uint32_t c = (uint32_t)(gid % chunks_per_row);
 
     uint32_t stack[(H > 0) ? H : 1][8];
 #pragma unroll 1
-    for (uint32_t i = 0; i < (1u << H); i++) {
+    for (uint32_t i = 0; i < (active ? (1u << H) : 0u); i++) {
         const uint32_t idx = (c << H) | i;  // index within level_in
         uint32_t d[8];
         if constexpr (LEAF32 > 0) {
@@ -90,6 +93,7 @@ __global__ void __launch_bounds__(128, MINB)
         } else {
             load_digest(node_ptr(layers, roots, g, row, level_in, idx), d);
         }
+        if (H == 0 && fan && level_in == g.depth) fan_store_root(fan, fan_step, fan_row_begin + row, d);  // depth 0
         bool parked = false;
 #pragma unroll
         for (int l = 0; l < H; l++) {
@@ -105,6 +109,7 @@ __global__ void __launch_bounds__(128, MINB)
 #pragma unroll
                     for (int w = 0; w < 8; w++) d[w] = o.w[w];
                     store_digest(node_ptr(layers, roots, g, row, level_in + l + 1, idx >> (l + 1)), d);
+                    if (fan && level_in + l + 1 == g.depth) fan_store_root(fan, fan_step, fan_row_begin + row, d);
                 } else {
 #pragma unroll
                     for (int w = 0; w < 8; w++) stack[l][w] = d[w];
@@ -113,6 +118,7 @@ __global__ void __launch_bounds__(128, MINB)
             }
         }
     }
+    if (fan) fan_finish(fan, fan_step);  // every thread of every CTA (inactive ones included) gets here
 }
 
 // Latency path for small jobs (a prover's 2^12..2^16 commits, the reference's own criterion shapes): ONE CTA walks a
@@ -127,7 +133,8 @@ constexpr int CTA_TREE_BUF = (1 << CTA_TREE_MAX_LEVELS) + 2 * CTA_TREE_MAX_ROWS;
 template <int LEAF32>
 __global__ void __launch_bounds__(512)
     merkle_cta_tree_kernel(const uint32_t *__restrict__ leaves, uint8_t *layers, uint8_t *roots, uint32_t num_rows, TreeGeom g,
-                           uint32_t level_in, uint32_t S, uint32_t RL, uint32_t one) {
+                           uint32_t level_in, uint32_t S, uint32_t RL, uint32_t one, const RootsFanout *__restrict__ fan,
+                           unsigned long long fan_step, uint32_t fan_row_begin) {
     __shared__ __align__(8) uint32_t buf[8][CTA_TREE_BUF];
     const uint32_t subtrees_per_row = (g.cw >> level_in) >> S;
     const uint32_t row0 = RL ? blockIdx.x << RL : blockIdx.x / subtrees_per_row;
@@ -170,58 +177,62 @@ __global__ void __launch_bounds__(512)
 #pragma unroll
             for (int w = 0; w < 8; w++) buf[w][rl * stride + i] = o.w[w];
             store_digest(node_ptr(layers, roots, g, row, level_in + l, (b << nlog) | i), o.w);
+            if (fan && level_in + l == g.depth) fan_store_root(fan, fan_step, fan_row_begin + row, o.w);
         }
         __syncthreads();
     }
+    if (fan) fan_finish(fan, fan_step);
 }
 
 template <int LEAF32>
-cudaError_t launch_cta_tree(const MerkleArgs &a, const TreeGeom &g, uint32_t level_in, uint32_t S) {
+cudaError_t launch_cta_tree(const MerkleArgs &a, const TreeGeom &g, uint32_t level_in, uint32_t S, bool fan = false) {
     const uint32_t subtrees_per_row = (g.cw >> level_in) >> S;
     uint32_t RL = 0;
     // whole rows: pack rows while the CTA stays within 2^10 inputs and 32 rows -- but only as long as two CTAs per SM
     // remain (a tiny job is faster spread over many SMs than packed into full warps: commit of 2^12, 14.5 vs 19.6 us)
     if (subtrees_per_row == 1)
-        while (RL < 5 && (S + RL + 1) <= (uint32_t)CTA_TREE_MAX_LEVELS && (a.num_rows >> (RL + 1)) >= 2u * 148u) RL++;
+        while (RL < 5 && (S + RL + 1) <= (uint32_t)CTA_TREE_MAX_LEVELS && (a.num_rows >> (RL + 1)) >= 2u * (uint32_t)a.num_sms) RL++;
     const size_t grid = RL ? ((size_t)a.num_rows + (1u << RL) - 1) >> RL : (size_t)a.num_rows * subtrees_per_row;
     if (grid == 0) return cudaSuccess;
     if (grid > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     const uint32_t half = (1u << (S + RL)) / 2, block = half < 32 ? 32 : half;
     merkle_cta_tree_kernel<LEAF32><<<(uint32_t)grid, block, 0, a.stream>>>(a.leaves, a.layers, a.roots, a.num_rows, g, level_in,
-                                                                     S, RL, 1u);
+                                                                     S, RL, 1u, fan ? a.fan : nullptr, a.fan_step,
+                                                                     a.fan_row_begin);
     return cudaGetLastError();
 }
 
 // MINB = 5: ptxas then keeps the whole working set in 92 registers without spills; measured on B200 the leaf pass
 // runs 2 % faster at 5 resident blocks/SM than squeezed into 80 registers for 6 (1.837 vs 1.880 ms at nv = 24)
 template <int LEAF32, int H, int MINB = 5>
-cudaError_t launch_pass(const MerkleArgs &a, const TreeGeom &g, uint32_t level_in) {
+cudaError_t launch_pass(const MerkleArgs &a, const TreeGeom &g, uint32_t level_in, bool fan = false) {
     const size_t threads = (size_t)a.num_rows * ((g.cw >> level_in) >> H);
     const uint32_t block = 128;
     const size_t grid = (threads + block - 1) / block;
     if (grid == 0) return cudaSuccess;
     if (grid > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     merkle_subtree_kernel<LEAF32, H, MINB><<<(uint32_t)grid, block, 0, a.stream>>>(a.leaves, a.layers, a.roots, a.num_rows,
-                                                                           g, level_in, 1u);
+                                                                           g, level_in, 1u, fan ? a.fan : nullptr,
+                                                                           a.fan_step, a.fan_row_begin);
     return cudaGetLastError();
 }
 
 template <int LEAF32>
-cudaError_t launch_leaf_pass(const MerkleArgs &a, const TreeGeom &g, int h) {
+cudaError_t launch_leaf_pass(const MerkleArgs &a, const TreeGeom &g, int h, bool fan) {
     switch (h) {
-        case 0: return launch_pass<LEAF32, 0>(a, g, 0);
-        case 1: return launch_pass<LEAF32, 1>(a, g, 0);
-        case 2: return launch_pass<LEAF32, 2>(a, g, 0);
-        default: return launch_pass<LEAF32, 3>(a, g, 0);
+        case 0: return launch_pass<LEAF32, 0>(a, g, 0, fan);
+        case 1: return launch_pass<LEAF32, 1>(a, g, 0, fan);
+        case 2: return launch_pass<LEAF32, 2>(a, g, 0, fan);
+        default: return launch_pass<LEAF32, 3>(a, g, 0, fan);
     }
 }
 
-cudaError_t launch_node_pass(const MerkleArgs &a, const TreeGeom &g, uint32_t level_in, int h) {
+cudaError_t launch_node_pass(const MerkleArgs &a, const TreeGeom &g, uint32_t level_in, int h, bool fan) {
     switch (h) {
-        case 1: return launch_pass<0, 1>(a, g, level_in);
-        case 2: return launch_pass<0, 2>(a, g, level_in);
-        case 3: return launch_pass<0, 3>(a, g, level_in);
-        default: return launch_pass<0, 4>(a, g, level_in);
+        case 1: return launch_pass<0, 1>(a, g, level_in, fan);
+        case 2: return launch_pass<0, 2>(a, g, level_in, fan);
+        case 3: return launch_pass<0, 3>(a, g, level_in, fan);
+        default: return launch_pass<0, 4>(a, g, level_in, fan);
     }
 }
 
@@ -239,22 +250,28 @@ cudaError_t launch_merkle_levels(const MerkleArgs &a, int from_level, int until_
     if (until_level < 0 || until_level > a.depth) until_level = a.depth;
     int n = 0, level = from_level;
     cudaError_t err = cudaSuccess;
+    // the launch that reaches the roots carries the multi-GPU roots exchange (RootsFanout), if one was asked for
+    const bool want_fan = a.fan != nullptr && until_level == a.depth && a.num_rows > 0;
+    bool fused = false;
+    if (a.fan_fused) *a.fan_fused = false;
     // small whole trees: the CTA-per-subtree latency path (at most 2^18 leaves in total, i.e. <= 256 CTAs of work)
     if (from_level == 0 && until_level == a.depth && a.depth >= 1 && ((size_t)a.num_rows << a.depth) <= ((size_t)1 << 18) &&
         !getenv("ZIPGPU_NO_CTA_TREE")) {
         while (level < a.depth) {
             const uint32_t S = (uint32_t)std::min(CTA_TREE_MAX_LEVELS, a.depth - level);
+            const bool fan = want_fan && level + (int)S == a.depth;
+            fused |= fan;
             if (level == 0) {
                 switch (a.leaf32) {
-                    case 2: err = launch_cta_tree<2>(a, g, 0, S); break;
-                    case 4: err = launch_cta_tree<4>(a, g, 0, S); break;
-                    case 6: err = launch_cta_tree<6>(a, g, 0, S); break;
-                    case 8: err = launch_cta_tree<8>(a, g, 0, S); break;
-                    case 16: err = launch_cta_tree<16>(a, g, 0, S); break;
+                    case 2: err = launch_cta_tree<2>(a, g, 0, S, fan); break;
+                    case 4: err = launch_cta_tree<4>(a, g, 0, S, fan); break;
+                    case 6: err = launch_cta_tree<6>(a, g, 0, S, fan); break;
+                    case 8: err = launch_cta_tree<8>(a, g, 0, S, fan); break;
+                    case 16: err = launch_cta_tree<16>(a, g, 0, S, fan); break;
                     default: return cudaErrorInvalidValue;
                 }
             } else {
-                err = launch_cta_tree<0>(a, g, (uint32_t)level, S);
+                err = launch_cta_tree<0>(a, g, (uint32_t)level, S, fan);
             }
             if (err != cudaSuccess) return err;
             n++;
@@ -262,17 +279,20 @@ cudaError_t launch_merkle_levels(const MerkleArgs &a, int from_level, int until_
         }
         if (reached) *reached = level;
         if (launches) *launches = n;
+        if (a.fan_fused) *a.fan_fused = fused;
         return cudaSuccess;
     }
     if (level == 0 && (until_level > 0 || a.depth == 0)) {
         // the leaf pass covers levels 0..min(3, depth) (15/16 of all compressions)
         const int h = a.depth < 3 ? a.depth : 3;
+        const bool fan = want_fan && h == a.depth;
+        fused |= fan;
         switch (a.leaf32) {
-            case 2: err = launch_leaf_pass<2>(a, g, h); break;
-            case 4: err = launch_leaf_pass<4>(a, g, h); break;
-            case 6: err = launch_leaf_pass<6>(a, g, h); break;
-            case 8: err = launch_leaf_pass<8>(a, g, h); break;
-            case 16: err = launch_leaf_pass<16>(a, g, h); break;
+            case 2: err = launch_leaf_pass<2>(a, g, h, fan); break;
+            case 4: err = launch_leaf_pass<4>(a, g, h, fan); break;
+            case 6: err = launch_leaf_pass<6>(a, g, h, fan); break;
+            case 8: err = launch_leaf_pass<8>(a, g, h, fan); break;
+            case 16: err = launch_leaf_pass<16>(a, g, h, fan); break;
             default: return cudaErrorInvalidValue;
         }
         if (err != cudaSuccess) return err;
@@ -285,7 +305,9 @@ cudaError_t launch_merkle_levels(const MerkleArgs &a, int from_level, int until_
         // the CTA-per-subtree kernel (one launch per 10 levels, one compression of latency per level)
         if (cta_top_ok && level > 0 && ((size_t)a.num_rows << (a.depth - level)) <= ((size_t)1 << 18)) {
             const uint32_t S = (uint32_t)std::min(CTA_TREE_MAX_LEVELS, a.depth - level);
-            err = launch_cta_tree<0>(a, g, (uint32_t)level, S);
+            const bool fan = want_fan && level + (int)S == a.depth;
+            fused |= fan;
+            err = launch_cta_tree<0>(a, g, (uint32_t)level, S, fan);
             if (err != cudaSuccess) return err;
             n++;
             level += (int)S;
@@ -293,13 +315,16 @@ cudaError_t launch_merkle_levels(const MerkleArgs &a, int from_level, int until_
         }
         const int remaining = a.depth - level;
         const int h = remaining <= 4 ? remaining : 3;
-        err = launch_node_pass(a, g, (uint32_t)level, h);
+        const bool fan = want_fan && level + h == a.depth;
+        fused |= fan;
+        err = launch_node_pass(a, g, (uint32_t)level, h, fan);
         if (err != cudaSuccess) return err;
         n++;
         level += h;
     }
     if (reached) *reached = level;
     if (launches) *launches = n;
+    if (a.fan_fused) *a.fan_fused = fused;
     return cudaSuccess;
 }
 

@@ -1,0 +1,84 @@
+// zinc_b200/csrc/peer_sync.cuh -- device side of the roots exchange of a row-sharded commit (RootsFanout, kernels.h).
+//
+// The reference's commitment is the list of per-row roots (commit.rs:71-81), so a commit sharded by row range has ONE
+// exchange step: every GPU needs every other GPU's 32-byte roots.  It is fused into the kernel that produces them:
+//   * fan_store_root: the thread that holds a finished root stores it into every rank's result buffer (P2P stores
+//     through NVLink / NVSwitch; the own buffer is one of them);
+//   * fan_finish: every CTA fences its stores at system scope and counts itself done; the LAST CTA of the launch
+//     publishes this rank's step counter into every peer's flag words (st.release.sys) and waits until every peer's
+//     counter in the own flag words has reached the step (ld.acquire.sys).  When the kernel completes, the own result
+//     buffer holds all roots.  The wait is bounded: a peer that does not show up within timeout_ns is reported through
+//     the mapped status word and the kernel ends -- the context stays usable and the host call returns an error.
+#pragma once
+#include <stdint.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace zipgpu {
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void fan_store_root(const RootsFanout *fan, unsigned long long step, uint32_t global_row,
+                                               const uint32_t (&d)[8]) {
+    const int par = (int)(step & 1ull);
+    for (int p = 0; p < fan->world; p++) st_global_v8(fan->bufs[par][p] + (size_t)global_row * 32, d);
+}
+
+// publish + wait, by the threads tid < world of ONE CTA (called by the last CTA of the launch, or by the stand-alone
+// exchange kernel).  Preceded by a system-scope fence of the calling thread.
+__device__ __forceinline__ void fan_handshake(const RootsFanout *fan, unsigned long long step, uint32_t tid) {
+    if (tid < (uint32_t)fan->world) {
+        __threadfence_system();
+        st_release_sys_u64(fan->flags[tid] + fan->rank, step);  // flag word [my rank] of peer `tid`
+        const unsigned long long *mine = fan->flags[fan->rank] + tid;
+        const unsigned long long t0 = global_timer_ns();
+        unsigned int spins = 0;
+        while (ld_acquire_sys_u64(mine) < step) {
+            if ((++spins & 63u) == 0) {
+                if (global_timer_ns() - t0 > fan->timeout_ns) {
+                    *reinterpret_cast<volatile unsigned int *>(fan->status) = 1u + tid;  // mapped host memory
+                    __threadfence_system();
+                    break;
+                }
+                __nanosleep(200);
+            }
+        }
+    }
+}
+
+// End of a kernel that called fan_store_root.  EVERY thread of EVERY CTA must reach it (it contains barriers).
+__device__ __forceinline__ void fan_finish(const RootsFanout *fan, unsigned long long step) {
+    __shared__ unsigned int s_last;
+    __threadfence_system();  // this thread's peer stores are visible system-wide before the CTA counts itself done
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();  // cumulative over what the barrier made visible to this thread
+        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        const unsigned int prev = atomicAdd(fan->done, 1u);
+        s_last = (prev == total - 1u) ? 1u : 0u;
+        if (s_last) {
+            *fan->done = 0u;  // re-armed for the next launch on this stream
+            __threadfence_system();
+        }
+    }
+    __syncthreads();
+    if (s_last) {
+        fan_handshake(fan, step, threadIdx.x);
+        __threadfence_system();
+    }
+}
+
+}  // namespace zipgpu

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
                       const uint16_t *__restrict__ tab1, const uint16_t *__restrict__ tab2,
                       const uint8_t *__restrict__ colw, uint32_t num_rows, uint32_t row_len, uint32_t cw,
                       uint32_t out32_rt, uint8_t *__restrict__ layers, uint32_t one, uint32_t *__restrict__ evals_copy,
-                      uint32_t *__restrict__ row_counter, uint32_t endgame_q) {
+                      uint32_t *__restrict__ row_counter) {
     static_assert(!FUSE || (EXACT && OUT32 != 0), "the fused commit kernel exists for exact shapes only");
     static_assert(!BULK || (EXACT && OUT32 == 8 && W <= 4), "bulk write-out: exact shapes, 32-byte records");
     extern __shared__ __align__(16) uint32_t smem[];
@@ -280,40 +280,21 @@ __global__ void __launch_bounds__(MAXT, MINB)
     // between its two CTAs -- measured with static rows, one CTA of every pair finished its 14 rows in 1.05 ms and
     // left the other alone for the remaining 0.9 ms, with nobody to hide its encode phases.  Claiming keeps every
     // pair together to the end.  The claim for the row after this one is made early and published through a barrier.
-    // End game: the CTA that is being starved by its SM-mate (its rows take several times the fastest CTA's) stops
-    // claiming once less than one round of rows is left, so that the last rows go to CTAs that finish them quickly and
-    // the kernel does not wait for a slow CTA that has just started a row.  row_counter[1] = fastest row time seen.
-    // FUSE: the claim is made only after the hash phase (a starved CTA spends ~0.4 ms in it; claiming a row ahead would
-    // commit it to a row long before it can know that the rows are running out); the other kernels claim a row ahead,
-    // which gives the L2 prefetch of the input a whole row-time of lead.
+    // FUSE: the claim is made only after the hash phase (a starved CTA spends ~0.4 ms in it and would otherwise sit on
+    // a claimed row for that long); the other kernels claim a row ahead, which gives the L2 prefetch of the input a
+    // whole row-time of lead.  Every claim is a plain atomicAdd: a row is processed if and only if somebody claimed it,
+    // and nobody ever declines one (round 1 had a timing heuristic here that let slow CTAs stop claiming near the end;
+    // it made whether a row gets processed depend on %globaltimer and is gone).
     __shared__ volatile uint32_t s_next;
     constexpr uint32_t kPending = 0xffffffffu;
-    unsigned long long t_row = 0;
-    uint32_t my_row_ns = 0;
     auto publish_next = [&](uint32_t nx) {
         // pull that row's input into L2 now: one bulk prefetch, no registers
         if (nx < num_rows && !evals_copy)  // (a no-op on system memory)
             prefetch_l2_bulk(evals + (size_t)nx * in_words, in_words * 4u);
         s_next = nx;
     };
-    auto claim_late = [&]() {  // thread 0 only, FUSE: with the end-game rule
-        unsigned long long now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (t_row) {
-            my_row_ns = (uint32_t)(now - t_row);
-            atomicMin(row_counter + 1, my_row_ns);
-        }
-        t_row = now;
-        const uint32_t fastest = *reinterpret_cast<volatile uint32_t *>(row_counter + 1);
-        // word 0 counts the claims made so far minus one (armed to 0xffffffff by one memset): row = gridDim.x + claims
-        const uint32_t claimed = gridDim.x + *reinterpret_cast<volatile uint32_t *>(row_counter) + 1u;
-        // a starved CTA (its rows take several times the fastest CTA's) starts another row only if that row can be
-        // finished before the fast CTAs have consumed what is left -- otherwise the whole kernel would wait for it
-        const bool slow = my_row_ns > 2u * fastest;
-        const unsigned long long left = claimed < num_rows ? num_rows - claimed : 0;
-        const unsigned long long t_left = left * fastest / (gridDim.x / 2 + 1);  // ns until the rows run out
-        const bool too_late = (unsigned long long)my_row_ns * endgame_q > 4ull * t_left;
-        publish_next((slow && too_late) ? num_rows : gridDim.x + atomicAdd(row_counter, 1u) + 1u);
+    auto claim_late = [&]() {  // thread 0 only, FUSE
+        publish_next(gridDim.x + atomicAdd(row_counter, 1u) + 1u);
     };
     constexpr bool LATE_CLAIM = FUSE && MINB >= 2;  // with one CTA per SM nobody hides the unprefetched input load
     while (row < num_rows) {
@@ -756,12 +737,12 @@ cudaError_t launch_one(const EncodeArgs &a, int T, size_t smem) {
     if (grid > a.num_rows) grid = a.num_rows;
     // few rows per CTA: static rows (arming and claiming cost more than the imbalance they remove; measured at nv = 20)
     uint32_t *row_counter = a.num_rows >= 6 * grid ? a.row_counter : nullptr;
-    if (row_counter) {  // word 0: claims so far - 1, word 1: fastest row time seen; one fill arms both
+    if (row_counter) {  // word 0: claims so far - 1 (word 1 unused)
         err = cudaMemsetAsync(row_counter, 0xff, 2 * sizeof(uint32_t), a.stream);
         if (err != cudaSuccess) return err;
     }
     kern<<<grid, T, smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows, a.row_len, a.cw,
-                                      a.out32, a.fuse_layers, 1u, a.evals_copy, row_counter, getenv("ZIPGPU_ENDGAME_Q") ? (uint32_t)atoi(getenv("ZIPGPU_ENDGAME_Q")) : 1u);
+                                      a.out32, a.fuse_layers, 1u, a.evals_copy, row_counter);
     return cudaGetLastError();
 }
 

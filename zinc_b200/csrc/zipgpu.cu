@@ -100,6 +100,8 @@ struct zipgpu_data {
     uint64_t *d_rows;
     uint8_t *d_layers;
     uint8_t *d_roots;
+    uint8_t *d_roots_all = nullptr;  // row-sharded commit: ALL roots of the commitment (after the exchange)
+    size_t total_rows = 0;
 };
 
 static thread_local std::string g_err;
@@ -199,6 +201,17 @@ struct DevGuard {
     DevGuard(zipgpu_ctx *c, cudaStream_t st) : ctx(c), s(st), prev(current) { current = this; }
     ~DevGuard() {
         current = prev;
+        if (!owned.empty()) {
+            // an early error return: the copy / second kernel streams may still be using these buffers, and the cache
+            // only orders a reuse after `s` -- wait for all of the context's streams before handing them back
+            cudaStreamSynchronize(ctx->h2d);
+            cudaStreamSynchronize(ctx->d2h);
+            cudaStreamSynchronize(ctx->stream2);
+            cudaStreamSynchronize(ctx->stream_hi);
+            cudaStreamSynchronize(ctx->stream);
+            if (s != ctx->stream) cudaStreamSynchronize(s);
+            cudaGetLastError();
+        }
         for (void *p : owned) dev_free(ctx, p, s);
     }
     void add(void *p) { owned.push_back(p); }
@@ -230,6 +243,10 @@ static cudaError_t dev_free_tracked(zipgpu_ctx *c, void *p, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------------
 extern "C" const char *zipgpu_version(void) { return "zipgpu 0.1 (sm_100a)"; }
 extern "C" const char *zipgpu_last_error(void) { return g_err.c_str(); }
+namespace zipgpu {
+// mgpu.cu runs the per-device calls on worker threads and hands their (thread-local) message to the calling thread
+void set_last_error(const std::string &msg) { g_err = msg; }
+}
 
 extern "C" int zipgpu_device_count(int *count) {
     if (!count) return fail(ZIPGPU_ERR_INVALID, "count is NULL");
@@ -571,23 +588,33 @@ extern "C" size_t zipgpu_code_codeword_len(const zipgpu_code *c) { return c ? c-
 extern "C" int zipgpu_code_merkle_depth(const zipgpu_code *c) { return c ? ilog2(next_pow2(c->cw)) : -1; }
 
 // ------------------------------------------------------------------------------------------------------
-// multi-GPU: roots all-gather over peer memory (peer_roots.cu)
+// multi-GPU: the roots exchange of a row-sharded commit (peer_sync.cuh, peer_roots.cu, merkle.cu)
 // ------------------------------------------------------------------------------------------------------
 struct zipgpu_peer_roots {
     zipgpu_ctx *ctx;
     size_t total_rows, buf_bytes;
     int rank, world;
-    uint8_t *base = nullptr;                 // own allocation: [buffer 0 | buffer 1 | flags (PEER_MAX u64)]
-    uint8_t *peer_base[PEER_MAX] = {};       // every rank's allocation as mapped here (own = base)
+    uint8_t *base = nullptr;                 // own allocation: [buffer 0 | buffer 1 | flags (PEER_MAX u64) | done counter]
+    uint8_t *peer_base[PEER_MAX] = {};       // every rank's allocation as addressable from this device (own = base)
+    bool ipc_opened[PEER_MAX] = {};          // mapped with cudaIpcOpenMemHandle (to be closed)
+    RootsFanout *d_fan = nullptr;            // the device-side descriptor, written once at connect time
+    unsigned int *h_status = nullptr;        // mapped pinned host word the kernels report a missing peer through
     bool connected = false;
-    unsigned long long step = 0;
+    unsigned long long step = 0;             // steps launched so far (incremented only after a successful launch)
 };
+
+static unsigned long long peer_timeout_ns() {
+    if (const char *env = getenv("ZIPGPU_PEER_TIMEOUT_MS")) return (unsigned long long)atoll(env) * 1000000ull;
+    return 20ull * 1000000000ull;
+}
+
+extern "C" void zipgpu_peer_roots_destroy(zipgpu_peer_roots *p);
 
 extern "C" int zipgpu_peer_roots_create(zipgpu_ctx *ctx, size_t total_rows, int rank, int world, zipgpu_peer_roots **out,
                                         uint8_t *ipc_out) {
     if (!out) return fail(ZIPGPU_ERR_INVALID, "out is NULL");
     *out = nullptr;
-    if (!ctx || !ipc_out) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (!ctx) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
     if (world < 1 || world > PEER_MAX || rank < 0 || rank >= world) return fail(ZIPGPU_ERR_INVALID, "bad rank / world");
     static_assert(sizeof(cudaIpcMemHandle_t) <= ZIPGPU_IPC_BYTES, "IPC handle size");
     API_LOCK(ctx);
@@ -599,25 +626,53 @@ extern "C" int zipgpu_peer_roots_create(zipgpu_ctx *ctx, size_t total_rows, int 
     p->buf_bytes = (total_rows * 32 + 255) & ~(size_t)255;
     p->rank = rank;
     p->world = world;
-    const size_t bytes = 2 * p->buf_bytes + PEER_MAX * sizeof(unsigned long long);
+    const size_t bytes = 2 * p->buf_bytes + PEER_MAX * sizeof(unsigned long long) + 256;
     cudaError_t e = cudaMalloc(&p->base, bytes);  // IPC needs a cudaMalloc allocation of its own
     if (e == cudaSuccess) e = cudaMemset(p->base, 0, bytes);
-    cudaIpcMemHandle_t h;
-    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p->base);
-    if (e != cudaSuccess) {
-        cudaFree(p->base);
-        delete p;
-        return cuda_fail(e, "peer roots buffer");
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_fan, sizeof(RootsFanout));
+    if (e == cudaSuccess) e = cudaHostAlloc(&p->h_status, sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e == cudaSuccess) *p->h_status = 0;
+    if (e == cudaSuccess && ipc_out) {
+        cudaIpcMemHandle_t h;
+        e = cudaIpcGetMemHandle(&h, p->base);
+        if (e == cudaSuccess) {
+            memset(ipc_out, 0, ZIPGPU_IPC_BYTES);
+            memcpy(ipc_out, &h, sizeof(h));
+        }
     }
-    memset(ipc_out, 0, ZIPGPU_IPC_BYTES);
-    memcpy(ipc_out, &h, sizeof(h));
+    if (e != cudaSuccess) {
+        zipgpu_peer_roots_destroy(p);
+        return cuda_fail(e, "peer roots buffers");
+    }
     p->peer_base[rank] = p->base;
     *out = p;
     return ZIPGPU_OK;
 }
 
+// every rank's base pointer is known: write the device-side descriptor
+static int peer_roots_finish_connect(zipgpu_peer_roots *p) {
+    RootsFanout f;
+    memset(&f, 0, sizeof(f));
+    for (int r = 0; r < p->world; r++) {
+        f.bufs[0][r] = p->peer_base[r];
+        f.bufs[1][r] = p->peer_base[r] + p->buf_bytes;
+        f.flags[r] = reinterpret_cast<unsigned long long *>(p->peer_base[r] + 2 * p->buf_bytes);
+    }
+    f.done = reinterpret_cast<unsigned int *>(p->base + 2 * p->buf_bytes + PEER_MAX * sizeof(unsigned long long));
+    void *d_status = nullptr;
+    CU(cudaHostGetDevicePointer(&d_status, p->h_status, 0));
+    f.status = static_cast<unsigned int *>(d_status);
+    f.timeout_ns = peer_timeout_ns();
+    f.rank = p->rank;
+    f.world = p->world;
+    CU(cudaMemcpy(p->d_fan, &f, sizeof(f), cudaMemcpyHostToDevice));
+    p->connected = true;
+    return ZIPGPU_OK;
+}
+
+// one process per GPU: the peers' buffers arrive as CUDA IPC handles
 extern "C" int zipgpu_peer_roots_connect(zipgpu_peer_roots *p, const uint8_t *ipc_all) {
-    if (!p || !ipc_all) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (!p || (!ipc_all && p->world > 1)) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
     API_LOCK(p->ctx);
     CU(cudaSetDevice(p->ctx->device));
     for (int r = 0; r < p->world; r++) {
@@ -628,37 +683,67 @@ extern "C" int zipgpu_peer_roots_connect(zipgpu_peer_roots *p, const uint8_t *ip
         cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle (peer roots)");
         p->peer_base[r] = static_cast<uint8_t *>(ptr);
+        p->ipc_opened[r] = true;
     }
-    p->connected = true;
+    return peer_roots_finish_connect(p);
+}
+
+// all ranks in ONE process (one context per device): direct peer access, no IPC
+extern "C" int zipgpu_peer_roots_connect_local(zipgpu_peer_roots *const *all, int n) {
+    if (!all || n < 1 || n > PEER_MAX) return fail(ZIPGPU_ERR_INVALID, "bad argument");
+    for (int r = 0; r < n; r++)
+        if (!all[r] || all[r]->rank != r || all[r]->world != n || all[r]->total_rows != all[0]->total_rows)
+            return fail(ZIPGPU_ERR_INVALID, "connect_local: the objects must be ranks 0..n-1 of one exchange");
+    for (int r = 0; r < n; r++) {
+        zipgpu_peer_roots *p = all[r];
+        API_LOCK(p->ctx);
+        CU(cudaSetDevice(p->ctx->device));
+        for (int q = 0; q < n; q++) {
+            if (q == r) continue;
+            const int peer_dev = all[q]->ctx->device;
+            if (peer_dev != p->ctx->device) {
+                int can = 0;
+                CU(cudaDeviceCanAccessPeer(&can, p->ctx->device, peer_dev));
+                if (!can)
+                    return fail(ZIPGPU_ERR_UNSUPPORTED, "device " + std::to_string(p->ctx->device) + " cannot access device " +
+                                                            std::to_string(peer_dev) + " (no peer access)");
+                cudaError_t e = cudaDeviceEnablePeerAccess(peer_dev, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+            }
+            p->peer_base[q] = all[q]->base;
+        }
+        int rc = peer_roots_finish_connect(p);
+        if (rc) return rc;
+    }
     return ZIPGPU_OK;
+}
+
+// 0, or ZIPGPU_ERR_PEER_TIMEOUT if a kernel of this exchange gave up waiting for a peer (call after synchronising)
+extern "C" int zipgpu_peer_roots_status(zipgpu_peer_roots *p) {
+    if (!p) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    const unsigned int st = *reinterpret_cast<volatile unsigned int *>(p->h_status);
+    if (st == 0) return ZIPGPU_OK;
+    return fail(ZIPGPU_ERR_PEER_TIMEOUT, "roots exchange: rank " + std::to_string(st - 1) + " did not publish its roots within " +
+                                             std::to_string(peer_timeout_ns() / 1000000ull) +
+                                             " ms; the exchange object must be recreated on all ranks");
 }
 
 extern "C" int zipgpu_peer_roots_allgather(zipgpu_peer_roots *p, size_t row_begin, size_t count, const uint8_t *d_local_roots,
                                            void *stream, uint8_t **d_all_out) {
     if (!p || !d_all_out || (count && !d_local_roots)) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
-    if (!p->connected && p->world > 1) return fail(ZIPGPU_ERR_INVALID, "zipgpu_peer_roots_connect has not been called");
+    if (!p->connected) return fail(ZIPGPU_ERR_INVALID, "zipgpu_peer_roots_connect has not been called");
     if (row_begin + count > p->total_rows) return fail(ZIPGPU_ERR_INVALID, "row range outside the commitment");
     if (((row_begin * 32) | (uintptr_t)d_local_roots) & 15) return fail(ZIPGPU_ERR_INVALID, "roots must be 16-byte aligned");
     API_LOCK(p->ctx);
     CU(cudaSetDevice(p->ctx->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->ctx->stream;
-    p->step++;
-    const size_t parity_off = (p->step & 1) * p->buf_bytes;
-    PeerRootsArgs a;
-    for (int r = 0; r < PEER_MAX; r++) {
-        a.peer_roots[r] = r < p->world ? p->peer_base[r] + parity_off : nullptr;
-        a.peer_flags[r] = r < p->world ? reinterpret_cast<unsigned long long *>(p->peer_base[r] + 2 * p->buf_bytes) : nullptr;
-    }
-    a.src = d_local_roots;
-    a.offset = row_begin * 32;
-    a.nbytes = count * 32;
-    a.rank = p->rank;
-    a.world = p->world;
-    a.step = p->step;
-    cudaError_t e = launch_peer_roots_allgather(a, s);
+    const unsigned long long step = p->step + 1;
+    cudaError_t e = launch_peer_roots_allgather(p->d_fan, step, d_local_roots, row_begin * 32, count * 32, s);
     if (e != cudaSuccess) return cuda_fail(e, "launch_peer_roots_allgather");
+    p->step = step;  // only now: a failed launch must not leave this rank a step ahead of its peers
     p->ctx->launches++;
-    *d_all_out = p->base + parity_off;
+    *d_all_out = p->base + (step & 1) * p->buf_bytes;
     return ZIPGPU_OK;
 }
 
@@ -667,8 +752,11 @@ extern "C" void zipgpu_peer_roots_destroy(zipgpu_peer_roots *p) {
     cudaSetDevice(p->ctx->device);
     cudaDeviceSynchronize();
     for (int r = 0; r < p->world; r++)
-        if (r != p->rank && p->peer_base[r]) cudaIpcCloseMemHandle(p->peer_base[r]);
+        if (r != p->rank && p->peer_base[r] && p->ipc_opened[r]) cudaIpcCloseMemHandle(p->peer_base[r]);
     cudaFree(p->base);
+    cudaFree(p->d_fan);
+    if (p->h_status) cudaFreeHost(p->h_status);
+    cudaGetLastError();
     delete p;
 }
 
@@ -757,9 +845,18 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
 }
 
 // tree passes from `from_level` (0 = from the raw leaves) until a level >= until_level (-1: the roots)
+// A roots exchange requested for the rows of one commit_dev / merkle_dev call (row-sharded multi-GPU commit): the
+// launch that produces the roots carries it when there is exactly one such launch (`fused` reports it); otherwise
+// finish_exchange() runs the stand-alone kernel.
+struct FanReq {
+    zipgpu_peer_roots *pr;
+    size_t row_begin;    // index, in the whole commitment, of the first local row
+    bool fused = false;
+};
+
 static int merkle_dev(zipgpu_ctx *ctx, size_t num_rows, int depth, int leaf_limbs, const uint64_t *d_leaves,
                       uint8_t *d_layers, uint8_t *d_roots, cudaStream_t s, int from_level = 0, int until_level = -1,
-                      int *reached = nullptr) {
+                      int *reached = nullptr, FanReq *fan = nullptr) {
     if (reached) *reached = from_level;
     if (num_rows == 0) return ZIPGPU_OK;
     if (num_rows > 0xffffffffull) return fail(ZIPGPU_ERR_UNSUPPORTED, "too many rows");
@@ -774,10 +871,34 @@ static int merkle_dev(zipgpu_ctx *ctx, size_t num_rows, int depth, int leaf_limb
     a.depth = depth;
     a.leaf32 = leaf_limbs * 2;
     a.stream = s;
+    a.num_sms = ctx->num_sms;
+    if (fan && !fan->fused) {
+        a.fan = fan->pr->d_fan;
+        a.fan_step = fan->pr->step + 1;
+        a.fan_row_begin = (uint32_t)fan->row_begin;
+        a.fan_fused = &fan->fused;
+    }
     int n = 0;
     cudaError_t e = launch_merkle_levels(a, from_level, until_level, reached, &n);
     if (e != cudaSuccess) return cuda_fail(e, "launch_merkle_levels");
     ctx->launches += (uint64_t)n;
+    if (fan && fan->fused && a.fan) fan->pr->step++;  // the exchange of this step is in flight
+    return ZIPGPU_OK;
+}
+
+// After the kernels of a sharded commit: if no launch carried the exchange, run the stand-alone kernel on the local
+// roots.  *d_all = this rank's result buffer of the step (all total_rows roots once the stream has passed this point).
+static int finish_exchange(FanReq &fan, const uint8_t *d_local_roots, size_t count, cudaStream_t s, uint8_t **d_all) {
+    zipgpu_peer_roots *p = fan.pr;
+    if (!fan.fused) {
+        const unsigned long long step = p->step + 1;
+        cudaError_t e = launch_peer_roots_allgather(p->d_fan, step, d_local_roots, fan.row_begin * 32, count * 32, s);
+        if (e != cudaSuccess) return cuda_fail(e, "launch_peer_roots_allgather");
+        p->step = step;
+        p->ctx->launches++;
+        fan.fused = true;
+    }
+    if (d_all) *d_all = p->base + (p->step & 1) * p->buf_bytes;
     return ZIPGPU_OK;
 }
 
@@ -802,7 +923,7 @@ static size_t fuse_min_rows(const zipgpu_ctx *ctx, const zipgpu_code *code) {
 // Exact shapes run the fused commit kernel: encode + the lowest log2(E) tree levels in one launch.
 static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_evals, uint64_t *d_rows, uint8_t *d_layers,
                       uint8_t *d_roots, cudaStream_t s, int until_level = -1, int *reached = nullptr,
-                      uint64_t *evals_copy = nullptr) {
+                      uint64_t *evals_copy = nullptr, FanReq *fan = nullptr) {
     zipgpu_ctx *ctx = code->ctx;
     ProfRec r;
     const bool prof = prof_begin(ctx, &r);
@@ -827,7 +948,8 @@ static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
         const size_t per_row_layers = (((size_t)2 << code->depth) - 2) * 32;
         cudaStream_t hi = ctx->stream_hi;
         CU(chain(ctx, s, hi));
-        int split_level = 0;
+        int split_level = 0, chunk_level = 0;
+        bool first_chunk = true;
         for (size_t r0 = 0; r0 < num_rows; r0 += per) {
             const size_t nr = std::min(per, num_rows - r0);
             int rc = encode_dev(code, nr, d_evals + r0 * code->row_len * code->in_limbs,
@@ -836,11 +958,14 @@ static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
             CU(chain(ctx, hi, s));
             rc = merkle_dev(ctx, nr, code->depth, code->out_limbs, d_rows + r0 * code->cw * code->out_limbs,
                             d_layers + r0 * per_row_layers, d_roots + r0 * 32, s, 0, until_level >= 0 ? until_level : 6,
-                            &split_level);
+                            &chunk_level);
             if (rc) return rc;
+            split_level = first_chunk ? chunk_level : std::min(split_level, chunk_level);  // lowest level any chunk stopped at
+            first_chunk = false;
         }
         if (until_level < 0 && split_level < code->depth) {
-            int rc = merkle_dev(ctx, num_rows, code->depth, code->out_limbs, d_rows, d_layers, d_roots, s, split_level, -1);
+            int rc = merkle_dev(ctx, num_rows, code->depth, code->out_limbs, d_rows, d_layers, d_roots, s, split_level, -1,
+                                nullptr, fan);
             if (rc) return rc;
             split_level = code->depth;
         }
@@ -864,7 +989,7 @@ static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     if (reached) *reached = 0;
     if (d_roots) {
         rc = merkle_dev(ctx, num_rows, code->depth, code->out_limbs, d_rows, d_layers, d_roots, s,
-                        fuse ? code->fused_levels : 0, until_level, reached);
+                        fuse ? code->fused_levels : 0, until_level, reached, fan);
         if (rc) return rc;
         if (prof) {
             cudaEventRecord(r.e2, s);
@@ -880,12 +1005,13 @@ static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
 
 // the passes above `from_level` of the trees of `num_rows` rows whose lower levels are already in d_layers
 static int merkle_top_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_rows, uint8_t *d_layers, uint8_t *d_roots,
-                          cudaStream_t s, int from_level) {
+                          cudaStream_t s, int from_level, FanReq *fan = nullptr) {
     zipgpu_ctx *ctx = code->ctx;
     ProfRec r;
     const bool prof = prof_begin(ctx, &r);
     if (prof) cudaEventRecord(r.e1, s);
-    int rc = merkle_dev(ctx, num_rows, code->depth, code->out_limbs, d_rows, d_layers, d_roots, s, from_level, -1);
+    int rc = merkle_dev(ctx, num_rows, code->depth, code->out_limbs, d_rows, d_layers, d_roots, s, from_level, -1, nullptr,
+                        fan);
     if (rc) return rc;
     if (prof) {
         cudaEventRecord(r.e2, s);
@@ -933,6 +1059,10 @@ struct HostJob {
     uint8_t *roots_out;   // host, nullable (encode only)
     bool want_roots;
     zipgpu_data **keep;   // nullable
+    // row-sharded multi-GPU commit: exchange the roots with the peers (the launch that produces them carries it) and
+    // copy ALL total_rows roots of the commitment to roots_all_out (host, nullable)
+    FanReq *fan = nullptr;
+    uint8_t *roots_all_out = nullptr;
 };
 
 // OPT-IN (ZIPGPU_ZEROCOPY=1).  Pinned host evaluations + a full-size commit that keeps its prover data on the device:
@@ -942,7 +1072,7 @@ struct HostJob {
 // against 2.72 ms for the chunked DMA pipeline below (SM-initiated PCIe reads reach ~48 GB/s, the copy engine 55 GB/s,
 // and an L2 prefetch of system memory is a no-op), so the DMA pipeline stays the default.
 static bool zero_copy_eligible(zipgpu_code *code, size_t num_rows, const HostJob &job, const uint64_t **dev_alias) {
-    if (!job.want_roots || job.rows_out || job.layers_out) return false;
+    if (!job.want_roots || job.rows_out || job.layers_out || job.fan) return false;
     if (code->fused_levels <= 0 || code->depth < code->fused_levels || num_rows < fuse_min_rows(code->ctx, code)) return false;
     if (!fusion_enabled() || !getenv("ZIPGPU_ZEROCOPY")) return false;
     if (((uintptr_t)job.evals & 31) != 0) return false;
@@ -1014,7 +1144,16 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
         return fail(ZIPGPU_ERR_INVALID, "leaves.len().is_power_of_two(): codeword_len is not a power of two");
     const size_t lay_row_bytes = merkle ? layers_per_row(code->depth) * 32 : 0;
     if (job.keep) *job.keep = nullptr;
-    if (num_rows == 0) return ZIPGPU_OK;
+    if (num_rows == 0) {
+        if (job.fan) {  // a rank without rows still takes part in the exchange
+            uint8_t *d_all = nullptr;
+            int rc = finish_exchange(*job.fan, nullptr, 0, ctx->stream, &d_all);
+            if (rc) return rc;
+            if (job.roots_all_out)
+                CU(cudaMemcpyAsync(job.roots_all_out, d_all, job.fan->pr->total_rows * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        return ZIPGPU_OK;
+    }
 
     uint64_t *d_evals = nullptr, *d_rows = nullptr;
     uint8_t *d_layers = nullptr, *d_roots = nullptr;
@@ -1061,7 +1200,7 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
 
     // Per chunk the trees are taken to the first pass boundary >= level 6 (the wide passes); the rest is deferred.
     const bool defer_top = merkle && !job.layers_out && sched.size() > 1 && code->depth > 7;
-    int split_level = -1;
+    int split_level = -1, min_split = 1 << 30;  // the deferred top passes start at the LOWEST level any chunk stopped at
     // ZIPGPU_TIMELINE=1: timing events after every copy / chunk, printed relative to the first (diagnostics only)
     static const bool timeline = getenv("ZIPGPU_TIMELINE") != nullptr;
     std::vector<cudaEvent_t> tl_copy, tl_kern;
@@ -1085,8 +1224,9 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
         int rc = commit_dev(code, n, (const uint64_t *)((uint8_t *)d_evals + r0 * in_row_bytes),
                             (uint64_t *)((uint8_t *)d_rows + r0 * out_row_bytes),
                             merkle ? d_layers + r0 * lay_row_bytes : nullptr, merkle ? d_roots + r0 * 32 : nullptr, k,
-                            defer_top ? 6 : -1, &split_level);
+                            defer_top ? 6 : -1, &split_level, nullptr, single ? job.fan : nullptr);
         if (rc) return rc;
+        min_split = std::min(min_split, split_level);
         if (timeline) {
             cudaEvent_t ev;
             cudaEventCreate(&ev);
@@ -1104,9 +1244,18 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
         }
     }
     if ((e = chain(ctx, st2, s)) != cudaSuccess) return cuda_fail(e, "chain");
-    if (defer_top && split_level < code->depth) {
-        int rc = merkle_top_dev(code, num_rows, d_rows, d_layers, d_roots, s, split_level);
+    if (defer_top && min_split < code->depth) {
+        int rc = merkle_top_dev(code, num_rows, d_rows, d_layers, d_roots, s, min_split, job.fan);
         if (rc) return rc;
+    }
+    uint8_t *d_all_roots = nullptr, *d_roots_all_keep = nullptr;
+    if (merkle && job.fan) {  // (a no-op when one of the launches above carried the exchange)
+        int rc = finish_exchange(*job.fan, d_roots, num_rows, s, &d_all_roots);
+        if (rc) return rc;
+        if (job.keep) {  // the exchange buffer is recycled two steps later: the handle keeps its own copy
+            DEV_ALLOC(ctx, &d_roots_all_keep, job.fan->pr->total_rows * 32, s);
+            CU(cudaMemcpyAsync(d_roots_all_keep, d_all_roots, job.fan->pr->total_rows * 32, cudaMemcpyDeviceToDevice, s));
+        }
     }
     if (timeline) {
         cudaEvent_t ev;
@@ -1132,6 +1281,10 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
         if ((e = chain(ctx, s, d2h)) != cudaSuccess) return cuda_fail(e, "chain");
         CU(cudaMemcpyAsync(job.roots_out, d_roots, num_rows * 32, cudaMemcpyDeviceToHost, d2h));
     }
+    if (merkle && job.fan && job.roots_all_out) {
+        if ((e = chain(ctx, s, d2h)) != cudaSuccess) return cuda_fail(e, "chain");
+        CU(cudaMemcpyAsync(job.roots_all_out, d_all_roots, job.fan->pr->total_rows * 32, cudaMemcpyDeviceToHost, d2h));
+    }
     // join the copy streams back into the kernel stream so the frees are ordered after every use
     if ((e = chain(ctx, d2h, s)) != cudaSuccess) return cuda_fail(e, "chain");
     if ((e = chain(ctx, h2d, s)) != cudaSuccess) return cuda_fail(e, "chain");
@@ -1152,10 +1305,13 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
         d->d_rows = d_rows;
         d->d_layers = d_layers;
         d->d_roots = d_roots;
+        d->d_roots_all = d_roots_all_keep;
+        d->total_rows = job.fan ? job.fan->pr->total_rows : num_rows;
         guard.release(d_evals);
         guard.release(d_rows);
         guard.release(d_layers);
         guard.release(d_roots);
+        if (d_roots_all_keep) guard.release(d_roots_all_keep);
         *job.keep = d;
     } else {
         DEV_FREE(ctx, d_rows, s);
@@ -1316,7 +1472,7 @@ static int run_batch_job(zipgpu_code *code, size_t num_polys, size_t num_rows, c
     cudaStream_t ks[2] = {s, ctx->stream2};
     const size_t group = std::max<size_t>(1, (8u << 20) / std::max<size_t>(poly_in, 1));
     const bool defer_top = !want_layers && num_polys > group && code->depth > 7;
-    int split_level = -1;
+    int split_level = -1, min_split = 1 << 30;
     size_t chunk_no = 0;
     for (size_t p0 = 0; p0 < num_polys; p0 += group) {
         const size_t np = std::min(group, num_polys - p0);
@@ -1329,6 +1485,7 @@ static int run_batch_job(zipgpu_code *code, size_t num_polys, size_t num_rows, c
                             (uint64_t *)((uint8_t *)d_rows + r0 * out_row_bytes), d_layers + r0 * lay_row_bytes,
                             d_roots + r0 * 32, k, defer_top ? 6 : -1, &split_level);
         if (rc) return rc;
+        min_split = std::min(min_split, split_level);
         if (want_rows || want_layers) {
             if ((e = chain(ctx, k, ctx->d2h)) != cudaSuccess) return cuda_fail(e, "chain");
             for (size_t p = p0; p < p0 + np; p++) {
@@ -1340,8 +1497,8 @@ static int run_batch_job(zipgpu_code *code, size_t num_polys, size_t num_rows, c
         }
     }
     if ((e = chain(ctx, ctx->stream2, s)) != cudaSuccess) return cuda_fail(e, "chain");
-    if (defer_top && split_level < code->depth) {
-        int rc = merkle_top_dev(code, total_rows, d_rows, d_layers, d_roots, s, split_level);
+    if (defer_top && min_split < code->depth) {
+        int rc = merkle_top_dev(code, total_rows, d_rows, d_layers, d_roots, s, min_split);
         if (rc) return rc;
     }
     if ((e = chain(ctx, s, ctx->d2h)) != cudaSuccess) return cuda_fail(e, "chain");
@@ -1399,6 +1556,68 @@ extern "C" int zipgpu_commit_resident(zipgpu_code *code, size_t num_rows, const 
     return rc ? rc : rc2;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// row-sharded commit: this GPU's row range of ONE commitment, roots exchanged with the peers in the same launch
+// ------------------------------------------------------------------------------------------------------
+static int check_shard(const zipgpu_code *code, const zipgpu_peer_roots *pr, size_t row_begin, size_t count) {
+    if (!pr->connected) return fail(ZIPGPU_ERR_INVALID, "zipgpu_peer_roots_connect has not been called");
+    if (pr->ctx != code->ctx) return fail(ZIPGPU_ERR_INVALID, "code and peer_roots belong to different contexts");
+    if (row_begin + count > pr->total_rows) return fail(ZIPGPU_ERR_INVALID, "row range outside the commitment");
+    if (code->depth < 0)
+        return fail(ZIPGPU_ERR_INVALID, "leaves.len().is_power_of_two(): codeword_len is not a power of two");
+    return ZIPGPU_OK;
+}
+
+extern "C" int zipgpu_commit_device_sharded(zipgpu_code *code, zipgpu_peer_roots *pr, size_t row_begin, size_t count,
+                                            const uint64_t *d_evals, uint64_t *d_rows_out, uint8_t *d_layers_out,
+                                            void *stream, uint8_t **d_all_roots_out) {
+    if (!code || !pr || (count && !d_evals)) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    int rc = check_shard(code, pr, row_begin, count);
+    if (rc) return rc;
+    zipgpu_ctx *ctx = code->ctx;
+    API_LOCK(ctx);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    DevGuard guard(ctx, s);
+    if ((rc = check_align16(d_layers_out, "layers_out"))) return rc;
+    FanReq fan{pr, row_begin};
+    uint64_t *rows_scratch = nullptr;
+    uint8_t *layers_scratch = nullptr, *d_roots = nullptr;
+    if (count) {
+        if (!d_rows_out) {
+            DEV_ALLOC(ctx, &rows_scratch, count * code->cw * code->out_limbs * 8, s);
+            d_rows_out = rows_scratch;
+        }
+        if (!d_layers_out && code->depth > 0) {
+            DEV_ALLOC(ctx, &layers_scratch, count * layers_per_row(code->depth) * 32, s);
+            d_layers_out = layers_scratch;
+        }
+        DEV_ALLOC(ctx, &d_roots, count * 32, s);
+        rc = commit_dev(code, count, d_evals, d_rows_out, d_layers_out, d_roots, s, -1, nullptr, nullptr, &fan);
+        if (rc) return rc;
+    }
+    rc = finish_exchange(fan, d_roots, count, s, d_all_roots_out);
+    if (rows_scratch) DEV_FREE(ctx, rows_scratch, s);
+    if (layers_scratch) DEV_FREE(ctx, layers_scratch, s);
+    if (d_roots) DEV_FREE(ctx, d_roots, s);
+    return rc;
+}
+
+extern "C" int zipgpu_commit_resident_sharded(zipgpu_code *code, zipgpu_peer_roots *pr, size_t row_begin, size_t count,
+                                              const uint64_t *evals, uint8_t *roots_all_out, zipgpu_data **handle) {
+    if (!code || !pr || (count && !evals)) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    int rc = check_shard(code, pr, row_begin, count);
+    if (rc) return rc;
+    API_LOCK(code->ctx);
+    CU(cudaSetDevice(code->ctx->device));
+    FanReq fan{pr, row_begin};
+    HostJob job{evals, nullptr, nullptr, nullptr, true, handle, &fan, roots_all_out};
+    rc = run_host_job(code, count, job);
+    int rc2 = zipgpu_ctx_sync(code->ctx);
+    if (rc == 0 && rc2 == 0) rc = zipgpu_peer_roots_status(pr);
+    return rc ? rc : rc2;
+}
+
 extern "C" void zipgpu_data_free(zipgpu_data *d) {
     if (!d) return;
     API_LOCK(d->ctx);
@@ -1408,12 +1627,14 @@ extern "C" void zipgpu_data_free(zipgpu_data *d) {
     dev_free(d->ctx, d->d_rows, s);
     dev_free(d->ctx, d->d_layers, s);
     dev_free(d->ctx, d->d_roots, s);
+    dev_free(d->ctx, d->d_roots_all, s);
     delete d;
 }
 extern "C" size_t zipgpu_data_num_rows(const zipgpu_data *d) { return d ? d->num_rows : 0; }
 extern "C" const uint64_t *zipgpu_data_rows_device(const zipgpu_data *d) { return d ? d->d_rows : nullptr; }
 extern "C" const uint8_t *zipgpu_data_layers_device(const zipgpu_data *d) { return d ? d->d_layers : nullptr; }
 extern "C" const uint8_t *zipgpu_data_roots_device(const zipgpu_data *d) { return d ? d->d_roots : nullptr; }
+extern "C" const uint8_t *zipgpu_data_all_roots_device(const zipgpu_data *d) { return d ? d->d_roots_all : nullptr; }
 
 extern "C" int zipgpu_data_read_rows(const zipgpu_data *d, size_t row_begin, size_t row_count, uint64_t *rows_out) {
     if (!d || (row_count && !rows_out)) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
@@ -1440,10 +1661,12 @@ extern "C" int zipgpu_data_read_layers(const zipgpu_data *d, size_t row_begin, s
     return ZIPGPU_OK;
 }
 
-extern "C" int zipgpu_data_open_columns(const zipgpu_data *d, size_t num_cols, const uint32_t *columns,
-                                        uint64_t *col_values_out, uint8_t *paths_out) {
+extern "C" int zipgpu_data_open_columns_strided(const zipgpu_data *d, size_t num_cols, const uint32_t *columns,
+                                                uint64_t *col_values_out, uint8_t *paths_out, size_t total_rows,
+                                                size_t row_offset) {
     if (!d || (num_cols && (!columns || !col_values_out || (!paths_out && d->depth > 0))))
         return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (row_offset + d->num_rows > total_rows) return fail(ZIPGPU_ERR_INVALID, "shard rows outside the commitment");
     if (num_cols == 0) return ZIPGPU_OK;
     for (size_t i = 0; i < num_cols; i++)
         if (columns[i] >= d->cw) return fail(ZIPGPU_ERR_INVALID, "column index out of range");
@@ -1475,8 +1698,13 @@ extern "C" int zipgpu_data_open_columns(const zipgpu_data *d, size_t num_cols, c
     cudaError_t e = launch_open_columns(a);
     if (e != cudaSuccess) return cuda_fail(e, "launch_open_columns");
     ctx->launches++;
-    CU(cudaMemcpyAsync(col_values_out, d_vals, val_bytes, cudaMemcpyDeviceToHost, s));
-    if (path_bytes) CU(cudaMemcpyAsync(paths_out, d_paths, path_bytes, cudaMemcpyDeviceToHost, s));
+    // per column the shard's rows land at rows [row_offset, row_offset + num_rows) of a total_rows-row block
+    const size_t vrow = (size_t)d->out_limbs * 8, prow = (size_t)d->depth * 32;
+    CU(cudaMemcpy2DAsync((uint8_t *)col_values_out + row_offset * vrow, total_rows * vrow, d_vals, d->num_rows * vrow,
+                         d->num_rows * vrow, num_cols, cudaMemcpyDeviceToHost, s));
+    if (path_bytes)
+        CU(cudaMemcpy2DAsync(paths_out + row_offset * prow, total_rows * prow, d_paths, d->num_rows * prow,
+                             d->num_rows * prow, num_cols, cudaMemcpyDeviceToHost, s));
     DEV_FREE(ctx, d_cols, s);
     DEV_FREE(ctx, d_vals, s);
     DEV_FREE(ctx, d_paths, s);
@@ -1484,13 +1712,30 @@ extern "C" int zipgpu_data_open_columns(const zipgpu_data *d, size_t num_cols, c
     return ZIPGPU_OK;
 }
 
+extern "C" int zipgpu_data_open_columns(const zipgpu_data *d, size_t num_cols, const uint32_t *columns,
+                                        uint64_t *col_values_out, uint8_t *paths_out) {
+    return zipgpu_data_open_columns_strided(d, num_cols, columns, col_values_out, paths_out, d ? d->num_rows : 0, 0);
+}
+
 extern "C" size_t zipgpu_data_open_columns_wire_bytes(const zipgpu_data *d) {
     return d ? open_columns_wire_bytes((uint32_t)d->num_rows, (uint32_t)d->out_limbs, d->depth) : 0;
 }
 
+namespace zipgpu {
+int data_open_columns_wire_strided(const zipgpu_data *d, size_t num_cols, const uint32_t *columns, uint8_t *stream_out,
+                                   size_t total_rows, size_t row_offset);
+}
 extern "C" int zipgpu_data_open_columns_wire(const zipgpu_data *d, size_t num_cols, const uint32_t *columns,
                                              uint8_t *stream_out) {
+    return zipgpu::data_open_columns_wire_strided(d, num_cols, columns, stream_out, d ? d->num_rows : 0, 0);
+}
+
+// a shard's part of the proof stream of a total_rows-row commitment (mgpu.cu): per column the values block and the
+// proofs block of the shard's rows go to their places inside the column's [values | proofs] record
+int zipgpu::data_open_columns_wire_strided(const zipgpu_data *d, size_t num_cols, const uint32_t *columns,
+                                           uint8_t *stream_out, size_t total_rows, size_t row_offset) {
     if (!d || (num_cols && (!columns || !stream_out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (row_offset + d->num_rows > total_rows) return fail(ZIPGPU_ERR_INVALID, "shard rows outside the commitment");
     if (num_cols == 0) return ZIPGPU_OK;
     for (size_t i = 0; i < num_cols; i++)
         if (columns[i] >= d->cw) return fail(ZIPGPU_ERR_INVALID, "column index out of range");
@@ -1520,7 +1765,14 @@ extern "C" int zipgpu_data_open_columns_wire(const zipgpu_data *d, size_t num_co
     cudaError_t e = launch_open_columns_wire(a, d_out);
     if (e != cudaSuccess) return cuda_fail(e, "launch_open_columns_wire");
     ctx->launches++;
-    CU(cudaMemcpyAsync(stream_out, d_out, bytes, cudaMemcpyDeviceToHost, s));
+    {
+        const size_t vrow = (size_t)d->out_limbs * 8, prow = 8 + (size_t)d->depth * 32;
+        const size_t col_local = d->num_rows * (vrow + prow), col_total = total_rows * (vrow + prow);
+        CU(cudaMemcpy2DAsync(stream_out + row_offset * vrow, col_total, d_out, col_local, d->num_rows * vrow, num_cols,
+                             cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpy2DAsync(stream_out + total_rows * vrow + row_offset * prow, col_total, d_out + d->num_rows * vrow,
+                             col_local, d->num_rows * prow, num_cols, cudaMemcpyDeviceToHost, s));
+    }
     DEV_FREE(ctx, d_cols, s);
     DEV_FREE(ctx, d_out, s);
     CU(cudaStreamSynchronize(s));

@@ -61,6 +61,11 @@ def sharded_commit(pp, poly, ctx=None, group=None, commit_rows: Callable | None 
         f"Polynomial has an incorrect number of evaluations ({ev.shape[0]}) for the expected matrix size ({expected})")
     begin, count = shard_range(pp.num_rows, rank, world)
     local_evals = ev[begin * row_len:(begin + count) * row_len]
+    if world > 1 and peer is not None and commit_rows is None:
+        # the GPU path proper: H2D of this rank's slice, encode + hash, and the roots exchange inside the kernel that
+        # produces the roots (zipgpu_commit_resident_sharded); every rank ends up with all roots
+        local_data, roots = peer.commit_resident(lc, pp, np.ascontiguousarray(local_evals), begin, count, ctx)
+        return local_data, begin, count, MultilinearZipCommitment([roots[i].tobytes() for i in range(pp.num_rows)])
     if commit_rows is None:
         def commit_rows(pp_, evals_, n_):
             sub = MultilinearZipParams(pp_.num_vars, n_, pp_.linear_code)
@@ -71,14 +76,7 @@ def sharded_commit(pp, poly, ctx=None, group=None, commit_rows: Callable | None 
         local_data, local_roots = commit_rows(pp, local_evals, count)
     else:
         local_data, local_roots = None, np.empty((0, 32), dtype=np.uint8)
-    if world > 1 and peer is not None:
-        from . import _native as nat
-
-        d_local = nat.lib().zipgpu_data_roots_device(local_data.handle) if count else None
-        ptr = peer.allgather(begin, count, d_local)
-        peer.sync()
-        roots = peer.tensor(ptr).cpu().numpy().reshape(pp.num_rows, 32).copy()
-    elif world > 1:
+    if world > 1:
         counts = [shard_range(pp.num_rows, r, world)[1] * 32 for r in range(world)]
         roots = _all_gather_bytes(local_roots.reshape(-1), counts, group).reshape(pp.num_rows, 32)
     else:
@@ -205,19 +203,54 @@ class PeerRoots:
             everyone = np.ascontiguousarray(out.cpu().numpy())
             nat.check(nat.lib().zipgpu_peer_roots_connect(self.handle, nat.ptr(everyone)))
             dist.barrier(group)  # nobody stores into a peer before that peer's buffers exist and are mapped
+        else:
+            nat.check(nat.lib().zipgpu_peer_roots_connect(self.handle, nat.ptr(mine)))
 
     def allgather(self, row_begin: int, count: int, d_local_roots: int, stream=None) -> int:
         """d_local_roots: device pointer to count*32 bytes.  Enqueues on `stream` (None = the context's stream) and
         returns the device pointer that holds all total_rows*32 bytes once the stream has passed this point."""
         C = self._C
         out = C.c_void_p()
-        self._nat.check(self._nat.lib().zipgpu_peer_roots_allgather(self.handle, row_begin, count, C.c_void_p(d_local_roots),
-                                                                    stream, C.byref(out)))
+        self._nat.check(self._nat.lib().zipgpu_peer_roots_allgather(
+            self.handle, row_begin, count, C.c_void_p(d_local_roots) if d_local_roots else None, stream, C.byref(out)))
         return out.value
 
+    def commit_device(self, hcode, row_begin: int, count: int, d_evals: int, d_rows: int | None, d_layers: int | None,
+                      stream=None) -> int:
+        """zipgpu_commit_device_sharded: commit of this rank's row range from device-resident evaluations with the
+        roots exchange fused into the kernel that produces the roots.  Returns the device pointer holding ALL roots
+        once the stream has passed this point (valid until the call after next)."""
+        C = self._C
+        out = C.c_void_p()
+        self._nat.check(self._nat.lib().zipgpu_commit_device_sharded(
+            hcode, self.handle, row_begin, count, C.c_void_p(d_evals) if d_evals else None,
+            C.c_void_p(d_rows) if d_rows else None, C.c_void_p(d_layers) if d_layers else None, stream, C.byref(out)))
+        return out.value
+
+    def commit_resident(self, code, pp, local_evals: np.ndarray, row_begin: int, count: int, ctx):
+        """zipgpu_commit_resident_sharded: host evaluations of this rank's rows in, ALL roots of the commitment out
+        (uint8 [num_rows, 32]); the prover data of the local rows stays on this GPU."""
+        from .zip import ResidentZipData
+
+        C = self._C
+        zt = code.zt
+        roots = np.empty((self.total_rows, 32), dtype=np.uint8)
+        h = C.c_void_p()
+        self._nat.check(self._nat.lib().zipgpu_commit_resident_sharded(
+            code.native(ctx, zt.N, zt.K), self.handle, row_begin, count, self._nat.ptr(local_evals) if count else None,
+            self._nat.ptr(roots), C.byref(h)))
+        cw = code.codeword_len()
+        data = ResidentZipData(h, count, cw, zt.K, cw.bit_length() - 1, code.row_len(), ctx) if h else None
+        return data, roots
+
+    def status(self) -> None:
+        """raises ZipGpuError(ERR_PEER_TIMEOUT) if a kernel of this exchange gave up waiting for a peer"""
+        self._nat.check(self._nat.lib().zipgpu_peer_roots_status(self.handle))
+
     def sync(self) -> None:
-        """wait for the context's stream (where `allgather` enqueues by default)"""
+        """wait for the context's stream (where the exchange enqueues by default) and check the exchange's status"""
         self._ctx.sync()
+        self.status()
 
     def tensor(self, ptr: int):
         """a torch uint8 view of the gathered roots behind the pointer `allgather` returned"""

@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -39,8 +40,22 @@ class InvalidPcsParam(Error):
 # ----------------------------------------------------------------------------------------------------------
 # context
 # ----------------------------------------------------------------------------------------------------------
+_uid_counter = [0]
+
+
+def _next_uid() -> int:
+    _uid_counter[0] += 1
+    return _uid_counter[0]
+
+
 class Context:
-    """One zipgpu context = one GPU (one process per GPU under torch.distributed)."""
+    """One zipgpu context = one GPU (one process per GPU under torch.distributed).
+
+    Native handles that live inside the context (per-pp codes, resident prover data, roots exchanges) are registered
+    here, keyed by the owning Python object's uid -- never by id(), which Python reuses -- and are destroyed by close()
+    BEFORE the context, so that nothing can point into a destroyed context afterwards."""
+
+    multi = False
 
     def __init__(self, device: int | None = None):
         if device is None:
@@ -49,18 +64,93 @@ class Context:
         nat.check(nat.lib().zipgpu_ctx_create(device, C.byref(h)))
         self.handle = h
         self.device = device
+        self._codes: dict[tuple[int, int, int], C.c_void_p] = {}   # (code uid, in_limbs, out_limbs) -> zipgpu_code*
+        self._live: dict[int, weakref.ref] = {}                    # uid -> weak ref to an object with _release()
+
+    def _check_open(self) -> None:
+        if not self.handle:
+            raise ZipGpuClosed("this zipgpu context has been closed")
 
     def sync(self) -> None:
+        self._check_open()
         nat.check(nat.lib().zipgpu_ctx_sync(self.handle))
 
     @property
     def launch_count(self) -> int:
+        self._check_open()
         return int(nat.lib().zipgpu_ctx_launch_count(self.handle))
+
+    def _destroy_code(self, h) -> None:
+        nat.lib().zipgpu_code_destroy(h)
+
+    def drop_code(self, code) -> None:
+        """destroy the native handles of one code object (RaaCode / ZipLinearCode) in this context"""
+        for key in [k for k in self._codes if k[0] == code._uid]:
+            self._destroy_code(self._codes.pop(key))
 
     def close(self) -> None:
         if self.handle:
-            nat.lib().zipgpu_ctx_destroy(self.handle)
+            for ref in list(self._live.values()):
+                obj = ref()
+                if obj is not None:
+                    obj._release()
+            self._live.clear()
+            for h in self._codes.values():
+                self._destroy_code(h)
+            self._codes.clear()
+            self._destroy_ctx()
             self.handle = None
+
+    def _destroy_ctx(self) -> None:
+        nat.lib().zipgpu_ctx_destroy(self.handle)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ZipGpuClosed(RuntimeError):
+    pass
+
+
+class MultiContext(Context):
+    """zipgpu_mgpu: ONE process driving several GPUs behind the same commit API (include/zipgpu.h).  Pass it wherever
+    a Context goes: MultilinearZip.commit / commit_no_merkle / batch_commit / commit_resident shard rows (or whole
+    polynomials) over the devices and return results in the reference's order; the roots are exchanged between the
+    GPUs by the kernel that produces them."""
+
+    multi = True
+
+    def __init__(self, devices: list[int] | None = None, n: int = 0):
+        h = C.c_void_p()
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            nat.check(nat.lib().zipgpu_mgpu_create(arr, len(devices), C.byref(h)))
+        else:
+            nat.check(nat.lib().zipgpu_mgpu_create(None, n, C.byref(h)))
+        self.handle = h
+        self.num_devices = int(nat.lib().zipgpu_mgpu_num_devices(h))
+        self.device = None
+        self._codes = {}
+        self._live = {}
+
+    def sync(self) -> None:
+        self._check_open()
+        for g in range(self.num_devices):
+            nat.check(nat.lib().zipgpu_ctx_sync(C.c_void_p(nat.lib().zipgpu_mgpu_ctx(self.handle, g))))
+
+    @property
+    def launch_count(self) -> int:
+        self._check_open()
+        return int(nat.lib().zipgpu_mgpu_launch_count(self.handle))
+
+    def _destroy_code(self, h) -> None:
+        nat.lib().zipgpu_mgpu_code_destroy(h)
+
+    def _destroy_ctx(self) -> None:
+        nat.lib().zipgpu_mgpu_destroy(self.handle)
 
 
 _default_ctx: Context | None = None
@@ -101,7 +191,9 @@ def as_limbs(values, limbs: int) -> np.ndarray:
         if limbs > 1:
             out[:, 1:] = np.where(a < 0, np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64(0))[:, None]
         return out
-    if a.dtype.kind in "iu" and a.dtype != np.uint64:
+    if a.dtype == np.int64:  # already limb-shaped: [n, limbs] (or flat, n * limbs) two's-complement words
+        a = np.ascontiguousarray(a).view(np.uint64)
+    elif a.dtype.kind in "iu" and a.dtype != np.uint64:
         return as_limbs(a.astype(np.int64), limbs)
     if a.dtype == object:  # python ints
         flat = [int(v) for v in a.reshape(-1)]
@@ -181,7 +273,7 @@ class RaaCode:
         self.perm_1_seed = perm_1_seed
         self.perm_2_seed = perm_2_seed
         self._perms = perms
-        self._native: dict[tuple[int, int, int], C.c_void_p] = {}
+        self._uid = _next_uid()
 
     @staticmethod
     def new(spec, poly_size: int, transcript, zt: ZipTypes = ZipTypes()) -> "RaaCode":
@@ -226,17 +318,20 @@ class RaaCode:
         return self._perms
 
     def native(self, ctx: Context, in_limbs: int, out_limbs: int) -> C.c_void_p:
-        key = (id(ctx), in_limbs, out_limbs)
-        h = self._native.get(key)
+        """the per-pp device state in `ctx` (zipgpu_code, or zipgpu_mgpu_code for a MultiContext); owned by the context"""
+        ctx._check_open()
+        key = (self._uid, in_limbs, out_limbs)
+        h = ctx._codes.get(key)
         if h is None:
             p1, p2 = self.permutations()
             h = C.c_void_p()
-            rc = nat.lib().zipgpu_code_create(ctx.handle, self._row_len, self.repetition_factor, in_limbs, out_limbs,
-                                              nat.ptr(p1), nat.ptr(p2), C.byref(h))
+            create = nat.lib().zipgpu_mgpu_code_create if ctx.multi else nat.lib().zipgpu_code_create
+            rc = create(ctx.handle, self._row_len, self.repetition_factor, in_limbs, out_limbs,
+                        nat.ptr(p1), nat.ptr(p2), C.byref(h))
             if rc == nat.ERR_WIDTH:
                 raise AssertionError(nat.lib().zipgpu_last_error().decode())
             nat.check(rc)
-            self._native[key] = h
+            ctx._codes[key] = h
         return h
 
     def encode_wide(self, row, in_limbs: int | None = None, out_limbs: int | None = None,
@@ -248,7 +343,8 @@ class RaaCode:
         assert r.shape[0] == self._row_len, "Row length must match the code's row length"  # code_raa.rs:93-97
         ctx = ctx or default_context()
         out = np.empty((self.codeword_len(), out_limbs), dtype=np.uint64)
-        nat.check(nat.lib().zipgpu_encode_rows(self.native(ctx, in_limbs, out_limbs), 1, nat.ptr(r), nat.ptr(out)))
+        enc = nat.lib().zipgpu_mgpu_encode_rows if ctx.multi else nat.lib().zipgpu_encode_rows
+        nat.check(enc(self.native(ctx, in_limbs, out_limbs), 1, nat.ptr(r), nat.ptr(out)))
         return out
 
     def encode(self, row, ctx: Context | None = None) -> np.ndarray:
@@ -300,7 +396,7 @@ class ZipLinearCode:
         self._num_column_opening = num_column_opening
         self._num_proximity_testing = num_proximity_testing
         self.a, self.b = a, b
-        self._native: dict[tuple[int, int, int], C.c_void_p] = {}
+        self._uid = _next_uid()
 
     @staticmethod
     def new(spec, poly_size: int, transcript, zt: ZipTypes = ZipTypes()) -> "ZipLinearCode":
@@ -334,14 +430,17 @@ class ZipLinearCode:
         return self._num_proximity_testing
 
     def native(self, ctx: Context, in_limbs: int, out_limbs: int) -> C.c_void_p:
-        key = (id(ctx), in_limbs, out_limbs)
-        h = self._native.get(key)
+        ctx._check_open()
+        if ctx.multi:
+            raise Error("the sparse ZipLinearCode is single-GPU (the multi-GPU context takes RaaCode)")
+        key = (self._uid, in_limbs, out_limbs)
+        h = ctx._codes.get(key)
         if h is None:
             h = C.c_void_p()
             nat.check(nat.lib().zipgpu_sparse_code_create(ctx.handle, self._row_len, self._codeword_len, self.a.d, in_limbs,
                                                           out_limbs, nat.ptr(self.a.cols), nat.ptr(self.a.coef),
                                                           nat.ptr(self.b.cols), nat.ptr(self.b.coef), C.byref(h)))
-            self._native[key] = h
+            ctx._codes[key] = h
         return h
 
     def kernel_kind(self, ctx: Context | None = None, in_limbs: int | None = None, out_limbs: int | None = None) -> str:
@@ -445,40 +544,71 @@ class MultilinearZipCommitment:
 
 
 class ResidentZipData:
-    """Device-resident MultilinearZipData (rows + layers stay in HBM for `open`); see zipgpu_commit_resident."""
+    """Device-resident MultilinearZipData (rows + layers stay in HBM for `open`); see zipgpu_commit_resident.
+    With a MultiContext the data stays sharded by row range over the GPUs that produced it (zipgpu_mgpu_data); every
+    accessor returns results in row order."""
 
-    def __init__(self, handle: C.c_void_p, num_rows: int, cw: int, out_limbs: int, depth: int, row_len: int):
+    def __init__(self, handle: C.c_void_p, num_rows: int, cw: int, out_limbs: int, depth: int, row_len: int,
+                 ctx: "Context | None" = None):
         self.handle, self.num_rows, self.cw, self.out_limbs, self.depth = handle, num_rows, cw, out_limbs, depth
         self.row_len = row_len
+        self._ctx = ctx
+        self._multi = bool(ctx is not None and ctx.multi)
+        self._uid = _next_uid()
+        if ctx is not None:
+            ctx._live[self._uid] = weakref.ref(self)
+
+    def _h(self):
+        if not self.handle:
+            raise ZipGpuClosed("this prover data has been freed (or its context closed)")
+        return self.handle
+
+    def shards(self):
+        """[(zipgpu_data* or None, row_begin, row_count)] -- one entry for a single-GPU handle"""
+        if not self._multi:
+            return [(self._h(), 0, self.num_rows)]
+        out = []
+        for g in range(self._ctx.num_devices):
+            b, n = C.c_size_t(), C.c_size_t()
+            h = nat.lib().zipgpu_mgpu_data_shard(self._h(), g, C.byref(b), C.byref(n))
+            out.append((C.c_void_p(h) if h else None, b.value, n.value))
+        return out
+
+    def _read(self, fn, per_row_shape, dtype, row_begin, row_count):
+        row_count = self.num_rows - row_begin if row_count is None else row_count
+        out = np.empty((row_count,) + per_row_shape, dtype=dtype)
+        for h, b, n in self.shards():
+            lo, hi = max(b, row_begin), min(b + n, row_begin + row_count)
+            if h is None or lo >= hi:
+                continue
+            nat.check(fn(h, lo - b, hi - lo, nat.ptr(out[lo - row_begin:hi - row_begin])))
+        return out
 
     def rows(self, row_begin: int = 0, row_count: int | None = None) -> np.ndarray:
-        row_count = self.num_rows - row_begin if row_count is None else row_count
-        out = np.empty((row_count * self.cw, self.out_limbs), dtype=np.uint64)
-        nat.check(nat.lib().zipgpu_data_read_rows(self.handle, row_begin, row_count, nat.ptr(out)))
-        return out
+        out = self._read(nat.lib().zipgpu_data_read_rows, (self.cw, self.out_limbs), np.uint64, row_begin, row_count)
+        return out.reshape(-1, self.out_limbs)
 
     def layers(self, row_begin: int = 0, row_count: int | None = None) -> np.ndarray:
-        row_count = self.num_rows - row_begin if row_count is None else row_count
-        out = np.empty((row_count, (2 << self.depth) - 2, 32), dtype=np.uint8)
-        nat.check(nat.lib().zipgpu_data_read_layers(self.handle, row_begin, row_count, nat.ptr(out)))
-        return out
+        return self._read(nat.lib().zipgpu_data_read_layers, ((2 << self.depth) - 2, 32), np.uint8, row_begin, row_count)
 
     def open_columns(self, columns) -> tuple[np.ndarray, np.ndarray]:
         """open_z.rs:124-143: -> (values [ncols, num_rows, K], paths [ncols, num_rows, depth, 32])"""
         cols = np.ascontiguousarray(columns, dtype=np.uint32)
         vals = np.empty((cols.size, self.num_rows, self.out_limbs), dtype=np.uint64)
         paths = np.empty((cols.size, self.num_rows, self.depth, 32), dtype=np.uint8)
-        nat.check(nat.lib().zipgpu_data_open_columns(self.handle, cols.size, nat.ptr(cols), nat.ptr(vals),
-                                                     nat.ptr(paths) if paths.size else None))
+        fn = nat.lib().zipgpu_mgpu_data_open_columns if self._multi else nat.lib().zipgpu_data_open_columns
+        nat.check(fn(self._h(), cols.size, nat.ptr(cols), nat.ptr(vals), nat.ptr(paths) if paths.size else None))
         return vals, paths
 
     def open_columns_wire(self, columns) -> bytes:
         """open_z.rs:124-143 as proof-stream bytes (PcsTranscript::write_integers + write_merkle_proof,
         pcs_transcript.rs:115-135,198-211): what `open` appends to the transcript stream for these columns"""
         cols = np.ascontiguousarray(columns, dtype=np.uint32)
-        per = int(nat.lib().zipgpu_data_open_columns_wire_bytes(self.handle))
+        L = nat.lib()
+        per = int((L.zipgpu_mgpu_data_open_columns_wire_bytes if self._multi else L.zipgpu_data_open_columns_wire_bytes)(self._h()))
         out = np.empty(cols.size * per, dtype=np.uint8)
-        nat.check(nat.lib().zipgpu_data_open_columns_wire(self.handle, cols.size, nat.ptr(cols), nat.ptr(out)))
+        fn = L.zipgpu_mgpu_data_open_columns_wire if self._multi else L.zipgpu_data_open_columns_wire
+        nat.check(fn(self._h(), cols.size, nat.ptr(cols), nat.ptr(out)))
         return out.tobytes()
 
     def combine_rows(self, coeffs, out_limbs: int = 8) -> np.ndarray:
@@ -488,13 +618,26 @@ class ResidentZipData:
         assert c.size == self.num_rows, "one coefficient per row"
         row_len = self.row_len
         out = np.empty((row_len, out_limbs), dtype=np.uint64)
-        nat.check(nat.lib().zipgpu_data_combine_rows(self.handle, nat.ptr(c), out_limbs, nat.ptr(out)))
+        fn = nat.lib().zipgpu_mgpu_data_combine_rows if self._multi else nat.lib().zipgpu_data_combine_rows
+        nat.check(fn(self._h(), nat.ptr(c), out_limbs, nat.ptr(out)))
         return out
 
-    def free(self) -> None:
+    def _release(self) -> None:
         if self.handle:
-            nat.lib().zipgpu_data_free(self.handle)
+            (nat.lib().zipgpu_mgpu_data_free if self._multi else nat.lib().zipgpu_data_free)(self.handle)
             self.handle = None
+
+    def free(self) -> None:
+        self._release()
+        if self._ctx is not None:
+            self._ctx._live.pop(self._uid, None)
+
+    def __del__(self):
+        try:
+            if self._ctx is None or self._ctx.handle:
+                self.free()
+        except Exception:
+            pass
 
 
 def _validate_input(function: str, param_num_vars: int, polys) -> None:
@@ -529,7 +672,8 @@ class MultilinearZip:
         assert ev.shape[0] >= pp.num_rows * row_len, "not enough evaluations for num_rows rows"
         ctx = ctx or default_context()
         out = np.empty((pp.num_rows * codeword_len, zt.K), dtype=np.uint64)
-        nat.check(nat.lib().zipgpu_encode_rows(lc.native(ctx, zt.N, zt.K), pp.num_rows, nat.ptr(ev), nat.ptr(out)))
+        enc = nat.lib().zipgpu_mgpu_encode_rows if ctx.multi else nat.lib().zipgpu_encode_rows
+        nat.check(enc(lc.native(ctx, zt.N, zt.K), pp.num_rows, nat.ptr(ev), nat.ptr(out)))
         return out
 
     @staticmethod
@@ -552,8 +696,9 @@ class MultilinearZip:
         rows = np.empty((pp.num_rows * cw, zt.K), dtype=np.uint64)
         layers = np.empty((pp.num_rows, (2 << depth) - 2, 32), dtype=np.uint8)
         roots = np.empty((pp.num_rows, 32), dtype=np.uint8)
-        nat.check(nat.lib().zipgpu_commit(lc.native(ctx, zt.N, zt.K), pp.num_rows, nat.ptr(ev), nat.ptr(rows),
-                                          nat.ptr(layers) if layers.size else None, nat.ptr(roots)))
+        com = nat.lib().zipgpu_mgpu_commit if ctx.multi else nat.lib().zipgpu_commit
+        nat.check(com(lc.native(ctx, zt.N, zt.K), pp.num_rows, nat.ptr(ev), nat.ptr(rows),
+                      nat.ptr(layers) if layers.size else None, nat.ptr(roots)))
         trees = [MerkleTree(roots[i].tobytes(), depth, layers[i]) for i in range(pp.num_rows)]
         assert len(trees) == pp.num_rows  # commit.rs:76
         return MultilinearZipData(rows, trees), MultilinearZipCommitment([t.root for t in trees])
@@ -591,8 +736,9 @@ class MultilinearZip:
         layers = [np.empty((pp.num_rows, (2 << depth) - 2, 32), dtype=np.uint8) for _ in range(k)]
         roots = [np.empty((pp.num_rows, 32), dtype=np.uint8) for _ in range(k)]
         arr = lambda xs: (C.c_void_p * k)(*[nat.ptr(x) for x in xs])
-        nat.check(nat.lib().zipgpu_batch_commit(lc.native(ctx, zt.N, zt.K), k, pp.num_rows, arr(evs), arr(rows),
-                                                arr(layers) if layers[0].size else None, arr(roots)))
+        bc = nat.lib().zipgpu_mgpu_batch_commit if ctx.multi else nat.lib().zipgpu_batch_commit
+        nat.check(bc(lc.native(ctx, zt.N, zt.K), k, pp.num_rows, arr(evs), arr(rows),
+                     arr(layers) if layers[0].size else None, arr(roots)))
         out = []
         for p in range(k):
             trees = [MerkleTree(roots[p][i].tobytes(), depth, layers[p][i]) for i in range(pp.num_rows)]
@@ -617,7 +763,7 @@ class MultilinearZip:
         ev = as_limbs(poly.evaluations, zt.N)
         roots = np.empty((pp.num_rows, 32), dtype=np.uint8)
         h = C.c_void_p()
-        nat.check(nat.lib().zipgpu_commit_resident(lc.native(ctx, zt.N, zt.K), pp.num_rows, nat.ptr(ev),
-                                                   nat.ptr(roots), C.byref(h)))
-        return (ResidentZipData(h, pp.num_rows, cw, zt.K, depth, lc.row_len()),
+        cr = nat.lib().zipgpu_mgpu_commit_resident if ctx.multi else nat.lib().zipgpu_commit_resident
+        nat.check(cr(lc.native(ctx, zt.N, zt.K), pp.num_rows, nat.ptr(ev), nat.ptr(roots), C.byref(h)))
+        return (ResidentZipData(h, pp.num_rows, cw, zt.K, depth, lc.row_len(), ctx),
                 MultilinearZipCommitment([roots[i].tobytes() for i in range(pp.num_rows)]))
