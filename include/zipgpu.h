@@ -284,7 +284,8 @@ int zipgpu_profile_enable(zipgpu_ctx *ctx, int on);
 /* Sums since the last reset, milliseconds of device time: encoder kernel, hash kernels; and call count. */
 int zipgpu_profile_read(zipgpu_ctx *ctx, double *encode_ms, double *hash_ms, uint64_t *calls, int reset);
 /* Dependency-free INT32 micro-benchmark: runs `iters` rounds of `kind` ops per thread on the whole GPU and
- * returns achieved warp-level lane-ops/s.  kind 0 = LOP3/SHF/IADD3 (alu pipe), 1 = alu + IMAD mix. */
+ * returns achieved warp-level lane-ops/s.  kind 0 = 3 alu + 1 IMAD.IADD, 1 = 8 alu : 6 IMAD (a BLAKE3 G), 2 = LOP3/SHF
+ * only: the alu pipe's own peak (the roofline of the hash kernels). */
 int zipgpu_microbench_int32(zipgpu_ctx *ctx, int kind, int iters, double *lane_ops_per_s);
 
 #ifdef __cplusplus

@@ -1873,7 +1873,7 @@ extern "C" int zipgpu_profile_read(zipgpu_ctx *c, double *encode_ms, double *has
 
 extern "C" int zipgpu_microbench_int32(zipgpu_ctx *c, int kind, int iters, double *lane_ops_per_s) {
     if (!c || !lane_ops_per_s) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
-    if (kind < 0 || kind > 1 || iters < 1) return fail(ZIPGPU_ERR_INVALID, "bad kind/iters");
+    if (kind < 0 || kind > 2 || iters < 1) return fail(ZIPGPU_ERR_INVALID, "bad kind/iters");
     API_LOCK(c);
     CU(cudaSetDevice(c->device));
     cudaEvent_t e0, e1;
