@@ -89,6 +89,9 @@ int zipgpu_host_unregister(void *p);
 /* ---- code (RaaCode, per-pp state) -------------------------------------------------------------------- */
 /* shuffle_seeded(&mut [0..n), seed) restated (zip/utils.rs:139-142; rand 0.9.2).  Host-side, no GPU needed. */
 int zipgpu_perm_from_seed(uint64_t seed, uint32_t n, uint32_t *perm_out);
+/* The ChaCha block function underneath it (rand_chacha 0.9 state layout: 8 key words, 64-bit counter, stream 0), so
+ * that the core can be checked against published ChaCha vectors (StdRng uses rounds = 12).  out: 16 words. */
+int zipgpu_chacha_block(const uint32_t *key, uint64_t counter, int rounds, uint32_t *out);
 /* RaaCode::new geometry (code_raa.rs:42-43), MultilinearZip::setup (structs.rs:79-90). Host-side. */
 size_t zipgpu_raa_row_len(size_t poly_size);
 size_t zipgpu_num_rows(size_t poly_size, size_t row_len);

@@ -198,6 +198,40 @@ def test_chacha_core_against_openssl():
     assert np.array(blocks, dtype="<u4").tobytes() == ks
 
 
+CHACHA12_TC1 = ("9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f"
+                "0564f879d27ae3c02ce82834acfa8c793a629f2ca0de6919610be82f411326be")
+CHACHA20_TC1 = ("76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7"
+                "da41597c5157488d7724e03fb8d84a376a43b8f41518a11cc387b669b2ee6586")
+
+
+def test_chacha12_published_vector(oracle):
+    """StdRng = ChaCha12: the published ChaCha12 test vector (zero 256-bit key, zero nonce, block 0), and the ChaCha20
+    one for the same core, for ALL three restatements: oracle C, pyoracle, and the product's csrc/rand_compat.cpp"""
+    import ctypes as C
+
+    from oracle import pyoracle as po
+    from zinc_b200 import _native as nat
+
+    zero = np.zeros(8, dtype=np.uint32)
+    for rounds, expect in ((12, CHACHA12_TC1), (20, CHACHA20_TC1)):
+        out = np.empty(16, dtype=np.uint32)
+        oracle.lib().zo_chacha_block(zero.ctypes.data_as(C.POINTER(C.c_uint32)), 0, 0, rounds,
+                                     out.ctypes.data_as(C.POINTER(C.c_uint32)))
+        assert out.astype("<u4").tobytes().hex() == expect, f"oracle C, {rounds} rounds"
+        assert np.array(po.chacha_block([0] * 8, 0, 0, rounds), dtype="<u4").tobytes().hex() == expect
+        out2 = np.empty(16, dtype=np.uint32)
+        nat.check(nat.lib().zipgpu_chacha_block(nat.ptr(zero), 0, rounds, nat.ptr(out2)))
+        assert out2.astype("<u4").tobytes().hex() == expect, f"rand_compat.cpp, {rounds} rounds"
+    # a non-trivial key and counter: the three agree with OpenSSL's ChaCha20 (covers key/counter word placement)
+    crypto = pytest.importorskip("cryptography.hazmat.primitives.ciphers")
+    key = bytes(range(32))
+    kw = np.frombuffer(key, dtype="<u4").astype(np.uint32)
+    ks = crypto.Cipher(crypto.algorithms.ChaCha20(key, (5).to_bytes(8, "little") + bytes(8)), mode=None).encryptor().update(bytes(64))
+    out3 = np.empty(16, dtype=np.uint32)
+    nat.check(nat.lib().zipgpu_chacha_block(nat.ptr(kw), 5, 20, nat.ptr(out3)))
+    assert out3.astype("<u4").tobytes() == ks
+
+
 def test_rand_python_equals_c(oracle):
     from oracle import pyoracle as po
 

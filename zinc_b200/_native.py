@@ -30,6 +30,7 @@ SIGNATURES = {
     "zipgpu_host_register": (i32, [vp, sz]),
     "zipgpu_host_unregister": (i32, [vp]),
     "zipgpu_perm_from_seed": (i32, [u64, C.c_uint32, vp]),
+    "zipgpu_chacha_block": (i32, [vp, u64, i32, vp]),
     "zipgpu_raa_row_len": (sz, [sz]),
     "zipgpu_num_rows": (sz, [sz, sz]),
     "zipgpu_raa_codeword_width_bits": (i32, [i32, sz, sz]),

@@ -16,6 +16,36 @@ namespace zipgpu {
 
 namespace {
 
+inline uint32_t rol32(uint32_t v, int n) { return (v << n) | (v >> (32 - n)); }
+inline void quarter_round(uint32_t *x, int a, int b, int c, int d) {
+    x[a] += x[b]; x[d] = rol32(x[d] ^ x[a], 16);
+    x[c] += x[d]; x[b] = rol32(x[b] ^ x[c], 12);
+    x[a] += x[b]; x[d] = rol32(x[d] ^ x[a], 8);
+    x[c] += x[d]; x[b] = rol32(x[b] ^ x[c], 7);
+}
+
+}  // namespace
+
+// One ChaCha block as rand_chacha 0.9 lays the state out: constants "expand 32-byte k", 256-bit key, 64-bit block
+// counter in words 12-13, 64-bit stream id (0) in words 14-15.  Exposed (zipgpu_chacha_block) so that the core can be
+// pinned to published vectors: 12 rounds, zero key and counter give the ChaCha12 test vector 9bf49a6a 0755f953 ...
+void chacha_block(const uint32_t key[8], uint64_t counter, int rounds, uint32_t out[16]) {
+    uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
+    std::memcpy(in + 4, key, 8 * sizeof(uint32_t));
+    in[12] = static_cast<uint32_t>(counter);
+    in[13] = static_cast<uint32_t>(counter >> 32);
+    in[14] = in[15] = 0;  // stream id 0
+    uint32_t x[16];
+    std::memcpy(x, in, sizeof x);
+    for (int dr = 0; dr < rounds / 2; ++dr) {
+        quarter_round(x, 0, 4, 8, 12); quarter_round(x, 1, 5, 9, 13); quarter_round(x, 2, 6, 10, 14); quarter_round(x, 3, 7, 11, 15);
+        quarter_round(x, 0, 5, 10, 15); quarter_round(x, 1, 6, 11, 12); quarter_round(x, 2, 7, 8, 13); quarter_round(x, 3, 4, 9, 14);
+    }
+    for (int i = 0; i < 16; ++i) out[i] = x[i] + in[i];
+}
+
+namespace {
+
 class ChaCha12Stream {
   public:
     explicit ChaCha12Stream(uint64_t seed) {
@@ -49,29 +79,8 @@ class ChaCha12Stream {
   private:
     static constexpr int kBuf = 64;  // rand_chacha refills four 16-word blocks at a time
 
-    static inline uint32_t rol(uint32_t v, int n) { return (v << n) | (v >> (32 - n)); }
-    static inline void quarter(uint32_t *x, int a, int b, int c, int d) {
-        x[a] += x[b]; x[d] = rol(x[d] ^ x[a], 16);
-        x[c] += x[d]; x[b] = rol(x[b] ^ x[c], 12);
-        x[a] += x[b]; x[d] = rol(x[d] ^ x[a], 8);
-        x[c] += x[d]; x[b] = rol(x[b] ^ x[c], 7);
-    }
-
     void refill() {
-        for (int blk = 0; blk < kBuf / 16; ++blk, ++counter_) {
-            uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
-            std::memcpy(in + 4, key_, sizeof key_);
-            in[12] = static_cast<uint32_t>(counter_);
-            in[13] = static_cast<uint32_t>(counter_ >> 32);
-            in[14] = in[15] = 0;  // stream id 0
-            uint32_t x[16];
-            std::memcpy(x, in, sizeof x);
-            for (int dr = 0; dr < 6; ++dr) {  // 12 rounds
-                quarter(x, 0, 4, 8, 12); quarter(x, 1, 5, 9, 13); quarter(x, 2, 6, 10, 14); quarter(x, 3, 7, 11, 15);
-                quarter(x, 0, 5, 10, 15); quarter(x, 1, 6, 11, 12); quarter(x, 2, 7, 8, 13); quarter(x, 3, 4, 9, 14);
-            }
-            for (int i = 0; i < 16; ++i) buf_[16 * blk + i] = x[i] + in[i];
-        }
+        for (int blk = 0; blk < kBuf / 16; ++blk, ++counter_) chacha_block(key_, counter_, 12, buf_ + 16 * blk);
         pos_ = 0;
     }
 

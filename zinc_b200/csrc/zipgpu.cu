@@ -23,6 +23,7 @@
 
 namespace zipgpu {
 void perm_from_seed(uint64_t seed, uint32_t n, uint32_t *perm);
+void chacha_block(const uint32_t key[8], uint64_t counter, int rounds, uint32_t out[16]);
 }
 
 using namespace zipgpu;
@@ -368,6 +369,13 @@ extern "C" int zipgpu_host_unregister(void *p) {
 extern "C" int zipgpu_perm_from_seed(uint64_t seed, uint32_t n, uint32_t *perm_out) {
     if (!perm_out && n) return fail(ZIPGPU_ERR_INVALID, "perm_out is NULL");
     perm_from_seed(seed, n, perm_out);
+    return ZIPGPU_OK;
+}
+
+extern "C" int zipgpu_chacha_block(const uint32_t *key, uint64_t counter, int rounds, uint32_t *out) {
+    if (!key || !out) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (rounds < 2 || rounds > 20 || (rounds & 1)) return fail(ZIPGPU_ERR_INVALID, "rounds must be even, 2..20");
+    chacha_block(key, counter, rounds, out);
     return ZIPGPU_OK;
 }
 
