@@ -337,6 +337,30 @@ def test_warp_specialised_commit_kernel(row_len, num_rows, oracle, ctx, monkeypa
         assert np.array_equal(g_lay, layers), knob
 
 
+@pytest.mark.parametrize("units", [1, 2])
+@pytest.mark.parametrize("row_len,num_rows", [(4096, 37), (4096, 391), (2048, 523), (1024, 97), (1024, 1500), (512, 611),
+                                              (256, 59), (256, 1777)])
+def test_warp_specialised_commit_kernel_sub_row_units(row_len, num_rows, units, oracle, ctx, monkeypatch):
+    """the sub-row work units of the warp-specialised commit kernel (a row hashed as 2 units, the units -- not
+    the rows -- split statically and evenly over the CTAs; rows shared by two CTAs are encoded by both and each writes
+    its part of the codeword): every unit count forced at row counts where CTAs get less than one, exactly one and
+    several units, with shares that start and end in the middle of a row"""
+    from zinc_b200 import RaaCode, ZipTypes
+
+    cw = 2 * row_len
+    p1, p2 = oracle.perm_from_seed(cw, KECCAK_SEEDS[0]), oracle.perm_from_seed(cw, KECCAK_SEEDS[1])
+    code = RaaCode.with_permutations(ZipTypes(), row_len, 2, p1, p2)
+    evals = np.random.default_rng(num_rows + units).integers(0, 1 << 64, size=num_rows * row_len, dtype=np.uint64)
+    rc, rows, layers, roots = oracle.commit_mt(evals, num_rows, row_len, 2, 0, 0, p1, p2, threads=16, faithful=False)
+    assert rc == 0
+    monkeypatch.setenv("ZIPGPU_FUSE_MIN_ROWS", "1")
+    monkeypatch.setenv("ZIPGPU_WS_UNITS", str(units))
+    g_rows, g_lay, g_roots = _commit_device(ctx, code, num_rows, cw, evals)
+    assert np.array_equal(g_roots, roots)
+    assert np.array_equal(g_rows, rows)
+    assert np.array_equal(g_lay, layers)
+
+
 def test_peer_roots_allgather_single_rank(ctx):
     """the peer-memory roots exchange degenerates to a copy + self-signal on one GPU (N > 1: scripts/strong_scaling.py
     --p2p and test_peer_roots_two_gpus below); two steps exercise the double buffering"""

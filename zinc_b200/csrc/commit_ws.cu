@@ -1,0 +1,280 @@
+// zinc_b200/csrc/commit_ws.cu -- the warp-specialised commit kernel: RAA encode + BLAKE3 leaves + the lowest Merkle
+// levels of every row in ONE launch (Int<1> -> Int<4>, cw = 512 ... 8192); what zipgpu_commit* launches for exact shapes.
+//
+// Replaces commit.rs:69-74 (encode_rows, then MerkleTree::new per row) up to tree level log2(E / U); the batched passes of
+// merkle.cu finish the trees.  Two thread groups per CTA, two plane sets in shared memory:
+//   warps 0..n-1  (ENC)  : stage -> gather -> scan -> gather -> scan -> park s2 in plane set `buf` -> write the codeword
+//                          out (record tiles + bulk stores), then straight on to the next row in the other plane set
+//   warps n..2n-1 (HASH) : BLAKE3 leaves and the lowest tree levels of the row parked in `buf`, straight from the planes
+// Two named barriers per plane set hand it back and forth (full: ENC arrives / HASH waits; empty: HASH arrives / ENC
+// waits).  This is what the hardware made of the two-CTA fused kernel anyway -- its warp schedulers let one CTA of
+// every pair run as if alone (75 us per row, 62 of them hashing) and starved the other -- minus the 13 us per row the
+// favoured CTA spent not hashing: here the hash warps never leave the alu pipe.
+//
+// (Tried and measured slower, round 2: letting the ENC group also reduce the level-log2(E/U) nodes of a unit to its root
+// through a shared-memory digest buffer, which would make a commit ONE launch.  A compression is a ~200-step dependent
+// chain; in a few ENC warps competing with 16 busy hash warps for the alu pipe it takes ~6 us per tree level, ~55 us
+// for the 9 levels of a row -- the ENC group became the critical path: nv = 24 went from 1.94 to 2.19 ms.  The narrow
+// tops stay with the batched passes of merkle.cu, which run them over all rows at once.)
+//
+// Work units.  U = 1: a CTA claims whole rows dynamically and hash thread t continues with the E entries ENC thread t
+// produced (one level-log2(E) node per thread and row).  That is right for thousands of rows, but a row is ~65 us of
+// hashing, and with 3-4 rows per SM (one 2^24 commit sharded over 8 GPUs; a 2^20 commit on one GPU) the last wave leaves
+// a quarter of the machine idle.  U = 2 / 4 hashes a row as U units: in a unit every hash thread takes E / U consecutive
+// entries, so all hash warps work on 1/U of the row (half / a quarter of the time), and the units -- not the rows -- are
+// split evenly and statically over the CTAs.  A row whose units fall into two CTAs is encoded by both (encoding is a
+// tenth of the hashing and runs in the otherwise idle ENC warps); each writes out only the part of the codeword its
+// units cover.  The fused part then stops one or two tree levels lower (level log2(E / U)).
+#include <cstdlib>
+
+#include "raa_common.cuh"
+
+namespace zipgpu {
+
+constexpr int kBarEnc = 1, kBarFull0 = 2, kBarEmpty0 = 4;  // + buf
+template <int ALL>
+__device__ __forceinline__ void ws_sync(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(ALL) : "memory"); }
+template <int ALL>
+__device__ __forceinline__ void ws_arrive(uint32_t id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(ALL) : "memory"); }
+
+// E entries per ENC thread, kWsEnc threads per group: (16, 512) = cw 8192, (8, 512) = cw 4096, (8, 256) = cw 2048,
+// (4, 256) = cw 1024, (4, 128) = cw 512 -- the (E, T) of the plain encoder for those shapes, so the same pre-translated
+// tables serve both kernels.  The 512-thread CTAs leave room for two CTAs per SM.
+template <int E, int kWsEnc, int U>
+__global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
+    commit_ws_kernel(const uint32_t *__restrict__ evals, uint32_t *__restrict__ rows_out,
+                     const uint16_t *__restrict__ tab1, const uint16_t *__restrict__ tab2,
+                     const uint8_t *__restrict__ colw, uint32_t num_rows, uint8_t *__restrict__ layers, uint32_t one,
+                     uint32_t *__restrict__ row_counter) {
+    constexpr int IN32 = 2, W = 3, OUT32 = 8, kWsAll = 2 * kWsEnc;
+    constexpr uint32_t T = kWsEnc, P = T * E, cw = P, in_words = (P / 2) * IN32;
+    constexpr int EH = E / U;                   // entries per hash thread and unit
+    static_assert(EH >= 2 && EH * U == E, "units must divide the entries per thread");
+    using T16 = Tab16<E>;
+    using T8 = Tab8<E>;
+    using EncBar = NamedBarrier<kBarEnc, kWsEnc>;
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *planes = smem;                    // [2][W][P]
+    uint32_t *aux = smem + 2 * W * P;           // scan scratch of the ENC group
+    uint32_t *tiles = aux + 64 * W;             // one 1 KiB record tile per ENC warp
+    __shared__ volatile uint32_t s_row[2];      // row parked in each plane set (0xffffffff: no more rows)
+    __shared__ volatile uint32_t s_next;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t t = tid & (kWsEnc - 1);      // index within the group
+    // U > 1: this CTA's static share of the num_rows * U units
+    const uint32_t total_units = num_rows * U;
+    const uint32_t u0 = U == 1 ? 0u : (uint32_t)(((uint64_t)blockIdx.x * total_units) / gridDim.x);
+    const uint32_t u1 = U == 1 ? 0u : (uint32_t)(((uint64_t)(blockIdx.x + 1) * total_units) / gridDim.x);
+
+    if (tid < kWsEnc) {
+        // ============================== ENC ==============================
+        uint32_t c1[T16::NR], c2[T16::NR], cc[T8::NR];
+        T16::load(tab1, t, T, c1);
+        const uint32_t wbase = (t >> 5) * (E * 32);
+        uint32_t *tile = tiles + (t >> 5) * 256;
+        const uint32_t lane = t & 31u, ha = (lane >> 2) & 1u;
+        uint32_t row = U == 1 ? blockIdx.x : u0 / U, it = 0;
+        const uint32_t row_end = U == 1 ? num_rows : (u1 + U - 1) / U;  // U > 1: rows [u0 / U, ceil(u1 / U))
+        for (; row < row_end; it++) {
+            const uint32_t buf = it & 1u;
+            uint32_t *pl = planes + buf * (W * P);
+            if (it >= 2) ws_sync<kWsAll>(kBarEmpty0 + buf);  // the hash warps are done with this plane set
+            uint32_t early = U == 1 ? row + gridDim.x : row + 1;
+            if (U == 1 && t == 0 && row_counter) early = gridDim.x + atomicAdd(row_counter, 1u) + 1u;
+            {
+                WarpStage<IN32, E> ws;
+                ws.load(evals + (size_t)row * in_words, t);
+                ws.store(pl, P, T, t);
+            }
+            EncBar::sync();
+            uint32_t v[E][W];
+#pragma unroll
+            for (int k = 0; k < E; k++) {
+                const uint32_t so = T16::get(c1, k) * IN32;
+                const uint2 x = *reinterpret_cast<const uint2 *>(pl + so);
+                v[k][0] = x.x;
+                v[k][1] = x.y;
+                v[k][2] = (uint32_t)((int32_t)x.y >> 31);
+            }
+            if (t == 0) {
+                if (early < row_end) prefetch_l2_bulk(evals + (size_t)early * in_words, in_words * 4u);
+                s_next = early;
+            }
+            uint32_t pre[W];
+            T8::load(colw, t, T, cc);
+            block_scan<W, E, EncBar>(v, pre, aux, t, T >> 5);
+#pragma unroll
+            for (int k = 0; k < E; k++) {
+                add_limbs<W>(v[k], pre);
+                const uint32_t s1 = wbase + k * 32 + T8::get(cc, k);
+#pragma unroll
+                for (int w = 0; w < W; w++) pl[w * P + s1] = v[k][w];
+            }
+            T16::load(tab2, t, T, c2);
+            EncBar::sync();
+#pragma unroll
+            for (int k = 0; k < E; k++) {
+                const uint32_t sl = T16::get(c2, k);
+#pragma unroll
+                for (int w = 0; w < W; w++) v[k][w] = pl[w * P + sl];
+            }
+            block_scan<W, E, EncBar>(v, pre, aux, t, T >> 5);
+#pragma unroll
+            for (int k = 0; k < E; k++) {
+                add_limbs<W>(v[k], pre);
+                const uint32_t s2 = slot_of<E>(t, k, T);
+#pragma unroll
+                for (int w = 0; w < W; w++) pl[w * P + s2] = v[k][w];
+            }
+            if (t == 0) s_row[buf] = row;
+            ws_arrive<kWsAll>(kBarFull0 + buf);  // hand the row to the hash warps
+            __syncwarp();
+            T16::load(tab1, t, T, c1);   // for the next row; in flight during the write-out
+            // write-out of this warp's 32E positions: 32-byte records into the warp's tile, one bulk store per KiB.
+            // U > 1: only the part of the codeword this CTA's units cover (the CTA that owns the other units of a
+            // shared row writes the rest); a warp's positions lie inside one unit.
+            bool mine = true;
+            if constexpr (U > 1) {
+                const uint32_t unit = row * U + ((t >> 5) * U) / (T >> 5);
+                mine = unit >= u0 && unit < u1;
+            }
+            if (mine) {
+                uint8_t *dst_w = reinterpret_cast<uint8_t *>(rows_out) + ((size_t)row * cw + (size_t)(t >> 5) * (32 * E)) * 32;
+#pragma unroll
+                for (int j = 0; j < E; j++) {
+                    const uint32_t i = (t >> 5) * (32 * E) + j * 32 + lane;
+                    const uint32_t s = slot_of<E>(i / E, i % E, T);
+                    const uint32_t a0 = pl[s], a1 = pl[P + s], a2 = pl[2 * P + s];
+                    const uint32_t sign = (uint32_t)((int32_t)a2 >> 31);
+                    const uint4 lo = make_uint4(a0, a1, a2, sign), hi = make_uint4(sign, sign, sign, sign);
+                    if (lane == 0) bulk_wait_read_all();
+                    __syncwarp();
+                    uint4 *rec = reinterpret_cast<uint4 *>(tile) + lane * 2;
+                    rec[ha] = ha ? hi : lo;
+                    rec[ha ^ 1u] = ha ? lo : hi;
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) bulk_store_s2g(dst_w + (size_t)j * 1024, tile, 1024);
+                }
+            }
+            row = s_next;  // published before this iteration's ENC barriers
+        }
+        {   // no more rows: tell the hash warps through the next plane set
+            const uint32_t buf = it & 1u;
+            if (it >= 2) ws_sync<kWsAll>(kBarEmpty0 + buf);
+            if (t == 0) s_row[buf] = 0xffffffffu;
+            ws_arrive<kWsAll>(kBarFull0 + buf);
+        }
+        if (lane == 0) bulk_wait_all();
+    } else {
+        // ============================== HASH ==============================
+        constexpr int H = EH >= 16 ? 4 : EH >= 8 ? 3 : EH >= 4 ? 2 : 1;
+        static_assert((1 << H) == EH, "entries per hash thread: a power of two");
+        for (uint32_t it = 0;; it++) {
+            const uint32_t buf = it & 1u;
+            ws_sync<kWsAll>(kBarFull0 + buf);
+            const uint32_t row = s_row[buf];
+            if (row == 0xffffffffu) break;
+            const uint32_t *pl = planes + buf * (W * P);
+            uint8_t *lay_row = layers + (size_t)row * (2 * (size_t)cw - 2) * 32;
+            // the units of this row that are ours (U == 1: the whole row)
+            uint32_t uu = 0, uu_end = 1;
+            if constexpr (U > 1) {
+                uu = u0 > row * U ? u0 - row * U : 0u;
+                uu_end = u1 < (row + 1) * U ? u1 - row * U : (uint32_t)U;
+            }
+#pragma unroll 1
+            for (; uu < uu_end; uu++) {
+                const uint32_t pbase = (uu * T + t) * EH;  // first of this thread's EH consecutive positions
+                b3::Digest stack[H];
+#pragma unroll 1
+                for (uint32_t k = 0; k < (uint32_t)EH; k++) {
+                    const uint32_t idx = pbase + k;  // leaf index within the row
+                    const uint32_t s = slot_of<E>(idx / E, idx % E, T);
+                    uint32_t x[OUT32];
+#pragma unroll
+                    for (int w = 0; w < W; w++) x[w] = pl[w * P + s];
+                    const uint32_t sign = (uint32_t)((int32_t)x[W - 1] >> 31);
+#pragma unroll
+                    for (int w = W; w < OUT32; w++) x[w] = sign;
+                    b3::Digest d;
+                    b3::hash_leaf<OUT32>(x, d.w, one);
+                    st_global_v8(lay_row + (size_t)idx * 32, d.w);
+#pragma unroll 1
+                    for (int l = 0; l < H; l++) {
+                        if ((k >> l) & 1u) {
+                            d = b3::hash_node_call(stack[l], d, one);
+                            const size_t off = 2 * (size_t)cw - ((2 * (size_t)cw) >> (l + 1));
+                            st_global_v8(lay_row + (off + (idx >> (l + 1))) * 32, d.w);
+                        } else {
+                            stack[l] = d;
+                            break;
+                        }
+                    }
+                }
+            }
+            ws_arrive<kWsAll>(kBarEmpty0 + buf);  // the plane set may be overwritten
+        }
+    }
+}
+
+namespace {
+
+template <int E, int TENC, int U>
+cudaError_t launch_ws_u(const EncodeArgs &a, uint32_t grid) {
+    const size_t ws_smem = (2 * 3 * (size_t)(E * TENC) + 64 * 3 + (TENC / 32) * 256) * sizeof(uint32_t);
+    auto kern = commit_ws_kernel<E, TENC, U>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem);
+    if (err != cudaSuccess) return err;
+    uint32_t *row_counter = nullptr;
+    if (U == 1) {
+        if (grid > a.num_rows) grid = a.num_rows;
+        row_counter = a.num_rows >= 2 * grid ? a.row_counter : nullptr;
+        if (row_counter) {
+            err = cudaMemsetAsync(row_counter, 0xff, 2 * sizeof(uint32_t), a.stream);
+            if (err != cudaSuccess) return err;
+        }
+    } else {
+        const uint32_t units = a.num_rows * U;
+        if (grid > units) grid = units;
+    }
+    kern<<<grid, 2 * TENC, ws_smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows, a.fuse_layers, 1u,
+                                                row_counter);
+    return cudaGetLastError();
+}
+
+// Units per row (measured on B200, scripts/shard_sweep.py, profiles/r2_shard_sweep.md): whole rows while every CTA gets
+// ~6 or more of them; halves when a one-CTA-per-SM kernel gets 3..6 rows per CTA (cw = 8192: 512 rows 0.304 -> 0.277 ms,
+// cw = 4096: 0.168 -> 0.159 ms).  Below 3 rows per CTA, and for the two-CTA-per-SM variants (whose co-resident CTAs
+// already even each other out), finer units only move work into the passes that follow and measure equal or slower.
+// ZIPGPU_WS_UNITS forces 1 / 2 for experiments.
+template <int E, int TENC>
+cudaError_t launch_ws(const EncodeArgs &a, int *fused_levels) {
+    const uint32_t grid = (uint32_t)a.num_sms * (TENC == 512 ? 1u : 2u);
+    int U = 1;
+    if (TENC == 512 && a.num_rows >= 3 * grid && a.num_rows < 6 * grid) U = 2;
+    if (const char *env = getenv("ZIPGPU_WS_UNITS")) U = atoi(env) >= 2 ? 2 : 1;
+    int h = 0;
+    while ((1 << h) < E / U) h++;
+    if (fused_levels) *fused_levels = h;
+    if (U == 2) return launch_ws_u<E, TENC, 2>(a, grid);
+    return launch_ws_u<E, TENC, 1>(a, grid);
+}
+
+}  // namespace
+
+bool commit_ws_supported(int E, int T) {
+    return (E == 16 && T == 512) || (E == 8 && T == 512) || (E == 8 && T == 256) || (E == 4 && T == 256) ||
+           (E == 4 && T == 128);
+}
+
+cudaError_t launch_commit_ws(const EncodeArgs &a, int E, int T, int *fused_levels) {
+    if (E == 16 && T == 512) return launch_ws<16, 512>(a, fused_levels);
+    if (E == 8 && T == 512) return launch_ws<8, 512>(a, fused_levels);
+    if (E == 8 && T == 256) return launch_ws<8, 256>(a, fused_levels);
+    if (E == 4 && T == 256) return launch_ws<4, 256>(a, fused_levels);
+    if (E == 4 && T == 128) return launch_ws<4, 128>(a, fused_levels);
+    return cudaErrorInvalidConfiguration;
+}
+
+}  // namespace zipgpu

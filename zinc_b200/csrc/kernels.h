@@ -19,9 +19,14 @@ struct EncodeArgs {
     uint32_t *evals_copy = nullptr;  // non-NULL (exact shapes only): `evals` is mapped pinned HOST memory read in place
                                      // (zero-copy over PCIe); every staged row is also written here, in HBM
     uint32_t *row_counter = nullptr; // device word for dynamic row claiming (armed by the launcher); NULL = static rows
-    uint8_t *fuse_layers = nullptr;  // non-NULL: the fused commit kernel also writes Merkle levels 0..encode_fused_levels()
+    uint8_t *fuse_layers = nullptr;  // non-NULL: the fused commit kernel also writes the lowest Merkle levels
+    int *fused_levels_out = nullptr; // receives the level up to which that launch builds the trees (<= encode_fused_levels():
+                                     // the warp-specialised kernel stops 1 or 2 levels lower when it hashes sub-row units)
     cudaStream_t stream;
 };
+// the warp-specialised commit kernel (commit_ws.cu) for the encoder configuration (E, T) of an exact Int<1> -> Int<4> shape
+bool commit_ws_supported(int E, int T);
+cudaError_t launch_commit_ws(const EncodeArgs &a, int E, int T, int *fused_levels);
 int encode_fused_levels(int in_limbs, int out_limbs, uint32_t row_len, uint32_t cw);
 size_t encode_perm_padded_len(uint32_t cw);
 void build_encode_tables(const uint32_t *perm1, const uint32_t *perm2, uint32_t row_len, uint32_t cw, int in_limbs,

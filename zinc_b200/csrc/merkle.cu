@@ -251,11 +251,14 @@ cudaError_t launch_merkle_levels(const MerkleArgs &a, int from_level, int until_
     int n = 0, level = from_level;
     cudaError_t err = cudaSuccess;
     // the launch that reaches the roots carries the multi-GPU roots exchange (RootsFanout), if one was asked for
+    // nodes (over all rows) from which the remaining levels go to the CTA-per-subtree kernel (ZIPGPU_CTA_TREE_LOG2: knob)
+    static const int cta_tree_log2 = getenv("ZIPGPU_CTA_TREE_LOG2") ? atoi(getenv("ZIPGPU_CTA_TREE_LOG2")) : 18;
+    const size_t cta_tree_max = (size_t)1 << cta_tree_log2;
     const bool want_fan = a.fan != nullptr && until_level == a.depth && a.num_rows > 0;
     bool fused = false;
     if (a.fan_fused) *a.fan_fused = false;
     // small whole trees: the CTA-per-subtree latency path (at most 2^18 leaves in total, i.e. <= 256 CTAs of work)
-    if (from_level == 0 && until_level == a.depth && a.depth >= 1 && ((size_t)a.num_rows << a.depth) <= ((size_t)1 << 18) &&
+    if (from_level == 0 && until_level == a.depth && a.depth >= 1 && ((size_t)a.num_rows << a.depth) <= cta_tree_max &&
         !getenv("ZIPGPU_NO_CTA_TREE")) {
         while (level < a.depth) {
             const uint32_t S = (uint32_t)std::min(CTA_TREE_MAX_LEVELS, a.depth - level);
@@ -303,7 +306,7 @@ cudaError_t launch_merkle_levels(const MerkleArgs &a, int from_level, int until_
     while (level < until_level) {  // every further pass 3 levels, the last one up to 4
         // once the trees have narrowed to <= 2^18 nodes in total the remaining passes are latency-bound: finish with
         // the CTA-per-subtree kernel (one launch per 10 levels, one compression of latency per level)
-        if (cta_top_ok && level > 0 && ((size_t)a.num_rows << (a.depth - level)) <= ((size_t)1 << 18)) {
+        if (cta_top_ok && level > 0 && ((size_t)a.num_rows << (a.depth - level)) <= cta_tree_max) {
             const uint32_t S = (uint32_t)std::min(CTA_TREE_MAX_LEVELS, a.depth - level);
             const bool fan = want_fan && level + (int)S == a.depth;
             fused |= fan;

@@ -25,198 +25,9 @@
 #include <cstdlib>
 #include <vector>
 
-#include "blake3_dev.cuh"
-#include "common.cuh"
-#include "kernels.h"
+#include "raa_common.cuh"
 
 namespace zipgpu {
-
-template <int E>
-struct Swz {
-    static constexpr int SH = (E >= 32) ? 0 : (E == 16 ? 1 : E == 8 ? 2 : E == 4 ? 3 : E == 2 ? 4 : 5);
-};
-
-template <int E>
-__device__ __forceinline__ uint32_t slot_of(uint32_t t, uint32_t k, uint32_t T) {
-    return k * T + (t ^ ((k << Swz<E>::SH) & 31u));
-}
-
-// Scan of W-limb values across the CTA in the logical order i = t*E + k.  On return v[k] holds the inclusive scan
-// WITHIN the thread and pre[] the sum of everything owned by lower threads; the caller adds pre to each v[k] at
-// the point where it consumes it (keeps the live register set small).  aux: 2 * 32 * W words of shared memory.
-struct CtaBarrier {  // all threads of the CTA
-    __device__ __forceinline__ static void sync() { __syncthreads(); }
-};
-template <int ID, int COUNT>
-struct NamedBarrier {  // a subset of the CTA's warps (warp-specialised kernels)
-    __device__ __forceinline__ static void sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
-    __device__ __forceinline__ static void arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
-};
-
-template <int W, int E, class BAR = CtaBarrier>
-__device__ __forceinline__ void block_scan(uint32_t (&v)[E][W], uint32_t (&pre)[W], uint32_t *aux, uint32_t t,
-                                           uint32_t nwarps) {
-    const uint32_t lane = t & 31u, warp = t >> 5;
-#pragma unroll
-    for (int k = 1; k < E; k++) add_limbs<W>(v[k], v[k - 1]);
-    uint32_t inc[W];
-#pragma unroll
-    for (int w = 0; w < W; w++) inc[w] = v[E - 1][w];
-    // warp inclusive scan of thread totals
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        uint32_t o[W];
-#pragma unroll
-        for (int w = 0; w < W; w++) o[w] = __shfl_up_sync(0xffffffffu, inc[w], off);
-        if (lane >= (uint32_t)off) add_limbs<W>(inc, o);
-    }
-    if (lane == 31) {
-#pragma unroll
-        for (int w = 0; w < W; w++) aux[warp * W + w] = inc[w];
-    }
-    BAR::sync();
-    if (warp == 0) {
-        uint32_t wt[W];
-#pragma unroll
-        for (int w = 0; w < W; w++) wt[w] = (lane < nwarps) ? aux[lane * W + w] : 0u;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            uint32_t o[W];
-#pragma unroll
-            for (int w = 0; w < W; w++) o[w] = __shfl_up_sync(0xffffffffu, wt[w], off);
-            if (lane >= (uint32_t)off) add_limbs<W>(wt, o);
-        }
-        // exclusive warp prefix
-#pragma unroll
-        for (int w = 0; w < W; w++) {
-            uint32_t e = __shfl_up_sync(0xffffffffu, wt[w], 1);
-            aux[32 * W + lane * W + w] = lane ? e : 0u;
-        }
-    }
-    BAR::sync();
-    // exclusive prefix of this thread = warp prefix + inclusive scan of the lower lanes of the warp
-#pragma unroll
-    for (int w = 0; w < W; w++) {
-        uint32_t e = __shfl_up_sync(0xffffffffu, inc[w], 1);
-        pre[w] = lane ? e : 0u;
-    }
-    uint32_t wp[W];
-#pragma unroll
-    for (int w = 0; w < W; w++) wp[w] = aux[32 * W + warp * W + w];
-    add_limbs<W>(pre, wp);
-}
-
-// ---- per-pp tables (built once by build_encode_tables, below) ---------------------------------------------
-//   tab1 (u16): element index of the staged input row that codeword position i gathers in pass 1
-//               ( perm1[i] mod row_len )
-//   tab2 (u16): shared-memory address (within a plane) of the s1 entry that position i gathers in pass 2
-//   colw (u8) : bank (edge colour) at which the owner of s1 entry i parks it; address = write_group*32 + colour
-// stored "lane-major" in groups of 16 bytes so that the entries a thread needs are whole vector loads and
-// consecutive lanes read consecutive addresses (the tables are shared by every row: L2-resident).
-template <int E>
-struct Tab16 {  // u16 entries
-    static constexpr int G = E < 8 ? E : 8;          // entries per group
-    static constexpr int NG = E / G;                 // groups per thread
-    static constexpr int NR = (E + 1) / 2;           // packed registers
-    __host__ __device__ static size_t at(uint32_t t, uint32_t k, uint32_t T) {
-        return ((size_t)(k / G) * T + t) * G + (k % G);
-    }
-    __device__ __forceinline__ static void load(const uint16_t *tab, uint32_t t, uint32_t T, uint32_t (&r)[NR]) {
-#pragma unroll
-        for (int g = 0; g < NG; g++) {
-            const uint16_t *p = tab + ((size_t)g * T + t) * G;
-            if constexpr (G == 8) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
-                r[4 * g] = v.x; r[4 * g + 1] = v.y; r[4 * g + 2] = v.z; r[4 * g + 3] = v.w;
-            } else if constexpr (G == 4) {
-                const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
-                r[0] = v.x; r[1] = v.y;
-            } else if constexpr (G == 2) {
-                r[0] = __ldg(reinterpret_cast<const uint32_t *>(p));
-            } else {
-                r[0] = __ldg(p);
-            }
-        }
-    }
-    __device__ __forceinline__ static uint32_t get(const uint32_t (&r)[NR], int k) {
-        return (k & 1) ? (r[k >> 1] >> 16) : (r[k >> 1] & 0xffffu);
-    }
-};
-template <int E>
-struct Tab8 {  // u8 entries
-    static constexpr int G = E < 16 ? E : 16;
-    static constexpr int NG = E / G;
-    static constexpr int NR = (E + 3) / 4;
-    __host__ __device__ static size_t at(uint32_t t, uint32_t k, uint32_t T) {
-        return ((size_t)(k / G) * T + t) * G + (k % G);
-    }
-    __device__ __forceinline__ static void load(const uint8_t *tab, uint32_t t, uint32_t T, uint32_t (&r)[NR]) {
-#pragma unroll
-        for (int g = 0; g < NG; g++) {
-            const uint8_t *p = tab + ((size_t)g * T + t) * G;
-            if constexpr (G == 16) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
-                r[4 * g] = v.x; r[4 * g + 1] = v.y; r[4 * g + 2] = v.z; r[4 * g + 3] = v.w;
-            } else if constexpr (G == 8) {
-                const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
-                r[0] = v.x; r[1] = v.y;
-            } else if constexpr (G == 4) {
-                r[0] = __ldg(reinterpret_cast<const uint32_t *>(p));
-            } else if constexpr (G == 2) {
-                r[0] = __ldg(reinterpret_cast<const uint16_t *>(p));
-            } else {
-                r[0] = __ldg(p);
-            }
-        }
-    }
-    __device__ __forceinline__ static uint32_t get(const uint32_t (&r)[NR], int k) {
-        return (r[k >> 2] >> (8 * (k & 3))) & 0xffu;
-    }
-};
-
-// coalesced, read-once copy of one input row into shared memory
-__device__ __forceinline__ void stage_row(const uint32_t *src, uint32_t *stage, uint32_t in_words, uint32_t t, uint32_t T) {
-    if ((in_words & 3u) == 0) {
-        const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-        uint4 *d4 = reinterpret_cast<uint4 *>(stage);
-        for (uint32_t i = t; i < (in_words >> 2); i += T) d4[i] = ld_stream_v4(s4 + i);
-    } else {
-        for (uint32_t i = t; i < in_words; i += T) stage[i] = src[i];
-    }
-}
-
-// EXACT shapes: every warp stages ITS OWN 1/nwarps of the input row into ITS OWN plane slots (the slots whose s2
-// entries it alone reads back in the write-out), so staging the next row needs no CTA-wide barrier after the
-// write-out: linear word x of the warp's chunk -> row r = x / 32 of the warp's 32-word slot rows, column x % 32;
-// slot row r lives in plane r / E at k = r % E.  build_encode_tables emits tab1 in the same layout.
-template <int IN32, int E>
-struct WarpStage {
-    static constexpr int WPL = E * IN32 / 2;  // words per lane
-    static constexpr int NV = WPL / 4 > 0 ? WPL / 4 : 1;
-    uint4 v[NV];
-    __device__ __forceinline__ void load(const uint32_t *row_src, uint32_t t) {
-        static_assert(WPL % 4 == 0, "warp staging moves 16-byte vectors");
-        const uint32_t w = t >> 5, L = t & 31u;
-        const uint4 *src = reinterpret_cast<const uint4 *>(row_src + (size_t)w * (32 * WPL));
-#pragma unroll
-        for (int j = 0; j < WPL / 4; j++) v[j] = ld_stream_v4(src + j * 32 + L);
-    }
-    __device__ __forceinline__ void store(uint32_t *stage, uint32_t P, uint32_t T, uint32_t t) const {
-        const uint32_t w = t >> 5, L = t & 31u;
-#pragma unroll
-        for (int j = 0; j < WPL / 4; j++) {
-            const uint32_t r = 4 * j + (L >> 3), col = (L & 7u) * 4;
-            *reinterpret_cast<uint4 *>(stage + (r / E) * P + (r % E) * T + 32 * w + col) = v[j];
-        }
-    }
-    // zero-copy input (the row was read straight from pinned host memory): keep a copy in HBM for the opening phase
-    __device__ __forceinline__ void copy_out(uint32_t *row_dst, uint32_t t) const {
-        const uint32_t w = t >> 5, L = t & 31u;
-        uint4 *dst = reinterpret_cast<uint4 *>(row_dst + (size_t)w * (32 * WPL));
-#pragma unroll
-        for (int j = 0; j < WPL / 4; j++) st_stream_v4(dst + j * 32 + L, v[j]);
-    }
-};
 
 // IN32 : u32 words per input value          W    : u32 limbs carried through the scans
 // E    : codeword positions per thread      OUT32: u32 words per output value (0 = run-time `out32`)
@@ -520,178 +331,6 @@ __global__ void __launch_bounds__(MAXT, MINB)
 }
 
 // ------------------------------------------------------------------------------------------------------
-// The warp-specialised commit kernel (cw = 2048 / 4096 / 8192, Int<1> -> Int<4>): two thread groups per CTA, two plane sets.
-//   warps  0..15 (ENC)  : stage -> gather -> scan -> gather -> scan -> park s2 in plane set `buf` -> write the codeword
-//                         out (record tiles + bulk stores), then straight on to the next row in the other plane set
-//   warps 16..31 (HASH) : BLAKE3 leaves and the four lowest tree levels of the row parked in `buf`, thread t on the 16
-//                         entries ENC thread t produced
-// Two named barriers per plane set hand it back and forth (full: ENC arrives / HASH waits; empty: HASH arrives / ENC
-// waits).  This is what the hardware made of the two-CTA fused kernel anyway -- its warp schedulers let one CTA of
-// every pair run as if alone (75 us per row, 62 of them hashing) and starved the other -- minus the 13 us per row the
-// favoured CTA spent not hashing: here the hash warps never leave the alu pipe.
-// ------------------------------------------------------------------------------------------------------
-constexpr int kBarEnc = 1, kBarFull0 = 2, kBarEmpty0 = 4;  // + buf
-template <int ALL>
-__device__ __forceinline__ void ws_sync(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(ALL) : "memory"); }
-template <int ALL>
-__device__ __forceinline__ void ws_arrive(uint32_t id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(ALL) : "memory"); }
-
-// E entries per thread, kWsEnc threads per group: (16, 512) = cw 8192, (8, 512) = cw 4096, (8, 256) = cw 2048,
-// (4, 256) = cw 1024, (4, 128) = cw 512 -- the
-// (E, T) of the plain encoder for those shapes, so the same pre-translated tables serve both kernels.  The 512-thread
-// CTA of cw = 2048 leaves room for two CTAs per SM.
-template <int E, int kWsEnc>
-__global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
-    commit_ws_kernel(const uint32_t *__restrict__ evals, uint32_t *__restrict__ rows_out,
-                     const uint16_t *__restrict__ tab1, const uint16_t *__restrict__ tab2,
-                     const uint8_t *__restrict__ colw, uint32_t num_rows, uint8_t *__restrict__ layers, uint32_t one,
-                     uint32_t *__restrict__ row_counter) {
-    constexpr int IN32 = 2, W = 3, OUT32 = 8, kWsAll = 2 * kWsEnc;
-    constexpr uint32_t T = kWsEnc, P = T * E, cw = P, in_words = (P / 2) * IN32;
-    using T16 = Tab16<E>;
-    using T8 = Tab8<E>;
-    using EncBar = NamedBarrier<kBarEnc, kWsEnc>;
-    extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *planes = smem;                    // [2][W][P]
-    uint32_t *aux = smem + 2 * W * P;           // scan scratch of the ENC group
-    uint32_t *tiles = aux + 64 * W;             // one 1 KiB record tile per ENC warp
-    __shared__ volatile uint32_t s_row[2];      // row parked in each plane set (0xffffffff: no more rows)
-    __shared__ volatile uint32_t s_next;
-    const uint32_t tid = threadIdx.x;
-    const uint32_t t = tid & (kWsEnc - 1);      // index within the group: HASH thread t continues ENC thread t's entries
-
-    if (tid < kWsEnc) {
-        // ============================== ENC ==============================
-        uint32_t c1[T16::NR], c2[T16::NR], cc[T8::NR];
-        T16::load(tab1, t, T, c1);
-        const uint32_t wbase = (t >> 5) * (E * 32);
-        uint32_t *tile = tiles + (t >> 5) * 256;
-        const uint32_t lane = t & 31u, ha = (lane >> 2) & 1u;
-        uint32_t row = blockIdx.x, it = 0;
-        for (; row < num_rows; it++) {
-            const uint32_t buf = it & 1u;
-            uint32_t *pl = planes + buf * (W * P);
-            if (it >= 2) ws_sync<kWsAll>(kBarEmpty0 + buf);  // the hash warps are done with this plane set
-            uint32_t early = row + gridDim.x;
-            if (t == 0 && row_counter) early = gridDim.x + atomicAdd(row_counter, 1u) + 1u;
-            {
-                WarpStage<IN32, E> ws;
-                ws.load(evals + (size_t)row * in_words, t);
-                ws.store(pl, P, T, t);
-            }
-            EncBar::sync();
-            uint32_t v[E][W];
-#pragma unroll
-            for (int k = 0; k < E; k++) {
-                const uint32_t so = T16::get(c1, k) * IN32;
-                const uint2 x = *reinterpret_cast<const uint2 *>(pl + so);
-                v[k][0] = x.x;
-                v[k][1] = x.y;
-                v[k][2] = (uint32_t)((int32_t)x.y >> 31);
-            }
-            if (t == 0) {
-                if (early < num_rows) prefetch_l2_bulk(evals + (size_t)early * in_words, in_words * 4u);
-                s_next = early;
-            }
-            uint32_t pre[W];
-            T8::load(colw, t, T, cc);
-            block_scan<W, E, EncBar>(v, pre, aux, t, T >> 5);
-#pragma unroll
-            for (int k = 0; k < E; k++) {
-                add_limbs<W>(v[k], pre);
-                const uint32_t s1 = wbase + k * 32 + T8::get(cc, k);
-#pragma unroll
-                for (int w = 0; w < W; w++) pl[w * P + s1] = v[k][w];
-            }
-            T16::load(tab2, t, T, c2);
-            EncBar::sync();
-#pragma unroll
-            for (int k = 0; k < E; k++) {
-                const uint32_t sl = T16::get(c2, k);
-#pragma unroll
-                for (int w = 0; w < W; w++) v[k][w] = pl[w * P + sl];
-            }
-            block_scan<W, E, EncBar>(v, pre, aux, t, T >> 5);
-#pragma unroll
-            for (int k = 0; k < E; k++) {
-                add_limbs<W>(v[k], pre);
-                const uint32_t s2 = slot_of<E>(t, k, T);
-#pragma unroll
-                for (int w = 0; w < W; w++) pl[w * P + s2] = v[k][w];
-            }
-            if (t == 0) s_row[buf] = row;
-            ws_arrive<kWsAll>(kBarFull0 + buf);  // hand the row to the hash warps
-            __syncwarp();
-            T16::load(tab1, t, T, c1);   // for the next row; in flight during the write-out
-            // write-out of this warp's 32E positions: 32-byte records into the warp's tile, one bulk store per KiB
-            uint8_t *dst_w = reinterpret_cast<uint8_t *>(rows_out) + ((size_t)row * cw + (size_t)(t >> 5) * (32 * E)) * 32;
-#pragma unroll
-            for (int j = 0; j < E; j++) {
-                const uint32_t i = (t >> 5) * (32 * E) + j * 32 + lane;
-                const uint32_t s = slot_of<E>(i / E, i % E, T);
-                const uint32_t a0 = pl[s], a1 = pl[P + s], a2 = pl[2 * P + s];
-                const uint32_t sign = (uint32_t)((int32_t)a2 >> 31);
-                const uint4 lo = make_uint4(a0, a1, a2, sign), hi = make_uint4(sign, sign, sign, sign);
-                if (lane == 0) bulk_wait_read_all();
-                __syncwarp();
-                uint4 *rec = reinterpret_cast<uint4 *>(tile) + lane * 2;
-                rec[ha] = ha ? hi : lo;
-                rec[ha ^ 1u] = ha ? lo : hi;
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) bulk_store_s2g(dst_w + (size_t)j * 1024, tile, 1024);
-            }
-            row = s_next;  // published before this iteration's ENC barriers
-        }
-        {   // no more rows: tell the hash warps through the next plane set
-            const uint32_t buf = it & 1u;
-            if (it >= 2) ws_sync<kWsAll>(kBarEmpty0 + buf);
-            if (t == 0) s_row[buf] = 0xffffffffu;
-            ws_arrive<kWsAll>(kBarFull0 + buf);
-        }
-        if (lane == 0) bulk_wait_all();
-    } else {
-        // ============================== HASH ==============================
-        constexpr int H = E == 16 ? 4 : E == 8 ? 3 : E == 4 ? 2 : 1;
-        for (uint32_t it = 0;; it++) {
-            const uint32_t buf = it & 1u;
-            ws_sync<kWsAll>(kBarFull0 + buf);
-            const uint32_t row = s_row[buf];
-            if (row == 0xffffffffu) break;
-            const uint32_t *pl = planes + buf * (W * P);
-            uint8_t *lay_row = layers + (size_t)row * (2 * (size_t)cw - 2) * 32;
-            b3::Digest stack[H];
-#pragma unroll 1
-            for (uint32_t k = 0; k < (uint32_t)E; k++) {
-                const uint32_t s = slot_of<E>(t, k, T);
-                uint32_t x[OUT32];
-#pragma unroll
-                for (int w = 0; w < W; w++) x[w] = pl[w * P + s];
-                const uint32_t sign = (uint32_t)((int32_t)x[W - 1] >> 31);
-#pragma unroll
-                for (int w = W; w < OUT32; w++) x[w] = sign;
-                const uint32_t idx = t * E + k;
-                b3::Digest d;
-                b3::hash_leaf<OUT32>(x, d.w, one);
-                st_global_v8(lay_row + (size_t)idx * 32, d.w);
-#pragma unroll 1
-                for (int l = 0; l < H; l++) {
-                    if ((k >> l) & 1u) {
-                        d = b3::hash_node_call(stack[l], d, one);
-                        const size_t off = 2 * (size_t)cw - ((2 * (size_t)cw) >> (l + 1));
-                        st_global_v8(lay_row + (off + (idx >> (l + 1))) * 32, d.w);
-                    } else {
-                        stack[l] = d;
-                        break;
-                    }
-                }
-            }
-            ws_arrive<kWsAll>(kBarEmpty0 + buf);  // the plane set may be overwritten
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
 namespace {
@@ -768,23 +407,6 @@ cudaError_t launch_e(const EncodeArgs &a, const EncodeCfg &c, size_t smem) {
     }
 }
 
-template <int E, int TENC>
-cudaError_t launch_ws(const EncodeArgs &a) {
-    const size_t ws_smem = (2 * 3 * (size_t)(E * TENC) + 64 * 3 + (TENC / 32) * 256) * sizeof(uint32_t);
-    cudaError_t err = cudaFuncSetAttribute(commit_ws_kernel<E, TENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem);
-    if (err != cudaSuccess) return err;
-    uint32_t grid = (uint32_t)a.num_sms * (TENC == 512 ? 1u : 2u);
-    if (grid > a.num_rows) grid = a.num_rows;
-    uint32_t *row_counter = a.num_rows >= 2 * grid ? a.row_counter : nullptr;
-    if (row_counter) {
-        err = cudaMemsetAsync(row_counter, 0xff, 2 * sizeof(uint32_t), a.stream);
-        if (err != cudaSuccess) return err;
-    }
-    commit_ws_kernel<E, TENC><<<grid, 2 * TENC, ws_smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows,
-                                                                     a.fuse_layers, 1u, row_counter);
-    return cudaGetLastError();
-}
-
 template <int IN32, int W>
 cudaError_t launch_w(const EncodeArgs &a) {
     const EncodeCfg c = pick_cfg(a.cw);
@@ -799,13 +421,15 @@ cudaError_t launch_w(const EncodeArgs &a) {
     // the hot instantiations (ZipTypes K = 4N limbs, exact power-of-two shapes) get a compile-time output width,
     // no padding predicates and the register prefetch of the next row
     // (zero-copy input, evals_copy != NULL, stays on the two-CTA fused kernel, which also writes the HBM copy)
-    if (a.fuse_layers && !a.evals_copy && IN32 == 2 && W == 3 && exact && a.out32 == 8 && !getenv("ZIPGPU_NO_WS")) {
-        // the warp-specialised commit kernel: an encode group and a hash group per CTA, two plane sets
-        if (c.E == 16 && c.T == 512) return launch_ws<16, 512>(a);
-        if (c.E == 8 && c.T == 512) return launch_ws<8, 512>(a);
-        if (c.E == 8 && c.T == 256) return launch_ws<8, 256>(a);
-        if (c.E == 4 && c.T == 256) return launch_ws<4, 256>(a);
-        if (c.E == 4 && c.T == 128) return launch_ws<4, 128>(a);
+    if (a.fuse_layers && !a.evals_copy && IN32 == 2 && W == 3 && exact && a.out32 == 8 && !getenv("ZIPGPU_NO_WS") &&
+        commit_ws_supported(c.E, c.T)) {
+        // the warp-specialised commit kernel (commit_ws.cu): an encode group and a hash group per CTA, two plane sets
+        return launch_commit_ws(a, c.E, c.T, a.fused_levels_out);
+    }
+    if (a.fuse_layers && a.fused_levels_out) {
+        int h = 0;
+        while ((1 << h) < c.E) h++;
+        *a.fused_levels_out = h;
     }
     if (a.fuse_layers) {
         if (!exact) return cudaErrorInvalidConfiguration;

@@ -794,8 +794,17 @@ static int check_align16(const void *p, const char *name) {  // 32 bytes: rows, 
 }
 
 // fuse_layers != NULL: the fused commit kernel (encode + Merkle levels 0..code->fused_levels into fuse_layers)
+// A roots exchange requested for the rows of one commit_dev / merkle_dev call (row-sharded multi-GPU commit): the
+// launch that produces the roots carries it when there is exactly one such launch (`fused` reports it); otherwise
+// finish_exchange() runs the stand-alone kernel.
+struct FanReq {
+    zipgpu_peer_roots *pr;
+    size_t row_begin;    // index, in the whole commitment, of the first local row
+    bool fused = false;
+};
+
 static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_evals, uint64_t *d_rows, cudaStream_t s,
-                      uint8_t *fuse_layers = nullptr, uint64_t *evals_copy = nullptr) {
+                      uint8_t *fuse_layers = nullptr, uint64_t *evals_copy = nullptr, int *fused_levels = nullptr) {
     if (num_rows == 0) return ZIPGPU_OK;
     if (num_rows > 0xffffffffull) return fail(ZIPGPU_ERR_UNSUPPORTED, "too many rows");
     int rc;
@@ -841,6 +850,7 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     a.in_limbs = code->in_limbs;
     a.num_sms = code->ctx->num_sms;
     a.fuse_layers = fuse_layers;
+    a.fused_levels_out = fused_levels;
     a.evals_copy = reinterpret_cast<uint32_t *>(evals_copy);
     if (!getenv("ZIPGPU_STATIC_ROWS")) {
         a.row_counter = code->ctx->d_row_counters + 2 * (code->ctx->row_counter_pos++ % 256);
@@ -853,15 +863,6 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
 }
 
 // tree passes from `from_level` (0 = from the raw leaves) until a level >= until_level (-1: the roots)
-// A roots exchange requested for the rows of one commit_dev / merkle_dev call (row-sharded multi-GPU commit): the
-// launch that produces the roots carries it when there is exactly one such launch (`fused` reports it); otherwise
-// finish_exchange() runs the stand-alone kernel.
-struct FanReq {
-    zipgpu_peer_roots *pr;
-    size_t row_begin;    // index, in the whole commitment, of the first local row
-    bool fused = false;
-};
-
 static int merkle_dev(zipgpu_ctx *ctx, size_t num_rows, int depth, int leaf_limbs, const uint64_t *d_leaves,
                       uint8_t *d_layers, uint8_t *d_roots, cudaStream_t s, int from_level = 0, int until_level = -1,
                       int *reached = nullptr, FanReq *fan = nullptr) {
@@ -916,14 +917,14 @@ static bool fusion_enabled() {
 // rows from which commit_dev takes the fused kernel (ZIPGPU_FUSE_MIN_ROWS overrides: tests force it at small shapes)
 static size_t fuse_min_rows(const zipgpu_ctx *ctx, const zipgpu_code *code) {
     if (const char *env = getenv("ZIPGPU_FUSE_MIN_ROWS")) return (size_t)atol(env);
-    // measured break-even (scratch/fuse_threshold_probe.py, scripts/size_sweep.py): the warp-specialised kernel
-    // (Int<1> -> Int<4>, cw = 2048 / 4096 / 8192) wins from ~1000 rows (nv = 20: 0.144 vs 0.151 ms, nv = 21: 0.266 vs
-    // 0.285, nv = 22: 0.506 vs 0.538) and ties at 512; the two-CTA fused kernel of the other shapes from 2048 rows
-    // cw = 1024: already from 256 rows (nv = 17: 0.031 vs 0.035 ms, nv = 18: 0.052 vs 0.057; 32768 rows: 1.96 vs 2.04)
+    // measured break-even (scripts/shard_sweep.py, round 2): the warp-specialised kernel (Int<1> -> Int<4>) beats encode +
+    // leaf pass from 128 rows for cw = 2048 / 4096 / 8192 (cw = 8192: 256 rows 0.162 vs 0.166 ms, 512 rows 0.277 vs 0.302;
+    // cw = 2048: 128 rows 0.043 vs 0.052) and from 256 rows for cw = 1024 (nv = 17: 0.031 vs 0.035 ms); the two-CTA fused
+    // kernel of the other shapes from ~10 rows per CTA slot
     const bool ws = code->in_limbs == 1 && code->out_limbs == 4 &&
                     (code->cw == 1024 || code->cw == 2048 || code->cw == 4096 || code->cw == 8192);
-    if (ws && code->cw == 1024) return 256;
-    return (size_t)(ws || code->cw >= 8192 ? 6 : 10) * ctx->num_sms;
+    if (ws) return code->cw == 1024 ? 256 : 128;
+    return (size_t)(code->cw >= 8192 ? 6 : 10) * ctx->num_sms;
 }
 
 // Encode + Merkle of a row range on stream s, with optional profiling events.  until_level >= 0 stops the trees at the
@@ -988,7 +989,8 @@ static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
         }
         return ZIPGPU_OK;
     }
-    int rc = encode_dev(code, num_rows, d_evals, d_rows, s, fuse ? d_layers : nullptr, evals_copy);
+    int fused_levels = code->fused_levels;  // the launch reports how far it really built the trees (sub-row units stop lower)
+    int rc = encode_dev(code, num_rows, d_evals, d_rows, s, fuse ? d_layers : nullptr, evals_copy, &fused_levels);
     if (rc) return rc;
     if (prof) {
         cudaEventRecord(r.e1, s);
@@ -997,7 +999,7 @@ static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     if (reached) *reached = 0;
     if (d_roots) {
         rc = merkle_dev(ctx, num_rows, code->depth, code->out_limbs, d_rows, d_layers, d_roots, s,
-                        fuse ? code->fused_levels : 0, until_level, reached, fan);
+                        fuse ? fused_levels : 0, until_level, reached, fan);
         if (rc) return rc;
         if (prof) {
             cudaEventRecord(r.e2, s);
