@@ -41,6 +41,13 @@ def main():
     torch.cuda.set_stream(stream)
     sptr = C.c_void_p(stream.cuda_stream)
     knobs = {k: v for k, v in os.environ.items() if k.startswith("ZIPGPU_")}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        nvh = pynvml.nvmlDeviceGetHandleByIndex(0)
+    except Exception:
+        pynvml = None
     for rows in [int(x) for x in args.rows.split(",")]:
         ev = torch.from_numpy(np.random.default_rng(rows).integers(0, 1 << 63, size=rows * row_len, dtype=np.int64)).to(dev)
         d_rows = torch.empty(rows * cw * 4, dtype=torch.int64, device=dev)
@@ -59,6 +66,12 @@ def main():
         for _ in range(args.reps):
             run()
         b.record(stream)
+        mhz = None
+        if pynvml is not None:  # the GPU is still busy with the queued launches: the clock under load
+            clk = []
+            while not b.query():
+                clk.append(pynvml.nvmlDeviceGetClockInfo(nvh, pynvml.NVML_CLOCK_SM))
+            mhz = float(np.median(clk)) if clk else None
         torch.cuda.synchronize()
         e_, h_, c_ = C.c_double(), C.c_double(), C.c_uint64()
         nat.check(L.zipgpu_profile_read(ctx.handle, C.byref(e_), C.byref(h_), C.byref(c_), 1))
@@ -67,7 +80,7 @@ def main():
         floor_ms = rows * (2 * cw - 1) * 456.0 / (64.0 * sms * 1.965e9) * 1e3
         print(json.dumps({"row_len": row_len, "rows": rows, "ms": round(ms, 4), "first_kernel_ms": round(e_.value / c_.value, 4),
                           "rest_ms": round(h_.value / c_.value, 4), "launches": (ctx.launch_count - l0) // args.reps,
-                          "x_alu_floor": round(ms / floor_ms, 3), "knobs": knobs}), flush=True)
+                          "x_alu_floor": round(ms / floor_ms, 3), "sm_mhz": mhz, "knobs": knobs}), flush=True)
         del ev, d_rows, d_lay, d_roots
         torch.cuda.empty_cache()
 

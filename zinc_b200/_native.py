@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzipgpu.so")
+LIB_PATH = os.environ.get("ZIPGPU_LIB") or os.path.join(_HERE, "libzipgpu.so")  # ZIPGPU_LIB: A/B builds (build.py --variant)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_WIDTH, ERR_PEER_TIMEOUT = 0, -1, -2, -3, -4, -5, -6, -7
 

@@ -36,11 +36,11 @@ def _stale(target: str, srcs: list[str]) -> bool:
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
-def _compile(src: str, verbose: bool) -> str:
-    obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+def _compile(src: str, verbose: bool, objdir: str = OBJ, extra: tuple = ()) -> str:
+    obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
     path = os.path.join(CSRC, src)
     if _stale(obj, [path] + _deps()):
-        cmd = [NVCC, *ARCH, *CUFLAGS, "-c", path, "-o", obj]
+        cmd = [NVCC, *ARCH, *CUFLAGS, *extra, "-c", path, "-o", obj]
         if verbose:
             cmd += ["-Xptxas", "-v"]
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -66,5 +66,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """an A/B build for experiments: zinc_b200/libzipgpu_<name>.so compiled with extra -D flags (load it with ZIPGPU_LIB)"""
+    objdir = os.path.join(CSRC, "_build_" + name)
+    os.makedirs(objdir, exist_ok=True)
+    extra = tuple("-D" + d for d in defines)
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(lambda s: _compile(s, False, objdir, extra), SOURCES))
+    lib = os.path.join(HERE, f"libzipgpu_{name}.so")
+    r = subprocess.run([NVCC, *ARCH, "-shared", "-o", lib, *objs, "-cudart", "static"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return lib
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

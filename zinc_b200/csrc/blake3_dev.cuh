@@ -45,6 +45,10 @@ __device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t b, uint32_t one
     return r;
 }
 
+// (Round 2, measured slower: issuing the reg + constant adds of round 0 -- "+ x" onto a folded a + b, and c + d with c
+// still a constant -- as IMAD with the run-time multiplier instead of VIADD removed 8 alu-pipe instructions per
+// compression, but the fused commit kernel went from 1.849 to 1.923 ms: the three-register IMAD form is the expensive
+// one, as the 21.3 clk figure above already said.)
 #define ZIPGPU_B3_G(a, b, c, d, x, y, HX, HY)         \
     a = add_fma(a, b, one);                           \
     if (HX) a = a + (x);                              \

@@ -6,8 +6,11 @@
 //   warps 0..n-1  (ENC)  : stage -> gather -> scan -> gather -> scan -> park s2 in plane set `buf` -> write the codeword
 //                          out (record tiles + bulk stores), then straight on to the next row in the other plane set
 //   warps n..2n-1 (HASH) : BLAKE3 leaves and the lowest tree levels of the row parked in `buf`, straight from the planes
-// Two named barriers per plane set hand it back and forth (full: ENC arrives / HASH waits; empty: HASH arrives / ENC
-// waits).  This is what the hardware made of the two-CTA fused kernel anyway -- its warp schedulers let one CTA of
+// Two mbarriers per plane set hand it back and forth (full: ENC arrives / HASH waits; empty: HASH arrives / ENC waits).
+// (Round 1 used named barriers, bar.arrive / bar.sync: a bar.sync only completes when ALL waiters have arrived, which put
+// the 16 hash warps in lockstep at every row boundary -- the fast ones idled until the slowest was done.  With mbarriers
+// a hash warp starts the next row the moment it is parked, and the warps may drift apart by up to a row.)
+// This is what the hardware made of the two-CTA fused kernel anyway -- its warp schedulers let one CTA of
 // every pair run as if alone (75 us per row, 62 of them hashing) and starved the other -- minus the 13 us per row the
 // favoured CTA spent not hashing: here the hash warps never leave the alu pipe.
 //
@@ -31,7 +34,11 @@
 
 namespace zipgpu {
 
-constexpr int kBarEnc = 1, kBarFull0 = 2, kBarEmpty0 = 4;  // + buf
+constexpr int kBarEnc = 1;  // named barrier of the ENC group
+// hand-over of the plane sets: 0 = named barriers (bar.arrive / bar.sync), 1 = mbarriers, every thread waits for itself,
+// 2 = mbarriers, one ENC warp polls for its group (the hash threads always wait for themselves)
+constexpr uint32_t kHandNamed = 0, kHandMbarAll = 1, kHandMbarOne = 2;
+constexpr int kBarFull0 = 2, kBarEmpty0 = 4;  // + buf (kHandNamed)
 template <int ALL>
 __device__ __forceinline__ void ws_sync(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(ALL) : "memory"); }
 template <int ALL>
@@ -45,7 +52,7 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
     commit_ws_kernel(const uint32_t *__restrict__ evals, uint32_t *__restrict__ rows_out,
                      const uint16_t *__restrict__ tab1, const uint16_t *__restrict__ tab2,
                      const uint8_t *__restrict__ colw, uint32_t num_rows, uint8_t *__restrict__ layers, uint32_t one,
-                     uint32_t *__restrict__ row_counter) {
+                     uint32_t *__restrict__ row_counter, uint32_t hand) {
     constexpr int IN32 = 2, W = 3, OUT32 = 8, kWsAll = 2 * kWsEnc;
     constexpr uint32_t T = kWsEnc, P = T * E, cw = P, in_words = (P / 2) * IN32;
     constexpr int EH = E / U;                   // entries per hash thread and unit
@@ -59,12 +66,23 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
     uint32_t *tiles = aux + 64 * W;             // one 1 KiB record tile per ENC warp
     __shared__ volatile uint32_t s_row[2];      // row parked in each plane set (0xffffffff: no more rows)
     __shared__ volatile uint32_t s_next;
+    __shared__ unsigned long long s_full[2], s_empty[2];  // mbarriers: plane set parked / plane set free again
     const uint32_t tid = threadIdx.x;
     const uint32_t t = tid & (kWsEnc - 1);      // index within the group
     // U > 1: this CTA's static share of the num_rows * U units
     const uint32_t total_units = num_rows * U;
     const uint32_t u0 = U == 1 ? 0u : (uint32_t)(((uint64_t)blockIdx.x * total_units) / gridDim.x);
     const uint32_t u1 = U == 1 ? 0u : (uint32_t)(((uint64_t)(blockIdx.x + 1) * total_units) / gridDim.x);
+
+    if (tid == 0) {
+        mbar_init(&s_full[0], kWsEnc);
+        mbar_init(&s_full[1], kWsEnc);
+        mbar_init(&s_empty[0], kWsEnc);
+        mbar_init(&s_empty[1], kWsEnc);
+    }
+    __syncthreads();
+    // use number n (0, 1, ..) of plane set b is iteration it = 2n + b: its "full" phase has parity n & 1, and the ENC
+    // group may refill the set once the "empty" phase of use n - 1 has completed
 
     if (tid < kWsEnc) {
         // ============================== ENC ==============================
@@ -78,7 +96,14 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
         for (; row < row_end; it++) {
             const uint32_t buf = it & 1u;
             uint32_t *pl = planes + buf * (W * P);
-            if (it >= 2) ws_sync<kWsAll>(kBarEmpty0 + buf);  // the hash warps are done with this plane set
+            if (it >= 2) {  // the hash warps are done with this plane set
+                if (hand == kHandNamed) ws_sync<kWsAll>(kBarEmpty0 + buf);
+                else if (hand == kHandMbarAll) mbar_wait(&s_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                else {
+                    if (t < 32) mbar_wait(&s_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                    EncBar::sync();
+                }
+            }
             uint32_t early = U == 1 ? row + gridDim.x : row + 1;
             if (U == 1 && t == 0 && row_counter) early = gridDim.x + atomicAdd(row_counter, 1u) + 1u;
             {
@@ -127,7 +152,9 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
                 for (int w = 0; w < W; w++) pl[w * P + s2] = v[k][w];
             }
             if (t == 0) s_row[buf] = row;
-            ws_arrive<kWsAll>(kBarFull0 + buf);  // hand the row to the hash warps
+            // hand the row to the hash warps (every thread's arrive releases its own writes)
+            if (hand == kHandNamed) ws_arrive<kWsAll>(kBarFull0 + buf);
+            else mbar_arrive(&s_full[buf]);
             __syncwarp();
             T16::load(tab1, t, T, c1);   // for the next row; in flight during the write-out
             // write-out of this warp's 32E positions: 32-byte records into the warp's tile, one bulk store per KiB.
@@ -161,9 +188,13 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
         }
         {   // no more rows: tell the hash warps through the next plane set
             const uint32_t buf = it & 1u;
-            if (it >= 2) ws_sync<kWsAll>(kBarEmpty0 + buf);
+            if (it >= 2) {
+                if (hand == kHandNamed) ws_sync<kWsAll>(kBarEmpty0 + buf);
+                else mbar_wait(&s_empty[buf], ((it >> 1) & 1u) ^ 1u);
+            }
             if (t == 0) s_row[buf] = 0xffffffffu;
-            ws_arrive<kWsAll>(kBarFull0 + buf);
+            if (hand == kHandNamed) ws_arrive<kWsAll>(kBarFull0 + buf);
+            else mbar_arrive(&s_full[buf]);
         }
         if (lane == 0) bulk_wait_all();
     } else {
@@ -172,7 +203,8 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
         static_assert((1 << H) == EH, "entries per hash thread: a power of two");
         for (uint32_t it = 0;; it++) {
             const uint32_t buf = it & 1u;
-            ws_sync<kWsAll>(kBarFull0 + buf);
+            if (hand == kHandNamed) ws_sync<kWsAll>(kBarFull0 + buf);
+            else mbar_wait(&s_full[buf], (it >> 1) & 1u);
             const uint32_t row = s_row[buf];
             if (row == 0xffffffffu) break;
             const uint32_t *pl = planes + buf * (W * P);
@@ -187,10 +219,12 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
             for (; uu < uu_end; uu++) {
                 const uint32_t pbase = (uu * T + t) * EH;  // first of this thread's EH consecutive positions
                 b3::Digest stack[H];
-#pragma unroll 1
+#pragma unroll 1  // (unrolled by 2: 1.847 -> 2.045 ms, the loop no longer fits the instruction cache)
                 for (uint32_t k = 0; k < (uint32_t)EH; k++) {
                     const uint32_t idx = pbase + k;  // leaf index within the row
                     const uint32_t s = slot_of<E>(idx / E, idx % E, T);
+                    // (building the message from the 3 value words + the sign word directly -- a byte-swapped sign word is
+                    // itself -- saves 5 PRMT per leaf and measured 3 % SLOWER: ptxas schedules the compression differently)
                     uint32_t x[OUT32];
 #pragma unroll
                     for (int w = 0; w < W; w++) x[w] = pl[w * P + s];
@@ -203,7 +237,16 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
 #pragma unroll 1
                     for (int l = 0; l < H; l++) {
                         if ((k >> l) & 1u) {
+#ifdef ZIPGPU_WS_CALL_NODE  // A/B builds
                             d = b3::hash_node_call(stack[l], d, one);
+#else
+                            {   // inlined: this is the only call site in the loop, so nothing is duplicated, and the call,
+                                // its register shuffling and the late stack loads go away (fused kernel 1.847 -> 1.833 ms)
+                                b3::Digest o;
+                                b3::hash_node(stack[l].w, d.w, o.w, one);
+                                d = o;
+                            }
+#endif
                             const size_t off = 2 * (size_t)cw - ((2 * (size_t)cw) >> (l + 1));
                             st_global_v8(lay_row + (off + (idx >> (l + 1))) * 32, d.w);
                         } else {
@@ -213,7 +256,9 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
                     }
                 }
             }
-            ws_arrive<kWsAll>(kBarEmpty0 + buf);  // the plane set may be overwritten
+            // the plane set may be overwritten once all hash threads have said so
+            if (hand == kHandNamed) ws_arrive<kWsAll>(kBarEmpty0 + buf);
+            else mbar_arrive(&s_empty[buf]);
         }
     }
 }
@@ -238,8 +283,9 @@ cudaError_t launch_ws_u(const EncodeArgs &a, uint32_t grid) {
         const uint32_t units = a.num_rows * U;
         if (grid > units) grid = units;
     }
+    static const uint32_t hand = getenv("ZIPGPU_WS_HAND") ? (uint32_t)atoi(getenv("ZIPGPU_WS_HAND")) : kHandMbarOne;
     kern<<<grid, 2 * TENC, ws_smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows, a.fuse_layers, 1u,
-                                                row_counter);
+                                                row_counter, hand);
     return cudaGetLastError();
 }
 

@@ -42,6 +42,28 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 // all bulk groups of this thread are complete (the global writes are done)
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- mbarrier (shared-memory arrive/wait objects, sm_80+): unlike bar.sync, waiters do not synchronise with each
+// other -- every thread (warp) proceeds as soon as the phase it waits for has completed ----
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {  // release.cta
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {  // acquire.cta
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
 // 32-byte global accesses (sm_100: LDG/STG.E.ENL2.256): one full sector per lane, so a 32-byte digest or Int<4>
 // never reaches L2 as two partial-sector writes
 struct __align__(32) u32x8 {
