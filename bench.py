@@ -602,7 +602,7 @@ def single_gpu_extras(args, ctx, L, nat, C, torch, dev, stream, sptr, make_code,
         configs = {}
         # ---- per-size table (device-resident, kernel-only) ----
         sizes = {}
-        for snv in (16, 20, 22, 24, 26):
+        for snv in (16, 20, 22, 24, 26, 27):
             srl, snr, scw = shape_for(snv)
             sdepth = scw.bit_length() - 1
             try:
@@ -617,7 +617,7 @@ def single_gpu_extras(args, ctx, L, nat, C, torch, dev, stream, sptr, make_code,
                 run = lambda: nat.check(L.zipgpu_commit_device(shc, snr, sev.data_ptr(), srows.data_ptr(),
                                                                slay.data_ptr(), sroots.data_ptr(), sptr))
                 enc = lambda: nat.check(L.zipgpu_encode_rows_device(shc, snr, sev.data_ptr(), srows.data_ptr(), sptr))
-                reps = 10 if snv <= 24 else 4
+                reps = 10 if snv <= 24 else (4 if snv <= 26 else 2)
                 o = {"commit_ms": gpu_ms(run, reps), "encode_ms": gpu_ms(enc, reps)}
                 o["evals_per_s"] = (1 << snv) / (o["commit_ms"] * 1e-3)
                 o["encode_GBps"] = ENC_BYTES_PER_EVAL * (1 << snv) / (o["encode_ms"] * 1e-3) / 1e9

@@ -441,3 +441,44 @@ def test_peer_roots_two_gpus():
         p.join(120)
     res = sorted(q.get(timeout=5) for _ in range(2))
     assert res == [(0, True), (1, True)], res
+
+
+@pytest.mark.parametrize("row_len,num_rows,limbs", [(16384, 37, 1), (32768, 5, 1), (65536, 3, 1), (16384, 6, 2)])
+def test_codewords_longer_than_shared_memory(row_len, num_rows, limbs, oracle, ctx):
+    """cw = 32768 / 65536 / 131072 (nv = 27 ... 34 row shapes; code_raa.rs:42-43 and structs.rs:79-90 put no bound on nv):
+    the chunked encoder of raa_big.cu (scans through global scratch, raw permutations) -- codewords, every Merkle layer
+    and the roots of a row sample against the oracle; cw = 131072 needs 98-bit entries (4-limb scans), Int<2> inputs
+    5-limb scans"""
+    from zinc_b200 import DenseMultilinearExtension, MultilinearZip, MultilinearZipParams, RaaCode, RandomFieldZipTypes
+
+    cw = 2 * row_len
+    p1, p2 = oracle.perm_from_seed(cw, KECCAK_SEEDS[0]), oracle.perm_from_seed(cw, KECCAK_SEEDS[1])
+    zt = RandomFieldZipTypes(limbs)
+    code = RaaCode.with_permutations(zt, row_len, 2, p1, p2)
+    evals = np.random.default_rng(row_len + limbs).integers(0, 1 << 64, size=num_rows * row_len * limbs, dtype=np.uint64)
+    rc, rows, layers, roots = oracle.commit(evals, num_rows, row_len, 2, p1, p2, in_limbs=limbs, out_limbs=4 * limbs)
+    assert rc == 0
+    nv = (num_rows * row_len - 1).bit_length()
+    pp = MultilinearZipParams.new(nv, num_rows, code)
+    poly = DenseMultilinearExtension(evals.reshape(-1, limbs), nv)
+    data, comm = MultilinearZip.commit(pp, poly, ctx)
+    assert np.array_equal(data.rows.reshape(-1), rows)
+    assert np.array_equal(np.concatenate([t.layers.reshape(-1) for t in data.rows_merkle_trees]), layers)
+    assert b"".join(comm.roots) == roots.tobytes()
+
+
+def test_encode_rows_long_non_power_of_two_codeword(oracle, ctx):
+    """encode_rows / commit_no_merkle only need the code, not a power-of-two codeword: cw = 20000 (3 chunks, the last
+    one partial) through the chunked encoder"""
+    from zinc_b200 import MultilinearZip, MultilinearZipParams, RaaCode, ZipTypes
+
+    row_len, num_rows = 10000, 9
+    cw = 2 * row_len
+    p1, p2 = oracle.perm_from_seed(cw, 1), oracle.perm_from_seed(cw, 2)
+    code = RaaCode.with_permutations(ZipTypes(), row_len, 2, p1, p2)
+    evals = np.random.default_rng(3).integers(0, 1 << 64, size=num_rows * row_len, dtype=np.uint64)
+    rc, rows = oracle.encode_rows(evals, num_rows, row_len, 2, p1, p2)
+    assert rc == 0
+    pp = MultilinearZipParams.new(17, num_rows, code)
+    got = MultilinearZip.encode_rows(pp, cw, row_len, evals, ctx)
+    assert np.array_equal(got.reshape(-1), rows)

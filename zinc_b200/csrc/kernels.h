@@ -35,6 +35,21 @@ int encode_compute_limbs(int in_limbs, uint32_t cw);
 bool encode_supported(int in_limbs, uint32_t cw, uint32_t row_len);
 cudaError_t launch_raa_encode(const EncodeArgs &a);
 
+// ---- K1b: RAA encoder for codewords longer than one SM's shared memory holds (raa_big.cu): chunked scans through
+// global scratch; the permutations are used as uploaded ----
+struct BigEncodeArgs {
+    const uint32_t *evals;    // [num_rows][row_len][2*in_limbs]
+    uint32_t *rows_out;       // [num_rows][cw][out32]
+    const uint32_t *perm1, *perm2;  // device u32[cw]
+    uint32_t *scratch;        // raa_big_plan() bytes
+    uint32_t num_rows, row_len, cw, out32, batch_rows;
+    int in_limbs;
+    cudaStream_t stream;
+};
+bool raa_big_supported(int in_limbs, uint32_t cw);
+void raa_big_plan(int in_limbs, uint32_t cw, uint32_t num_rows, uint32_t *batch_rows, size_t *scratch_bytes);
+cudaError_t launch_raa_encode_big(const BigEncodeArgs &a, int *launches);
+
 // ---- multi-GPU: the roots exchange of a row-sharded commit (peer_roots.cu, merkle.cu) ----
 // One per zipgpu_peer_roots object, in device memory, written once when the peers are connected.  The kernel that
 // produces the roots of this GPU's row range stores every root straight into every peer's result buffer (P2P stores

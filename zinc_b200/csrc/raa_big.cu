@@ -1,0 +1,205 @@
+// zinc_b200/csrc/raa_big.cu -- RAA encoder for codewords that do not fit one SM's shared memory (cw > 16384: nv >= 27).
+//
+// Same function as raa_encode.cu -- repeat -> shuffle(perm1) -> accumulate -> shuffle(perm2) -> accumulate
+// (code_raa.rs:89-105,142-171) -- with the row cut into chunks of 8192 codeword positions, one CTA per chunk, and the two
+// intermediate vectors in global scratch instead of shared-memory planes:
+//   pass 1: y1[i] = widen(row[perm1[i] mod row_len]); scan inside the chunk -> s1_local, chunk total
+//   pass 2: y2[i] = s1_local[perm2[i]] + (sum of the totals of the chunks before perm2[i]'s); scan inside the chunk ->
+//           s2_local, chunk total
+//   pass 3: out[i] = sign_extend(s2_local[i] + sum of the totals of the chunks before i's)
+// The prefix over the chunk totals is recomputed by every consumer CTA (a row has cw / 8192 chunks: 4 at nv = 27/28), so
+// no pass waits for another CTA and there is no look-back chain.  Rows are processed in batches whose scratch stays
+// around 1 GiB.  Traffic is ~3x the compulsory 72 B per evaluation (scratch written and re-read, random 16-byte
+// gathers); at these sizes the BLAKE3 passes that follow take 4x longer than this encoder, so the commit is still
+// alu-bound.  The permutations are used as uploaded (u32[cw]); no per-pp table translation.
+#include <algorithm>
+
+#include "raa_common.cuh"
+
+namespace zipgpu {
+
+namespace {
+
+constexpr int kBigE = 16, kBigT = 512, kBigChunk = kBigE * kBigT;  // 8192 positions per CTA
+
+template <int W, int SW>
+__device__ __forceinline__ void load_entry(const uint32_t *p, uint32_t (&x)[W]) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(p);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z;
+    if constexpr (W > 3) x[3] = a.w;
+    if constexpr (SW == 8) {
+        const uint4 b = *reinterpret_cast<const uint4 *>(p + 4);
+        if constexpr (W > 4) x[4] = b.x;
+        if constexpr (W > 5) x[5] = b.y;
+    }
+}
+template <int W, int SW>
+__device__ __forceinline__ void store_entry(uint32_t *p, const uint32_t (&x)[W]) {
+    uint4 a;
+    a.x = x[0]; a.y = x[1]; a.z = x[2]; a.w = W > 3 ? x[W > 3 ? 3 : 0] : 0u;
+    *reinterpret_cast<uint4 *>(p) = a;
+    if constexpr (SW == 8) {
+        uint4 b;
+        b.x = W > 4 ? x[W > 4 ? 4 : 0] : 0u; b.y = W > 5 ? x[W > 5 ? 5 : 0] : 0u; b.z = 0u; b.w = 0u;
+        *reinterpret_cast<uint4 *>(p + 4) = b;
+    }
+}
+
+// exclusive prefix over the chunk totals of one row into shared memory: pref[c] = sum_{c' < c} tot[c']
+template <int W>
+__device__ __forceinline__ void chunk_prefixes(const uint32_t *tot_row, uint32_t nchunks, uint32_t *pref, uint32_t t) {
+    if (t == 0) {
+        uint32_t acc[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) acc[w] = 0u;
+        for (uint32_t c = 0; c < nchunks; c++) {
+#pragma unroll
+            for (int w = 0; w < W; w++) pref[c * W + w] = acc[w];
+            uint32_t x[W];
+#pragma unroll
+            for (int w = 0; w < W; w++) x[w] = tot_row[c * W + w];
+            add_limbs<W>(acc, x);
+        }
+    }
+    __syncthreads();
+}
+
+// PASS 1 / PASS 2 (GATHER2): one CTA = one chunk of one row
+template <int IN32, int W, int SW, bool GATHER2>
+__global__ void __launch_bounds__(kBigT)
+    raa_big_scan_kernel(const uint32_t *__restrict__ evals, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ src_local,
+                        const uint32_t *__restrict__ src_tot, uint32_t *__restrict__ dst_local, uint32_t *__restrict__ dst_tot,
+                        uint32_t row0, uint32_t row_len, uint32_t cw, uint32_t nchunks) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *aux = smem;                 // block_scan scratch: 64 * W words
+    uint32_t *pref = smem + 64 * W;       // GATHER2: nchunks * W words
+    const uint32_t t = threadIdx.x, chunk = blockIdx.x, lrow = blockIdx.y;
+    const size_t row = (size_t)row0 + lrow;
+    if constexpr (GATHER2) chunk_prefixes<W>(src_tot + (size_t)lrow * nchunks * W, nchunks, pref, t);
+    uint32_t v[kBigE][W];
+    const uint32_t i0 = chunk * kBigChunk + t * kBigE;
+#pragma unroll
+    for (int k = 0; k < kBigE; k++) {
+        const uint32_t i = i0 + k;
+        if (i < cw) {
+            const uint32_t j = __ldg(perm + i);
+            if constexpr (!GATHER2) {
+                const uint32_t *e = evals + (row * row_len + (j % row_len)) * IN32;
+#pragma unroll
+                for (int w = 0; w < IN32; w++) v[k][w] = __ldg(e + w);
+                const uint32_t sign = (uint32_t)((int32_t)v[k][IN32 - 1] >> 31);
+#pragma unroll
+                for (int w = IN32; w < W; w++) v[k][w] = sign;
+            } else {
+                load_entry<W, SW>(src_local + ((size_t)lrow * cw + j) * SW, v[k]);
+                uint32_t p[W];
+#pragma unroll
+                for (int w = 0; w < W; w++) p[w] = pref[(j / kBigChunk) * W + w];
+                add_limbs<W>(v[k], p);
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < W; w++) v[k][w] = 0u;
+        }
+    }
+    uint32_t pre[W];
+    block_scan<W, kBigE>(v, pre, aux, t, kBigT / 32);
+#pragma unroll
+    for (int k = 0; k < kBigE; k++) {
+        add_limbs<W>(v[k], pre);
+        if (i0 + k < cw) store_entry<W, SW>(dst_local + ((size_t)lrow * cw + i0 + k) * SW, v[k]);
+    }
+    if (t == kBigT - 1) {
+#pragma unroll
+        for (int w = 0; w < W; w++) dst_tot[((size_t)lrow * nchunks + chunk) * W + w] = v[kBigE - 1][w];
+    }
+}
+
+// PASS 3: out[i] = sign_extend(s2_local[i] + prefix of its chunk), out32 words per entry
+template <int W, int SW>
+__global__ void __launch_bounds__(kBigT)
+    raa_big_out_kernel(const uint32_t *__restrict__ src_local, const uint32_t *__restrict__ src_tot, uint32_t *__restrict__ rows_out,
+                       uint32_t row0, uint32_t cw, uint32_t nchunks, uint32_t out32) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *pref = smem;
+    const uint32_t t = threadIdx.x, chunk = blockIdx.x, lrow = blockIdx.y;
+    const size_t row = (size_t)row0 + lrow;
+    chunk_prefixes<W>(src_tot + (size_t)lrow * nchunks * W, nchunks, pref, t);
+    uint32_t p[W];
+#pragma unroll
+    for (int w = 0; w < W; w++) p[w] = pref[chunk * W + w];
+    for (uint32_t q = t; q < (uint32_t)kBigChunk; q += kBigT) {  // consecutive lanes write consecutive entries
+        const uint32_t i = chunk * kBigChunk + q;
+        if (i >= cw) break;
+        uint32_t x[W];
+        load_entry<W, SW>(src_local + ((size_t)lrow * cw + i) * SW, x);
+        add_limbs<W>(x, p);
+        const uint32_t sign = (uint32_t)((int32_t)x[W - 1] >> 31);
+        uint32_t *d = rows_out + (row * cw + i) * out32;
+        if ((out32 & 7u) == 0) {
+            for (uint32_t o = 0; o < out32; o += 8) {
+                uint32_t rec[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) rec[j] = (o + j < (uint32_t)W) ? x[(o + j < (uint32_t)W) ? o + j : 0] : sign;
+                st_global_v8(d + o, rec);
+            }
+        } else {
+            for (uint32_t o = 0; o < out32; o++) d[o] = o < (uint32_t)W ? x[o < (uint32_t)W ? o : 0] : sign;
+        }
+    }
+}
+
+template <int IN32, int W>
+cudaError_t launch_big_w(const BigEncodeArgs &a) {
+    constexpr int SW = W <= 4 ? 4 : 8;
+    const uint32_t nchunks = (a.cw + kBigChunk - 1) / kBigChunk;
+    const size_t smem_scan = (64 * W + (size_t)nchunks * W) * sizeof(uint32_t), smem_out = (size_t)nchunks * W * sizeof(uint32_t);
+    if (smem_scan > 200 * 1024) return cudaErrorInvalidConfiguration;
+    auto k1 = raa_big_scan_kernel<IN32, W, SW, false>;
+    auto k2 = raa_big_scan_kernel<IN32, W, SW, true>;
+    auto k3 = raa_big_out_kernel<W, SW>;
+    cudaError_t err;
+    if ((err = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_out, 16))) != cudaSuccess)
+        return err;
+    uint32_t *s1 = a.scratch, *s2 = s1 + (size_t)a.batch_rows * a.cw * SW;
+    uint32_t *t1 = s2 + (size_t)a.batch_rows * a.cw * SW, *t2 = t1 + (size_t)a.batch_rows * nchunks * W;
+    for (uint32_t r0 = 0; r0 < a.num_rows; r0 += a.batch_rows) {
+        const uint32_t nr = std::min(a.batch_rows, a.num_rows - r0);
+        const dim3 grid(nchunks, nr);
+        k1<<<grid, kBigT, 64 * W * sizeof(uint32_t), a.stream>>>(a.evals, a.perm1, nullptr, nullptr, s1, t1, r0, a.row_len, a.cw, nchunks);
+        k2<<<grid, kBigT, smem_scan, a.stream>>>(nullptr, a.perm2, s1, t1, s2, t2, r0, a.row_len, a.cw, nchunks);
+        k3<<<grid, kBigT, std::max<size_t>(smem_out, 16), a.stream>>>(s2, t2, a.rows_out, r0, a.cw, nchunks, a.out32);
+        if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace
+
+// rows per batch and scratch bytes for a big-codeword encode (s1 + s2 local scans, chunk totals): ~1 GiB of scratch
+void raa_big_plan(int in_limbs, uint32_t cw, uint32_t num_rows, uint32_t *batch_rows, size_t *scratch_bytes) {
+    const int W = encode_compute_limbs(in_limbs, cw), SW = W <= 4 ? 4 : 8;
+    const size_t per_row = (size_t)cw * SW * 4 * 2 + (size_t)((cw + kBigChunk - 1) / kBigChunk) * W * 4 * 2;
+    size_t rows = std::max<size_t>(1, ((size_t)1 << 30) / per_row);
+    rows = std::min<size_t>(rows, std::max<uint32_t>(num_rows, 1));
+    *batch_rows = (uint32_t)rows;
+    *scratch_bytes = rows * per_row + 256;
+}
+
+bool raa_big_supported(int in_limbs, uint32_t cw) {
+    const int W = encode_compute_limbs(in_limbs, cw);
+    return cw <= (1u << 24) && ((in_limbs == 1 && (W == 3 || W == 4)) || (in_limbs == 2 && (W == 5 || W == 6)));
+}
+
+cudaError_t launch_raa_encode_big(const BigEncodeArgs &a, int *launches) {
+    const int W = encode_compute_limbs(a.in_limbs, a.cw);
+    if (launches) *launches = 3 * (int)((a.num_rows + a.batch_rows - 1) / a.batch_rows);
+    if (a.in_limbs == 1 && W <= 3) return launch_big_w<2, 3>(a);
+    if (a.in_limbs == 1 && W == 4) return launch_big_w<2, 4>(a);
+    if (a.in_limbs == 2 && W <= 5) return launch_big_w<4, 5>(a);
+    if (a.in_limbs == 2 && W == 6) return launch_big_w<4, 6>(a);
+    return cudaErrorInvalidConfiguration;
+}
+
+}  // namespace zipgpu

@@ -83,6 +83,9 @@ struct zipgpu_code {
     int fused_levels;  // Merkle levels the fused commit kernel produces (0: no fused variant for this shape)
     uint16_t *d_tab1, *d_tab2;  // pre-translated gather tables (raa_encode.cu)
     uint8_t *d_colw;
+    // codewords longer than one SM's shared memory holds (cw > 16384): chunked encoder of raa_big.cu, raw permutations
+    bool big = false;
+    uint32_t *d_perm1 = nullptr, *d_perm2 = nullptr;
     // ZipLinearCode (zipgpu_sparse_code_create): either the ELL tables of the generic kernel or the dense 0/1 matrix
     // of the tensor-core kernel (sparse_encode.cu)
     bool sparse = false;
@@ -439,10 +442,10 @@ extern "C" int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t rep, i
                                           std::to_string(64 * out_limbs) + " bits integers");
     if (!is_permutation(perm1, cw) || !is_permutation(perm2, cw))
         return fail(ZIPGPU_ERR_INVALID, "perm1/perm2 must be permutations of [0, codeword_len)");
-    if (!encode_supported(in_limbs, (uint32_t)cw, (uint32_t)row_len))
+    const bool big = !encode_supported(in_limbs, (uint32_t)cw, (uint32_t)row_len);
+    if (big && !raa_big_supported(in_limbs, (uint32_t)cw))
         return fail(ZIPGPU_ERR_UNSUPPORTED, "no encoder kernel for in_limbs=" + std::to_string(in_limbs) +
-                                                " codeword_len=" + std::to_string(cw) +
-                                                " (the codeword must fit one SM's shared memory)");
+                                                " codeword_len=" + std::to_string(cw));
     API_LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     zipgpu_code *c = new (std::nothrow) zipgpu_code();
@@ -456,10 +459,24 @@ extern "C" int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t rep, i
     c->depth = is_pow2(cw) ? ilog2(cw) : -1;
     c->fused_levels = c->depth > 0 ? encode_fused_levels(in_limbs, out_limbs, (uint32_t)row_len, (uint32_t)cw) : 0;
     if (!merkle_supported(out_limbs * 2)) c->fused_levels = 0;
-    const size_t padded = encode_perm_padded_len((uint32_t)cw);
     c->d_tab1 = c->d_tab2 = nullptr;
     c->d_colw = nullptr;
     cudaError_t e;
+    if (big) {  // the chunked encoder reads the permutations as they are
+        c->big = true;
+        c->fused_levels = 0;
+        if ((e = cudaMalloc(&c->d_perm1, cw * 4)) != cudaSuccess || (e = cudaMalloc(&c->d_perm2, cw * 4)) != cudaSuccess ||
+            (e = cudaMemcpy(c->d_perm1, perm1, cw * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMemcpy(c->d_perm2, perm2, cw * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+            cudaFree(c->d_perm1);
+            cudaFree(c->d_perm2);
+            delete c;
+            return cuda_fail(e, "cudaMalloc/cudaMemcpy(permutations)");
+        }
+        *out = c;
+        return ZIPGPU_OK;
+    }
+    const size_t padded = encode_perm_padded_len((uint32_t)cw);
     if ((e = cudaMalloc(&c->d_tab1, padded * 2)) != cudaSuccess || (e = cudaMalloc(&c->d_tab2, padded * 2)) != cudaSuccess ||
         (e = cudaMalloc(&c->d_colw, padded)) != cudaSuccess) {
         cudaFree(c->d_tab1);
@@ -585,6 +602,8 @@ extern "C" void zipgpu_code_destroy(zipgpu_code *c) {
     cudaFree(c->d_tab1);
     cudaFree(c->d_tab2);
     cudaFree(c->d_colw);
+    cudaFree(c->d_perm1);
+    cudaFree(c->d_perm2);
     cudaFree(c->d_sp_dense);
     cudaFree(c->d_sp_bias);
     cudaFree(c->d_sp_cols);
@@ -835,6 +854,31 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
         if (e != cudaSuccess) return cuda_fail(e, "launch_sparse_encode");
         ctx->launches += n;
         if (sa.planes) DEV_FREE(ctx, sa.planes, s);
+        return ZIPGPU_OK;
+    }
+    if (code->big) {
+        if (fuse_layers || evals_copy) return fail(ZIPGPU_ERR_INVALID, "no fused commit kernel for codewords > 16384");
+        zipgpu_ctx *ctx = code->ctx;
+        BigEncodeArgs b;
+        b.evals = reinterpret_cast<const uint32_t *>(d_evals);
+        b.rows_out = reinterpret_cast<uint32_t *>(d_rows);
+        b.perm1 = code->d_perm1;
+        b.perm2 = code->d_perm2;
+        b.num_rows = (uint32_t)num_rows;
+        b.row_len = (uint32_t)code->row_len;
+        b.cw = (uint32_t)code->cw;
+        b.out32 = (uint32_t)code->out_limbs * 2;
+        b.in_limbs = code->in_limbs;
+        b.stream = s;
+        size_t scratch_bytes = 0;
+        raa_big_plan(code->in_limbs, b.cw, b.num_rows, &b.batch_rows, &scratch_bytes);
+        DevGuard guard(ctx, s);
+        DEV_ALLOC(ctx, &b.scratch, scratch_bytes, s);
+        int n = 0;
+        cudaError_t e = launch_raa_encode_big(b, &n);
+        if (e != cudaSuccess) return cuda_fail(e, "launch_raa_encode_big");
+        ctx->launches += n;
+        DEV_FREE(ctx, b.scratch, s);
         return ZIPGPU_OK;
     }
     EncodeArgs a;
