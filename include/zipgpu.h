@@ -129,6 +129,15 @@ int zipgpu_encode_rows(zipgpu_code *code, size_t num_rows, const uint64_t *evals
 int zipgpu_encode_rows_device(zipgpu_code *code, size_t num_rows, const uint64_t *d_evals, uint64_t *d_rows_out,
                               void *stream);
 
+/* ---- encode_f (code_raa.rs:133-138): the RAA code over field elements, as the verifier re-encodes the combined row
+ * (verify_z.rs:141-142).  Same permutations, every addition is the field's (RandomField AddAssign: add the stored
+ * residues, subtract the modulus once if the sum overflowed or is >= modulus; field/arithmetic.rs:66-77,
+ * field/config.rs:53-76).  Elements are `limbs` u64 words, least significant first -- the stored BigInt<N> of a
+ * RandomField<N> value (Montgomery form or not: addition does not care) -- and must be < modulus (checked).
+ *   rows: num_rows * row_len * limbs u64 (host);  out: num_rows * codeword_len * limbs u64 (host). */
+int zipgpu_encode_f(zipgpu_code *code, size_t num_rows, int limbs, const uint64_t *modulus, const uint64_t *rows,
+                    uint64_t *out);
+
 /* ---- MerkleTree::new batched over rows (pcs/utils.rs:74-118) ----------------------------------------- */
 /* leaves: num_rows * (1<<depth) values of leaf_limbs limbs.  layers_out nullable.  roots_out: num_rows*32. */
 int zipgpu_merkle_rows(zipgpu_ctx *ctx, size_t num_rows, int depth, int leaf_limbs, const uint64_t *leaves,

@@ -191,6 +191,30 @@ def encode_row_perm(row: list[int], rep: int, perm1: list[int], perm2: list[int]
     return accumulate([r[p] for p in perm2])
 
 
+def field_add(a: int, b: int, modulus: int, limbs: int) -> int:
+    """RandomField AddAssign (field/arithmetic.rs:66-77 -> FieldConfig::add_assign / reduce_modulus, field/config.rs:53-76):
+    s = a + b wrapping at 2^(64 limbs) with carry c; if c or s >= modulus: s -= modulus (wrapping)"""
+    full = a + b
+    carry, s = full >> (64 * limbs), full & ((1 << (64 * limbs)) - 1)
+    if carry or s >= modulus:
+        s = (s - modulus) & ((1 << (64 * limbs)) - 1)
+    return s
+
+
+def encode_f_row(row: list[int], rep: int, perm1, perm2, modulus: int, limbs: int) -> list[int]:
+    """RaaCode::encode_f (code_raa.rs:133-138) = encode_inner (code_raa.rs:89-105) with Out = F: repeat (142-152, a clone
+    of every element), shuffle, accumulate (164-171) with the field's +=, shuffle, accumulate.  Elements are the stored
+    residues of the RandomField values."""
+    n = len(row)
+    y = [row[perm1[i] % n] for i in range(n * rep)]  # repeat o shuffle_seeded in gather form
+    for i in range(1, len(y)):
+        y[i] = field_add(y[i], y[i - 1], modulus, limbs)
+    y = [y[perm2[i]] for i in range(len(y))]
+    for i in range(1, len(y)):
+        y[i] = field_add(y[i], y[i - 1], modulus, limbs)
+    return y
+
+
 def encode_rows(evals: list[int], num_rows: int, row_len: int, rep: int, perm1, perm2) -> list[int]:
     out: list[int] = []
     for i in range(num_rows):

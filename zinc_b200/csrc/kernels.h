@@ -50,6 +50,18 @@ bool raa_big_supported(int in_limbs, uint32_t cw);
 void raa_big_plan(int in_limbs, uint32_t cw, uint32_t num_rows, uint32_t *batch_rows, size_t *scratch_bytes);
 cudaError_t launch_raa_encode_big(const BigEncodeArgs &a, int *launches);
 
+// ---- encode_f: the RAA code over field elements (encode_f.cu) ----
+struct EncodeFArgs {
+    const uint32_t *rows_in;  // device [num_rows][row_len][2*limbs] residues < modulus
+    uint32_t *out;            // device [num_rows][cw][2*limbs]
+    const uint32_t *perm1, *perm2, *modulus;  // device u32[cw], u32[cw], u32[2*limbs]
+    uint32_t *scratch;        // device num_rows * cw * 2*limbs words
+    uint32_t num_rows, row_len, cw;
+    int limbs;                // u64 limbs per field element (1..6)
+    cudaStream_t stream;
+};
+cudaError_t launch_encode_f(const EncodeFArgs &a);
+
 // ---- multi-GPU: the roots exchange of a row-sharded commit (peer_roots.cu, merkle.cu) ----
 // One per zipgpu_peer_roots object, in device memory, written once when the peers are connected.  The kernel that
 // produces the roots of this GPU's row range stores every root straight into every peer's result buffer (P2P stores

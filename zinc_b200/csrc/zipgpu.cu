@@ -85,7 +85,8 @@ struct zipgpu_code {
     uint8_t *d_colw;
     // codewords longer than one SM's shared memory holds (cw > 16384): chunked encoder of raa_big.cu, raw permutations
     bool big = false;
-    uint32_t *d_perm1 = nullptr, *d_perm2 = nullptr;
+    uint32_t *d_perm1 = nullptr, *d_perm2 = nullptr;  // (also uploaded on first use by encode_f)
+    std::vector<uint32_t> h_perm1, h_perm2;           // host copy of the permutations
     // ZipLinearCode (zipgpu_sparse_code_create): either the ELL tables of the generic kernel or the dense 0/1 matrix
     // of the tensor-core kernel (sparse_encode.cu)
     bool sparse = false;
@@ -459,6 +460,8 @@ extern "C" int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t rep, i
     c->depth = is_pow2(cw) ? ilog2(cw) : -1;
     c->fused_levels = c->depth > 0 ? encode_fused_levels(in_limbs, out_limbs, (uint32_t)row_len, (uint32_t)cw) : 0;
     if (!merkle_supported(out_limbs * 2)) c->fused_levels = 0;
+    c->h_perm1.assign(perm1, perm1 + cw);
+    c->h_perm2.assign(perm2, perm2 + cw);
     c->d_tab1 = c->d_tab2 = nullptr;
     c->d_colw = nullptr;
     cudaError_t e;
@@ -1383,6 +1386,75 @@ extern "C" int zipgpu_encode_rows(zipgpu_code *code, size_t num_rows, const uint
     int rc = run_host_job(code, num_rows, job);
     int rc2 = zipgpu_ctx_sync(code->ctx);
     return rc ? rc : rc2;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// encode_f (code_raa.rs:133-138): the RAA code over field elements
+// ------------------------------------------------------------------------------------------------------
+extern "C" int zipgpu_encode_f(zipgpu_code *code, size_t num_rows, int limbs, const uint64_t *modulus, const uint64_t *rows,
+                               uint64_t *out) {
+    if (!code || !modulus || (num_rows && (!rows || !out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (code->sparse) return fail(ZIPGPU_ERR_UNSUPPORTED, "encode_f is implemented for the RAA code");
+    if (limbs < 1 || limbs > 6) return fail(ZIPGPU_ERR_UNSUPPORTED, "field elements of 1..6 u64 limbs");
+    if (num_rows > 0x7fffffffull) return fail(ZIPGPU_ERR_UNSUPPORTED, "too many rows");
+    bool nonzero = false;
+    for (int l = 0; l < limbs; l++) nonzero |= modulus[l] != 0;
+    if (!nonzero) return fail(ZIPGPU_ERR_INVALID, "modulus is zero");
+    // the parallel scan equals the reference's sequential accumulate because addition of residues < modulus is
+    // associative: insist on reduced inputs (the reference's RandomField values always are)
+    for (size_t i = 0; i < num_rows * code->row_len; i++) {
+        int cmp = 0;
+        for (int l = limbs - 1; l >= 0 && cmp == 0; l--)
+            cmp = rows[i * limbs + l] < modulus[l] ? -1 : rows[i * limbs + l] > modulus[l] ? 1 : 0;
+        if (cmp >= 0) return fail(ZIPGPU_ERR_INVALID, "encode_f: element " + std::to_string(i) + " is not reduced modulo the field modulus");
+    }
+    if (num_rows == 0) return ZIPGPU_OK;
+    zipgpu_ctx *ctx = code->ctx;
+    API_LOCK(ctx);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (!code->d_perm1) {  // first use: the gather form of the permutations, as uploaded
+        cudaError_t e;
+        if ((e = cudaMalloc(&code->d_perm1, code->cw * 4)) != cudaSuccess || (e = cudaMalloc(&code->d_perm2, code->cw * 4)) != cudaSuccess ||
+            (e = cudaMemcpy(code->d_perm1, code->h_perm1.data(), code->cw * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMemcpy(code->d_perm2, code->h_perm2.data(), code->cw * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+            cudaFree(code->d_perm1);
+            cudaFree(code->d_perm2);
+            code->d_perm1 = code->d_perm2 = nullptr;
+            return cuda_fail(e, "cudaMalloc/cudaMemcpy(permutations)");
+        }
+    }
+    DevGuard guard(ctx, s);
+    const size_t in_bytes = num_rows * code->row_len * limbs * 8, out_bytes = num_rows * code->cw * limbs * 8;
+    uint32_t *d_in = nullptr, *d_out = nullptr, *d_scr = nullptr, *d_mod = nullptr;
+    DEV_ALLOC(ctx, &d_in, in_bytes, s);
+    DEV_ALLOC(ctx, &d_out, out_bytes, s);
+    DEV_ALLOC(ctx, &d_scr, out_bytes, s);
+    DEV_ALLOC(ctx, &d_mod, 64, s);
+    CU(cudaMemcpyAsync(d_in, rows, in_bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_mod, modulus, (size_t)limbs * 8, cudaMemcpyHostToDevice, s));
+    EncodeFArgs a;
+    a.rows_in = d_in;
+    a.out = d_out;
+    a.perm1 = code->d_perm1;
+    a.perm2 = code->d_perm2;
+    a.modulus = d_mod;
+    a.scratch = d_scr;
+    a.num_rows = (uint32_t)num_rows;
+    a.row_len = (uint32_t)code->row_len;
+    a.cw = (uint32_t)code->cw;
+    a.limbs = limbs;
+    a.stream = s;
+    cudaError_t e = launch_encode_f(a);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_encode_f");
+    ctx->launches++;
+    CU(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    DEV_FREE(ctx, d_in, s);
+    DEV_FREE(ctx, d_out, s);
+    DEV_FREE(ctx, d_scr, s);
+    DEV_FREE(ctx, d_mod, s);
+    CU(cudaStreamSynchronize(s));
+    return ZIPGPU_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -351,6 +351,21 @@ class RaaCode:
         """code.rs:35-37: encode == encode_wide::<N, M>"""
         return self.encode_wide(row, self.zt.N, self.zt.M, ctx)
 
+    def encode_f(self, row, modulus: int, limbs: int, ctx: Context | None = None) -> np.ndarray:
+        """code_raa.rs:133-138: the same code over field elements, every += the field's addition.  `row`: the stored
+        residues of the RandomField<limbs> values ([row_len, limbs] uint64, python ints also accepted), all < modulus;
+        -> [cw, limbs] uint64.  (The verifier's re-encoding of the combined row, verify_z.rs:141-142.)"""
+        r = as_limbs(np.asarray(row, dtype=object) if not isinstance(row, np.ndarray) else row, limbs)
+        assert r.shape[0] == self._row_len, "Row length must match the code's row length"  # code_raa.rs:93-97
+        ctx = ctx or default_context()
+        if ctx.multi:
+            raise Error("encode_f runs on one GPU: pass a Context")
+        mod = as_limbs(np.array([modulus], dtype=object), limbs).reshape(-1)
+        out = np.empty((self.codeword_len(), limbs), dtype=np.uint64)
+        nat.check(nat.lib().zipgpu_encode_f(self.native(ctx, self.zt.N, self.zt.K), 1, limbs, nat.ptr(mod), nat.ptr(r),
+                                            nat.ptr(out)))
+        return out
+
 
 class SparseMatrixZ:
     """zip/code.rs:265-336: `n` rows of `d` (column, coefficient) cells over `m` columns; cells in row order."""
