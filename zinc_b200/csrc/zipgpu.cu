@@ -81,6 +81,7 @@ struct zipgpu_code {
     int in_limbs, out_limbs;
     int depth;  // -1 when cw is not a power of two (encode only)
     int fused_levels;  // Merkle levels the fused commit kernel produces (0: no fused variant for this shape)
+    void *d_tables = nullptr;   // one cached buffer holding the three tables below
     uint16_t *d_tab1, *d_tab2;  // pre-translated gather tables (raa_encode.cu)
     uint8_t *d_colw;
     // codewords longer than one SM's shared memory holds (cw > 16384): chunked encoder of raa_big.cu, raw permutations
@@ -480,26 +481,24 @@ extern "C" int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t rep, i
         return ZIPGPU_OK;
     }
     const size_t padded = encode_perm_padded_len((uint32_t)cw);
-    if ((e = cudaMalloc(&c->d_tab1, padded * 2)) != cudaSuccess || (e = cudaMalloc(&c->d_tab2, padded * 2)) != cudaSuccess ||
-        (e = cudaMalloc(&c->d_colw, padded)) != cudaSuccess) {
-        cudaFree(c->d_tab1);
-        cudaFree(c->d_tab2);
+    // the kernel consumes pre-translated, lane-major tables (raa_encode.cu), not the raw permutations.  One buffer from
+    // the context's cache (a prover builds a new code per proof, zinc/prover.rs:313: no cudaMalloc in steady state), one copy.
+    std::vector<uint8_t> host(padded * 5, 0);
+    uint16_t *t1 = reinterpret_cast<uint16_t *>(host.data()), *t2 = reinterpret_cast<uint16_t *>(host.data() + padded * 2);
+    uint8_t *cl = host.data() + padded * 4;
+    build_encode_tables(perm1, perm2, (uint32_t)row_len, (uint32_t)cw, in_limbs, out_limbs, t1, t2, cl);
+    void *d_tables = nullptr;
+    if ((e = dev_alloc(ctx, &d_tables, padded * 5, ctx->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_tables, host.data(), padded * 5, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+        if (d_tables) dev_free(ctx, d_tables, ctx->stream);
         delete c;
-        return cuda_fail(e, "cudaMalloc(tables)");
+        return cuda_fail(e, "code tables");
     }
-    // the kernel consumes pre-translated, lane-major tables (raa_encode.cu), not the raw permutations
-    std::vector<uint16_t> t1(padded, 0), t2(padded, 0);
-    std::vector<uint8_t> cl(padded, 0);
-    build_encode_tables(perm1, perm2, (uint32_t)row_len, (uint32_t)cw, in_limbs, out_limbs, t1.data(), t2.data(), cl.data());
-    if ((e = cudaMemcpy(c->d_tab1, t1.data(), padded * 2, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(c->d_tab2, t2.data(), padded * 2, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(c->d_colw, cl.data(), padded, cudaMemcpyHostToDevice)) != cudaSuccess) {
-        cudaFree(c->d_tab1);
-        cudaFree(c->d_tab2);
-        cudaFree(c->d_colw);
-        delete c;
-        return cuda_fail(e, "cudaMemcpy(tables)");
-    }
+    c->d_tables = d_tables;
+    c->d_tab1 = reinterpret_cast<uint16_t *>(d_tables);
+    c->d_tab2 = reinterpret_cast<uint16_t *>(static_cast<uint8_t *>(d_tables) + padded * 2);
+    c->d_colw = static_cast<uint8_t *>(d_tables) + padded * 4;
     *out = c;
     return ZIPGPU_OK;
 }
@@ -602,9 +601,7 @@ extern "C" void zipgpu_code_destroy(zipgpu_code *c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(c->d_tab1);
-    cudaFree(c->d_tab2);
-    cudaFree(c->d_colw);
+    if (c->d_tables) dev_free(c->ctx, c->d_tables, c->ctx->stream);  // back to the context's cache
     cudaFree(c->d_perm1);
     cudaFree(c->d_perm2);
     cudaFree(c->d_sp_dense);
