@@ -33,11 +33,14 @@ use crate::{
     zip::{code::LinearCode, code_raa::RaaCode, Error},
 };
 
-fn ctx() -> &'static sys::Ctx {
-    static CTX: OnceLock<sys::Ctx> = OnceLock::new();
+/// The process-wide multi-GPU context: `ZIPGPU_DEVICES=0,1,2,3` picks the devices, default = all visible B200s.
+/// One device is simply the n = 1 case; rows (commit) and polynomials (batch_commit) are sharded inside the library.
+fn ctx() -> &'static sys::MultiCtx {
+    static CTX: OnceLock<sys::MultiCtx> = OnceLock::new();
     CTX.get_or_init(|| {
-        let dev = std::env::var("ZIPGPU_DEVICE").ok().and_then(|s| s.parse().ok()).unwrap_or(0);
-        sys::Ctx::new(dev).expect("zipgpu: no B200 visible (the gpu feature has no CPU fallback)")
+        let devs: Vec<i32> = std::env::var("ZIPGPU_DEVICES").ok()
+            .map(|s| s.split(',').filter_map(|x| x.trim().parse().ok()).collect()).unwrap_or_default();
+        sys::MultiCtx::new(&devs).expect("zipgpu: no B200 visible (the gpu feature has no CPU fallback)")
     })
 }
 
@@ -67,13 +70,35 @@ fn hashes(bytes: &[u8]) -> Vec<blake3::Hash> {
 }
 
 impl<ZT: ZipTypes> MultilinearZip<ZT, RaaCode<ZT>> {
-    fn gpu_code(pp: &MultilinearZipParams<ZT, RaaCode<ZT>>) -> sys::Code {
-        // a production version caches this per pp (the tables depend only on the seeds and cw)
+    fn gpu_code(pp: &MultilinearZipParams<ZT, RaaCode<ZT>>) -> sys::MultiCode<'static> {
+        // a production version caches this per pp (the tables depend only on the seeds and cw); the prover builds one
+        // code per proof anyway (zinc/prover.rs:313), and zipgpu_mgpu_code_create takes its buffers from a cache
         let lc = &pp.linear_code;
         let (p1, p2) = lc.permutations();
-        sys::Code::new(ctx(), lc.row_len(), lc.repetition_factor(), <ZT::N as Integer>::W::num_words(),
-                       <ZT::K as Integer>::W::num_words(), &p1, &p2)
+        sys::MultiCode::new(ctx(), lc.row_len(), lc.repetition_factor(), <ZT::N as Integer>::W::num_words(),
+                            <ZT::K as Integer>::W::num_words(), &p1, &p2)
             .unwrap_or_else(|e| panic!("{e}"))   // ZIPGPU_ERR_WIDTH carries code_raa.rs:68-72's message
+    }
+
+    /// the reference's checks of commit.rs:54-63, host-side, BEFORE the FFI call, same Err / same panic text
+    fn check_poly<F: Field>(pp: &MultilinearZipParams<ZT, RaaCode<ZT>>, poly: &DenseMultilinearExtension<ZT::N>)
+        -> Result<(), Error> {
+        validate_input("commit", pp.num_vars, [poly], None::<&[F]>)?;          // Err(InvalidPcsParam) as upstream
+        let expected = pp.num_rows * pp.linear_code.row_len();
+        assert_eq!(poly.evaluations.len(), expected,                             // commit.rs:56-63
+            "Polynomial has an incorrect number of evaluations ({}) for the expected matrix size ({})",
+            poly.evaluations.len(), expected);
+        Ok(())
+    }
+
+    fn assemble(pp: &MultilinearZipParams<ZT, RaaCode<ZT>>, depth: usize, rows: &[u64], layers: &[u8], roots: &[u8])
+        -> (MultilinearZipData<ZT::K>, MultilinearZipCommitment) {
+        let per_row = (2usize << depth) - 2;
+        let roots = hashes(roots);
+        let trees: Vec<MerkleTree> = layers.chunks_exact(per_row * 32).zip(&roots)
+            .map(|(l, r)| MerkleTree { root: *r, depth, layers: hashes(l) }).collect();
+        assert_eq!(trees.len(), pp.num_rows);                                    // commit.rs:76
+        (MultilinearZipData::new(from_limbs(rows), trees), MultilinearZipCommitment { roots })
     }
 
     /// commit.rs:50-87
@@ -81,32 +106,30 @@ impl<ZT: ZipTypes> MultilinearZip<ZT, RaaCode<ZT>> {
         pp: &MultilinearZipParams<ZT, RaaCode<ZT>>,
         poly: &DenseMultilinearExtension<ZT::N>,
     ) -> Result<(MultilinearZipData<ZT::K>, MultilinearZipCommitment), Error> {
-        validate_input("commit", pp.num_vars, [poly], None::<&[F]>)?;          // Err(InvalidPcsParam) as upstream
-        let row_len = pp.linear_code.row_len();
-        let expected = pp.num_rows * row_len;
-        assert_eq!(poly.evaluations.len(), expected,                             // commit.rs:56-63, host-side
-            "Polynomial has an incorrect number of evaluations ({}) for the expected matrix size ({})",
-            poly.evaluations.len(), expected);
+        Self::check_poly::<F>(pp, poly)?;
         let cw = pp.linear_code.codeword_len();
         assert!(cw.is_power_of_two());                                           // utils.rs:75 via commit.rs:73
         let depth = cw.ilog2() as usize;                                         // commit.rs:67
         let k = <ZT::K as Integer>::W::num_words();
-
         let code = Self::gpu_code(pp);
         let evals = limbs(&poly.evaluations);
         let mut rows = vec![0u64; pp.num_rows * cw * k];
-        let per_row = (2usize << depth) - 2;
-        let mut layers = vec![0u8; pp.num_rows * per_row * 32];
+        let mut layers = vec![0u8; pp.num_rows * ((2usize << depth) - 2) * 32];
         let mut roots = vec![0u8; pp.num_rows * 32];
-        sys::check(unsafe { sys::zipgpu_commit(code.0, pp.num_rows, evals.as_ptr(), rows.as_mut_ptr(),
-                                               layers.as_mut_ptr(), roots.as_mut_ptr()) })
+        sys::check(unsafe { sys::zipgpu_mgpu_commit(code.0, pp.num_rows, evals.as_ptr(), rows.as_mut_ptr(),
+                                                    layers.as_mut_ptr(), roots.as_mut_ptr()) })
             .map_err(Error::InvalidPcsParam)?;
+        Ok(Self::assemble(pp, depth, &rows, &layers, &roots))
+    }
 
-        let roots = hashes(&roots);
-        let trees: Vec<MerkleTree> = layers.chunks_exact(per_row * 32).zip(&roots)
-            .map(|(l, r)| MerkleTree { root: *r, depth, layers: hashes(l) }).collect();
-        assert_eq!(trees.len(), pp.num_rows);                                    // commit.rs:76
-        Ok((MultilinearZipData::new(from_limbs(&rows), trees), MultilinearZipCommitment { roots }))
+    /// commit.rs:104-119: encode only, empty trees and roots
+    pub fn commit_no_merkle_gpu<F: Field>(
+        pp: &MultilinearZipParams<ZT, RaaCode<ZT>>,
+        poly: &DenseMultilinearExtension<ZT::N>,
+    ) -> Result<(MultilinearZipData<ZT::K>, MultilinearZipCommitment), Error> {
+        Self::check_poly::<F>(pp, poly)?;
+        let rows = Self::encode_rows_gpu(pp, pp.linear_code.codeword_len(), pp.linear_code.row_len(), &poly.evaluations);
+        Ok((MultilinearZipData::new(rows, vec![]), MultilinearZipCommitment { roots: vec![] }))
     }
 
     /// commit.rs:158-183
@@ -116,17 +139,52 @@ impl<ZT: ZipTypes> MultilinearZip<ZT, RaaCode<ZT>> {
         let code = Self::gpu_code(pp);
         let flat = limbs(evals);
         let mut rows = vec![0u64; pp.num_rows * codeword_len * k];
-        sys::check(unsafe { sys::zipgpu_encode_rows(code.0, pp.num_rows, flat.as_ptr(), rows.as_mut_ptr()) })
+        sys::check(unsafe { sys::zipgpu_mgpu_encode_rows(code.0, pp.num_rows, flat.as_ptr(), rows.as_mut_ptr()) })
             .unwrap_or_else(|e| panic!("{e}"));
         from_limbs(&rows)
     }
 
-    /// commit.rs:134-142: all polynomials in ONE pipelined submission (H2D of poly p+1 overlaps the kernels of p)
+    /// commit.rs:134-142: all polynomials in ONE submission -- polynomial p goes to device p mod n, and on each device
+    /// the batch runs as one matrix (H2D of poly p+1 overlaps the kernels of p)
     pub fn batch_commit_gpu<F: Field>(
         pp: &MultilinearZipParams<ZT, RaaCode<ZT>>,
         polys: &[DenseMultilinearExtension<ZT::N>],
     ) -> Result<Vec<(MultilinearZipData<ZT::K>, MultilinearZipCommitment)>, Error> {
-        // same validation per polynomial, then zipgpu_batch_commit with arrays of pointers; omitted for brevity:
-        polys.iter().map(|p| Self::commit_gpu::<F>(pp, p)).collect()
+        for poly in polys { Self::check_poly::<F>(pp, poly)?; }
+        if polys.is_empty() { return Ok(vec![]); }
+        let cw = pp.linear_code.codeword_len();
+        assert!(cw.is_power_of_two());
+        let depth = cw.ilog2() as usize;
+        let k = <ZT::K as Integer>::W::num_words();
+        let code = Self::gpu_code(pp);
+        let evals: Vec<Vec<u64>> = polys.iter().map(|p| limbs(&p.evaluations)).collect();
+        let mut rows: Vec<Vec<u64>> = polys.iter().map(|_| vec![0u64; pp.num_rows * cw * k]).collect();
+        let mut layers: Vec<Vec<u8>> = polys.iter().map(|_| vec![0u8; pp.num_rows * ((2usize << depth) - 2) * 32]).collect();
+        let mut roots: Vec<Vec<u8>> = polys.iter().map(|_| vec![0u8; pp.num_rows * 32]).collect();
+        let ev_ptrs: Vec<*const u64> = evals.iter().map(|v| v.as_ptr()).collect();
+        let row_ptrs: Vec<*mut u64> = rows.iter_mut().map(|v| v.as_mut_ptr()).collect();
+        let lay_ptrs: Vec<*mut u8> = layers.iter_mut().map(|v| v.as_mut_ptr()).collect();
+        let root_ptrs: Vec<*mut u8> = roots.iter_mut().map(|v| v.as_mut_ptr()).collect();
+        sys::check(unsafe { sys::zipgpu_mgpu_batch_commit(code.0, polys.len(), pp.num_rows, ev_ptrs.as_ptr(),
+                                                          row_ptrs.as_ptr(), lay_ptrs.as_ptr(), root_ptrs.as_ptr()) })
+            .map_err(Error::InvalidPcsParam)?;
+        Ok((0..polys.len()).map(|p| Self::assemble(pp, depth, &rows[p], &layers[p], &roots[p])).collect())
+    }
+
+    /// For provers that open right away (zinc/prover.rs:315-320): the rows and layers stay on the GPUs that produced them
+    /// (sharded by row range), only the roots come back; `open` then pulls the 1000 opened columns with
+    /// zipgpu_mgpu_data_open_columns_wire and the proximity row with zipgpu_mgpu_data_combine_rows.
+    pub fn commit_resident_gpu<F: Field>(
+        pp: &MultilinearZipParams<ZT, RaaCode<ZT>>,
+        poly: &DenseMultilinearExtension<ZT::N>,
+    ) -> Result<(sys::MultiData<'static>, MultilinearZipCommitment), Error> {
+        Self::check_poly::<F>(pp, poly)?;
+        let code = Self::gpu_code(pp);
+        let evals = limbs(&poly.evaluations);
+        let mut roots = vec![0u8; pp.num_rows * 32];
+        let mut h = core::ptr::null_mut();
+        sys::check(unsafe { sys::zipgpu_mgpu_commit_resident(code.0, pp.num_rows, evals.as_ptr(), roots.as_mut_ptr(), &mut h) })
+            .map_err(Error::InvalidPcsParam)?;
+        Ok((sys::MultiData(h, core::marker::PhantomData), MultilinearZipCommitment { roots: hashes(&roots) }))
     }
 }
