@@ -3,10 +3,10 @@
 // The reference's commitment is the list of per-row roots (commit.rs:71-81), so a commit sharded by row range has ONE
 // exchange step: every GPU needs every other GPU's 32-byte roots.  It is fused into the kernel that produces them:
 //   * fan_store_root: the thread that holds a finished root stores it into every rank's result buffer (P2P stores
-//     through NVLink / NVSwitch; the own buffer is one of them);
-//   * fan_finish: every CTA fences its stores at system scope and counts itself done; the LAST CTA of the launch
-//     publishes this rank's step counter into every peer's flag words (st.release.sys) and waits until every peer's
-//     counter in the own flag words has reached the step (ld.acquire.sys).  When the kernel completes, the own result
+//     through NVLink / NVSwitch; the own buffer is one of them) and fences at system scope;
+//   * fan_finish: every CTA counts itself done; the LAST CTA of the launch publishes this rank's step counter into
+//     every peer's flag words (st.release.sys) and waits until every peer's counter in the own flag words has reached
+//     the step (ld.acquire.sys).  When the kernel completes, the own result
 //     buffer holds all roots.  The wait is bounded: a peer that does not show up within timeout_ns is reported through
 //     the mapped status word and the kernel ends -- the context stays usable and the host call returns an error.
 #pragma once
@@ -31,12 +31,6 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-__device__ __forceinline__ void fan_store_root(const RootsFanout *fan, unsigned long long step, uint32_t global_row,
-                                               const uint32_t (&d)[8]) {
-    const int par = (int)(step & 1ull);
-    for (int p = 0; p < fan->world; p++) st_global_v8(fan->bufs[par][p] + (size_t)global_row * 32, d);
-}
-
 // publish + wait, by the threads tid < world of ONE CTA (called by the last CTA of the launch, or by the stand-alone
 // exchange kernel).  Preceded by a system-scope fence of the calling thread.
 __device__ __forceinline__ void fan_handshake(const RootsFanout *fan, unsigned long long step, uint32_t tid) {
@@ -59,11 +53,22 @@ __device__ __forceinline__ void fan_handshake(const RootsFanout *fan, unsigned l
     }
 }
 
-// End of a kernel that called fan_store_root.  EVERY thread of EVERY CTA must reach it (it contains barriers).
+// The thread that holds a finished root stores it into every rank's result buffer (P2P stores through NVLink; the own
+// buffer is one of them) and fences them at system scope right away, while the rest of the grid is still hashing.
+__device__ __forceinline__ void fan_store_root(const RootsFanout *fan, unsigned long long step, uint32_t global_row,
+                                               const uint32_t (&d)[8]) {
+    const int par = (int)(step & 1ull);
+    for (int p = 0; p < fan->world; p++) st_global_v8(fan->bufs[par][p] + (size_t)global_row * 32, d);
+    __threadfence_system();
+}
+
+// End of a kernel whose threads called fan_store_root.  EVERY thread of EVERY CTA must reach it (it contains barriers).
+// Every CTA counts itself done after its storing threads' system fences; the LAST one runs the handshake.  (Measured
+// against the alternative -- only local stores during the launch, the last CTA copies all roots to the peers, one system
+// fence -- on 8 GPUs at 512 rows each: 0.308 vs 0.318 ms per sharded commit; the spread-out stores overlap the hashing.)
 __device__ __forceinline__ void fan_finish(const RootsFanout *fan, unsigned long long step) {
     __shared__ unsigned int s_last;
-    __threadfence_system();  // this thread's peer stores are visible system-wide before the CTA counts itself done
-    __syncthreads();
+    __syncthreads();  // after the storing threads' fences
     if (threadIdx.x == 0) {
         __threadfence_system();  // cumulative over what the barrier made visible to this thread
         const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
