@@ -14,11 +14,17 @@
 // every pair run as if alone (75 us per row, 62 of them hashing) and starved the other -- minus the 13 us per row the
 // favoured CTA spent not hashing: here the hash warps never leave the alu pipe.
 //
-// (Tried and measured slower, round 2: letting the ENC group also reduce the level-log2(E/U) nodes of a unit to its root
-// through a shared-memory digest buffer, which would make a commit ONE launch.  A compression is a ~200-step dependent
-// chain; in a few ENC warps competing with 16 busy hash warps for the alu pipe it takes ~6 us per tree level, ~55 us
-// for the 9 levels of a row -- the ENC group became the critical path: nv = 24 went from 1.94 to 2.19 ms.  The narrow
-// tops stay with the batched passes of merkle.cu, which run them over all rows at once.)
+// Tree tops.  A hash thread ends a unit with one node of level log2(E / U) in `layers`.  Every kTopBatch units the HASH
+// group stops hashing rows and finishes the subtrees of those units together: level by level, node i of the batch to
+// thread i mod T (children re-read from `layers` -- the group's own stores, L2-resident -- parent written back), one
+// group barrier per level.  Batching is what makes this cheap: the three widest levels keep every lane busy (8 units x
+// 256 / 128 / 64 nodes over 512 threads), and the latency of the six narrow ones is paid once per batch, not per row.
+// With U = 1 the last level is the row's root: the whole commit is ONE launch, the root goes to `roots` and, in a
+// row-sharded multi-GPU commit, into every peer's buffer (RootsFanout; the last CTA runs the publish/wait handshake).
+// With U = 2 the two half-row roots of a row (possibly produced by different CTAs) are joined by one tiny pass of
+// merkle.cu.  (Tried first and measured slower: the same tops on the ENC warps, one unit at a time, through a
+// shared-memory digest buffer -- a compression is a ~200-step dependent chain, which in a few ENC warps competing with
+// 16 busy hash warps takes ~6 us per level; the ENC group became the critical path and nv = 24 went from 1.94 to 2.19 ms.)
 //
 // Work units.  U = 1: a CTA claims whole rows dynamically and hash thread t continues with the E entries ENC thread t
 // produced (one level-log2(E) node per thread and row).  That is right for thousands of rows, but a row is ~65 us of
@@ -30,19 +36,16 @@
 // units cover.  The fused part then stops one or two tree levels lower (level log2(E / U)).
 #include <cstdlib>
 
+#include "peer_sync.cuh"
 #include "raa_common.cuh"
 
 namespace zipgpu {
 
-constexpr int kBarEnc = 1;  // named barrier of the ENC group
-// hand-over of the plane sets: 0 = named barriers (bar.arrive / bar.sync), 1 = mbarriers, every thread waits for itself,
-// 2 = mbarriers, one ENC warp polls for its group (the hash threads always wait for themselves)
-constexpr uint32_t kHandNamed = 0, kHandMbarAll = 1, kHandMbarOne = 2;
-constexpr int kBarFull0 = 2, kBarEmpty0 = 4;  // + buf (kHandNamed)
-template <int ALL>
-__device__ __forceinline__ void ws_sync(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(ALL) : "memory"); }
-template <int ALL>
-__device__ __forceinline__ void ws_arrive(uint32_t id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(ALL) : "memory"); }
+constexpr int kBarEnc = 1, kBarHash = 2;  // named barriers of the ENC group and of the HASH group
+#ifndef ZIPGPU_TOP_BATCH
+#define ZIPGPU_TOP_BATCH 32
+#endif
+constexpr int kTopBatch = ZIPGPU_TOP_BATCH;  // units whose subtree tops the HASH group finishes together
 
 // E entries per ENC thread, kWsEnc threads per group: (16, 512) = cw 8192, (8, 512) = cw 4096, (8, 256) = cw 2048,
 // (4, 256) = cw 1024, (4, 128) = cw 512 -- the (E, T) of the plain encoder for those shapes, so the same pre-translated
@@ -52,14 +55,16 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
     commit_ws_kernel(const uint32_t *__restrict__ evals, uint32_t *__restrict__ rows_out,
                      const uint16_t *__restrict__ tab1, const uint16_t *__restrict__ tab2,
                      const uint8_t *__restrict__ colw, uint32_t num_rows, uint8_t *__restrict__ layers, uint32_t one,
-                     uint32_t *__restrict__ row_counter, uint32_t hand) {
-    constexpr int IN32 = 2, W = 3, OUT32 = 8, kWsAll = 2 * kWsEnc;
+                     uint32_t *__restrict__ row_counter, uint32_t do_tops, uint8_t *__restrict__ roots,
+                     const RootsFanout *__restrict__ fan, unsigned long long fan_step, uint32_t fan_row_begin) {
+    constexpr int IN32 = 2, W = 3, OUT32 = 8;
     constexpr uint32_t T = kWsEnc, P = T * E, cw = P, in_words = (P / 2) * IN32;
     constexpr int EH = E / U;                   // entries per hash thread and unit
     static_assert(EH >= 2 && EH * U == E, "units must divide the entries per thread");
     using T16 = Tab16<E>;
     using T8 = Tab8<E>;
     using EncBar = NamedBarrier<kBarEnc, kWsEnc>;
+    using HashBar = NamedBarrier<kBarHash, kWsEnc>;
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *planes = smem;                    // [2][W][P]
     uint32_t *aux = smem + 2 * W * P;           // scan scratch of the ENC group
@@ -67,6 +72,7 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
     __shared__ volatile uint32_t s_row[2];      // row parked in each plane set (0xffffffff: no more rows)
     __shared__ volatile uint32_t s_next;
     __shared__ unsigned long long s_full[2], s_empty[2];  // mbarriers: plane set parked / plane set free again
+    __shared__ uint32_t s_pend_row[kTopBatch + U], s_pend_uu[kTopBatch + U];  // units whose tops are still to be built
     const uint32_t tid = threadIdx.x;
     const uint32_t t = tid & (kWsEnc - 1);      // index within the group
     // U > 1: this CTA's static share of the num_rows * U units
@@ -96,13 +102,9 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
         for (; row < row_end; it++) {
             const uint32_t buf = it & 1u;
             uint32_t *pl = planes + buf * (W * P);
-            if (it >= 2) {  // the hash warps are done with this plane set
-                if (hand == kHandNamed) ws_sync<kWsAll>(kBarEmpty0 + buf);
-                else if (hand == kHandMbarAll) mbar_wait(&s_empty[buf], ((it >> 1) & 1u) ^ 1u);
-                else {
-                    if (t < 32) mbar_wait(&s_empty[buf], ((it >> 1) & 1u) ^ 1u);
-                    EncBar::sync();
-                }
+            if (it >= 2) {  // the hash warps are done with this plane set: one warp polls, the others sleep on the barrier
+                if (t < 32) mbar_wait(&s_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                EncBar::sync();
             }
             uint32_t early = U == 1 ? row + gridDim.x : row + 1;
             if (U == 1 && t == 0 && row_counter) early = gridDim.x + atomicAdd(row_counter, 1u) + 1u;
@@ -152,9 +154,7 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
                 for (int w = 0; w < W; w++) pl[w * P + s2] = v[k][w];
             }
             if (t == 0) s_row[buf] = row;
-            // hand the row to the hash warps (every thread's arrive releases its own writes)
-            if (hand == kHandNamed) ws_arrive<kWsAll>(kBarFull0 + buf);
-            else mbar_arrive(&s_full[buf]);
+            mbar_arrive(&s_full[buf]);  // hand the row to the hash warps (every thread's arrive releases its own writes)
             __syncwarp();
             T16::load(tab1, t, T, c1);   // for the next row; in flight during the write-out
             // write-out of this warp's 32E positions: 32-byte records into the warp's tile, one bulk store per KiB.
@@ -188,23 +188,49 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
         }
         {   // no more rows: tell the hash warps through the next plane set
             const uint32_t buf = it & 1u;
-            if (it >= 2) {
-                if (hand == kHandNamed) ws_sync<kWsAll>(kBarEmpty0 + buf);
-                else mbar_wait(&s_empty[buf], ((it >> 1) & 1u) ^ 1u);
-            }
+            if (it >= 2) mbar_wait(&s_empty[buf], ((it >> 1) & 1u) ^ 1u);
             if (t == 0) s_row[buf] = 0xffffffffu;
-            if (hand == kHandNamed) ws_arrive<kWsAll>(kBarFull0 + buf);
-            else mbar_arrive(&s_full[buf]);
+            mbar_arrive(&s_full[buf]);
         }
         if (lane == 0) bulk_wait_all();
     } else {
         // ============================== HASH ==============================
         constexpr int H = EH >= 16 ? 4 : EH >= 8 ? 3 : EH >= 4 ? 2 : 1;
         static_assert((1 << H) == EH, "entries per hash thread: a power of two");
+        constexpr int LT = kWsEnc == 512 ? 9 : kWsEnc == 256 ? 8 : 7;  // log2(T): levels between a unit's level-H nodes and its root
+        static_assert((1 << LT) == kWsEnc, "T is a power of two");
+        const size_t lay_stride = (2 * (size_t)cw - 2) * 32;
+        uint32_t npend = 0;
+        // the subtree tops of the `n` pending units, level by level over the whole batch
+        auto tree_tops = [&](uint32_t n) {
+            HashBar::sync();  // the batch's level-H nodes are in `layers` (the group's own stores)
+#pragma unroll 1
+            for (uint32_t sl = 1; sl <= (uint32_t)LT; sl++) {
+                const uint32_t nlog = LT - sl, level = H + sl;  // 2^nlog nodes per unit at this level
+                const size_t off_child = 2 * (size_t)cw - ((2 * (size_t)cw) >> (level - 1));
+                const size_t off = 2 * (size_t)cw - ((2 * (size_t)cw) >> level);
+#pragma unroll 1
+                for (uint32_t i = t; i < (n << nlog); i += T) {
+                    const uint32_t j = i >> nlog, q = i & ((1u << nlog) - 1u);
+                    const uint32_t r = s_pend_row[j], node = ((s_pend_uu[j] * T) >> sl) + q;
+                    uint8_t *lr = layers + (size_t)r * lay_stride;
+                    b3::Digest lft, rgt;
+                    ld_global_v8(lr + (off_child + 2 * (size_t)node) * 32, lft.w);
+                    ld_global_v8(lr + (off_child + 2 * (size_t)node + 1) * 32, rgt.w);
+                    const b3::Digest o = b3::hash_node_call(lft, rgt, one);
+                    if (U == 1 && sl == (uint32_t)LT) {  // the row's root
+                        st_global_v8(roots + (size_t)r * 32, o.w);
+                        if (fan) fan_store_root(fan, fan_step, fan_row_begin + r, o.w);
+                    } else {
+                        st_global_v8(lr + (off + node) * 32, o.w);
+                    }
+                }
+                HashBar::sync();
+            }
+        };
         for (uint32_t it = 0;; it++) {
             const uint32_t buf = it & 1u;
-            if (hand == kHandNamed) ws_sync<kWsAll>(kBarFull0 + buf);
-            else mbar_wait(&s_full[buf], (it >> 1) & 1u);
+            mbar_wait(&s_full[buf], (it >> 1) & 1u);
             const uint32_t row = s_row[buf];
             if (row == 0xffffffffu) break;
             const uint32_t *pl = planes + buf * (W * P);
@@ -255,18 +281,29 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
                         }
                     }
                 }
+                if (do_tops) {
+                    if (t == 0) {
+                        s_pend_row[npend] = row;
+                        s_pend_uu[npend] = uu;
+                    }
+                    npend++;
+                }
             }
-            // the plane set may be overwritten once all hash threads have said so
-            if (hand == kHandNamed) ws_arrive<kWsAll>(kBarEmpty0 + buf);
-            else mbar_arrive(&s_empty[buf]);
+            mbar_arrive(&s_empty[buf]);  // the plane set may be overwritten once all hash threads have said so
+            if (npend >= (uint32_t)kTopBatch) {
+                tree_tops(npend);
+                npend = 0;
+            }
         }
+        if (npend) tree_tops(npend);
     }
+    if (U == 1 && do_tops && fan) fan_finish(fan, fan_step);  // both groups, every CTA: the roots exchange of a sharded commit
 }
 
 namespace {
 
 template <int E, int TENC, int U>
-cudaError_t launch_ws_u(const EncodeArgs &a, uint32_t grid) {
+cudaError_t launch_ws_u(const EncodeArgs &a, uint32_t grid, bool tops) {
     const size_t ws_smem = (2 * 3 * (size_t)(E * TENC) + 64 * 3 + (TENC / 32) * 256) * sizeof(uint32_t);
     auto kern = commit_ws_kernel<E, TENC, U>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem);
@@ -283,9 +320,11 @@ cudaError_t launch_ws_u(const EncodeArgs &a, uint32_t grid) {
         const uint32_t units = a.num_rows * U;
         if (grid > units) grid = units;
     }
-    static const uint32_t hand = getenv("ZIPGPU_WS_HAND") ? (uint32_t)atoi(getenv("ZIPGPU_WS_HAND")) : kHandMbarOne;
+    const bool fan = U == 1 && tops && a.fan != nullptr;
     kern<<<grid, 2 * TENC, ws_smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows, a.fuse_layers, 1u,
-                                                row_counter, hand);
+                                                row_counter, tops ? 1u : 0u, a.roots, fan ? a.fan : nullptr, a.fan_step,
+                                                a.fan_row_begin);
+    if (fan && a.fan_fused) *a.fan_fused = true;
     return cudaGetLastError();
 }
 
@@ -300,11 +339,19 @@ cudaError_t launch_ws(const EncodeArgs &a, int *fused_levels) {
     int U = 1;
     if (TENC == 512 && a.num_rows >= 3 * grid && a.num_rows < 6 * grid) U = 2;
     if (const char *env = getenv("ZIPGPU_WS_UNITS")) U = atoi(env) >= 2 ? 2 : 1;
-    int h = 0;
+    // Tree tops inside the launch (then it builds every tree up to the roots of its work units: level depth, or depth - 1
+    // with half-row units) while a CTA gets at most ~8 rows: there the two extra launches of the batched passes cost more
+    // than they save (cw = 4096, 1024 rows: 0.284 -> 0.266 ms; cw = 2048, 1024 rows: 0.156 -> 0.152).  For bigger jobs the
+    // separate passes win -- they run the latency-bound levels at full occupancy (cw = 8192, 4096 rows: 1.921 vs 1.972 ms)
+    // -- and the launch stops at level log2(E / U).  ZIPGPU_WS_TOPS=0/1 forces.
+    bool tops = a.num_rows <= ((E == 8 && TENC == 512) ? 16u : 8u) * grid;  // (cw = 4096 still gains at 14 rows per CTA)
+    if (const char *env = getenv("ZIPGPU_WS_TOPS")) tops = atoi(env) != 0;
+    int depth = 0, h = 0;
+    while ((1u << depth) < (uint32_t)(E * TENC)) depth++;
     while ((1 << h) < E / U) h++;
-    if (fused_levels) *fused_levels = h;
-    if (U == 2) return launch_ws_u<E, TENC, 2>(a, grid);
-    return launch_ws_u<E, TENC, 1>(a, grid);
+    if (fused_levels) *fused_levels = tops ? depth - (U == 2 ? 1 : 0) : h;
+    if (U == 2) return launch_ws_u<E, TENC, 2>(a, grid, tops);
+    return launch_ws_u<E, TENC, 1>(a, grid, tops);
 }
 
 }  // namespace
