@@ -337,17 +337,14 @@ def test_warp_specialised_commit_kernel(row_len, num_rows, oracle, ctx, monkeypa
         assert np.array_equal(g_lay, layers), knob
 
 
-@pytest.mark.parametrize("tops", [0, 1])
 @pytest.mark.parametrize("units", [1, 2])
-@pytest.mark.parametrize("row_len,num_rows", [(4096, 37), (4096, 391), (4096, 1500), (2048, 523), (1024, 97), (1024, 1500),
-                                              (512, 611), (256, 59), (256, 1777), (256, 9001)])
-def test_warp_specialised_commit_kernel_sub_row_units(row_len, num_rows, units, tops, oracle, ctx, monkeypatch):
+@pytest.mark.parametrize("row_len,num_rows", [(4096, 37), (4096, 391), (2048, 523), (1024, 97), (1024, 1500), (512, 611),
+                                              (256, 59), (256, 1777)])
+def test_warp_specialised_commit_kernel_sub_row_units(row_len, num_rows, units, oracle, ctx, monkeypatch):
     """the sub-row work units of the warp-specialised commit kernel (a row hashed as 2 units, the units -- not
     the rows -- split statically and evenly over the CTAs; rows shared by two CTAs are encoded by both and each writes
     its part of the codeword): every unit count forced at row counts where CTAs get less than one, exactly one and
-    several units, with shares that start and end in the middle of a row; and both forms of the tree tops -- inside the
-    launch (the HASH group finishes the subtrees of up to 32 units together, several batches per CTA at the larger row
-    counts) and left to the batched passes"""
+    several units, with shares that start and end in the middle of a row"""
     from zinc_b200 import RaaCode, ZipTypes
 
     cw = 2 * row_len
@@ -358,7 +355,6 @@ def test_warp_specialised_commit_kernel_sub_row_units(row_len, num_rows, units, 
     assert rc == 0
     monkeypatch.setenv("ZIPGPU_FUSE_MIN_ROWS", "1")
     monkeypatch.setenv("ZIPGPU_WS_UNITS", str(units))
-    monkeypatch.setenv("ZIPGPU_WS_TOPS", str(tops))
     g_rows, g_lay, g_roots = _commit_device(ctx, code, num_rows, cw, evals)
     assert np.array_equal(g_roots, roots)
     assert np.array_equal(g_rows, rows)

@@ -14,17 +14,15 @@
 // every pair run as if alone (75 us per row, 62 of them hashing) and starved the other -- minus the 13 us per row the
 // favoured CTA spent not hashing: here the hash warps never leave the alu pipe.
 //
-// Tree tops.  A hash thread ends a unit with one node of level log2(E / U) in `layers`.  Every kTopBatch units the HASH
-// group stops hashing rows and finishes the subtrees of those units together: level by level, node i of the batch to
-// thread i mod T (children re-read from `layers` -- the group's own stores, L2-resident -- parent written back), one
-// group barrier per level.  Batching is what makes this cheap: the three widest levels keep every lane busy (8 units x
-// 256 / 128 / 64 nodes over 512 threads), and the latency of the six narrow ones is paid once per batch, not per row.
-// With U = 1 the last level is the row's root: the whole commit is ONE launch, the root goes to `roots` and, in a
-// row-sharded multi-GPU commit, into every peer's buffer (RootsFanout; the last CTA runs the publish/wait handshake).
-// With U = 2 the two half-row roots of a row (possibly produced by different CTAs) are joined by one tiny pass of
-// merkle.cu.  (Tried first and measured slower: the same tops on the ENC warps, one unit at a time, through a
-// shared-memory digest buffer -- a compression is a ~200-step dependent chain, which in a few ENC warps competing with
-// 16 busy hash warps takes ~6 us per level; the ENC group became the critical path and nv = 24 went from 1.94 to 2.19 ms.)
+// (Tried and measured slower, round 2: letting the ENC group also reduce the level-log2(E/U) nodes of a unit to its root
+// through a shared-memory digest buffer, which would make a commit ONE launch.  A compression is a ~200-step dependent
+// chain; in a few ENC warps competing with 16 busy hash warps for the alu pipe it takes ~6 us per tree level, ~55 us
+// for the 9 levels of a row -- the ENC group became the critical path: nv = 24 went from 1.94 to 2.19 ms.  A second attempt
+// gave the tops to the HASH group, batched over up to 32 units and level by level with children re-read from `layers`:
+// correct and one launch per commit, but it only beat the separate passes by 1-3 % below ~8 rows per CTA on two shapes,
+// lost 3-6 % on large jobs (the batched passes of merkle.cu run the latency-bound levels at full occupancy), and its mere
+// presence in the kernel slowed the main hash loop by 3.6 %.  The narrow tops stay with merkle.cu.
+// Numbers: profiles/r2_hash_ab.md.)
 //
 // Work units.  U = 1: a CTA claims whole rows dynamically and hash thread t continues with the E entries ENC thread t
 // produced (one level-log2(E) node per thread and row).  That is right for thousands of rows, but a row is ~65 us of
@@ -36,16 +34,11 @@
 // units cover.  The fused part then stops one or two tree levels lower (level log2(E / U)).
 #include <cstdlib>
 
-#include "peer_sync.cuh"
 #include "raa_common.cuh"
 
 namespace zipgpu {
 
-constexpr int kBarEnc = 1, kBarHash = 2;  // named barriers of the ENC group and of the HASH group
-#ifndef ZIPGPU_TOP_BATCH
-#define ZIPGPU_TOP_BATCH 32
-#endif
-constexpr int kTopBatch = ZIPGPU_TOP_BATCH;  // units whose subtree tops the HASH group finishes together
+constexpr int kBarEnc = 1;  // named barrier of the ENC group
 
 // E entries per ENC thread, kWsEnc threads per group: (16, 512) = cw 8192, (8, 512) = cw 4096, (8, 256) = cw 2048,
 // (4, 256) = cw 1024, (4, 128) = cw 512 -- the (E, T) of the plain encoder for those shapes, so the same pre-translated
@@ -55,8 +48,7 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
     commit_ws_kernel(const uint32_t *__restrict__ evals, uint32_t *__restrict__ rows_out,
                      const uint16_t *__restrict__ tab1, const uint16_t *__restrict__ tab2,
                      const uint8_t *__restrict__ colw, uint32_t num_rows, uint8_t *__restrict__ layers, uint32_t one,
-                     uint32_t *__restrict__ row_counter, uint32_t do_tops, uint8_t *__restrict__ roots,
-                     const RootsFanout *__restrict__ fan, unsigned long long fan_step, uint32_t fan_row_begin) {
+                     uint32_t *__restrict__ row_counter) {
     constexpr int IN32 = 2, W = 3, OUT32 = 8;
     constexpr uint32_t T = kWsEnc, P = T * E, cw = P, in_words = (P / 2) * IN32;
     constexpr int EH = E / U;                   // entries per hash thread and unit
@@ -64,7 +56,6 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
     using T16 = Tab16<E>;
     using T8 = Tab8<E>;
     using EncBar = NamedBarrier<kBarEnc, kWsEnc>;
-    using HashBar = NamedBarrier<kBarHash, kWsEnc>;
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *planes = smem;                    // [2][W][P]
     uint32_t *aux = smem + 2 * W * P;           // scan scratch of the ENC group
@@ -72,7 +63,6 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
     __shared__ volatile uint32_t s_row[2];      // row parked in each plane set (0xffffffff: no more rows)
     __shared__ volatile uint32_t s_next;
     __shared__ unsigned long long s_full[2], s_empty[2];  // mbarriers: plane set parked / plane set free again
-    __shared__ uint32_t s_pend_row[kTopBatch + U], s_pend_uu[kTopBatch + U];  // units whose tops are still to be built
     const uint32_t tid = threadIdx.x;
     const uint32_t t = tid & (kWsEnc - 1);      // index within the group
     // U > 1: this CTA's static share of the num_rows * U units
@@ -197,37 +187,6 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
         // ============================== HASH ==============================
         constexpr int H = EH >= 16 ? 4 : EH >= 8 ? 3 : EH >= 4 ? 2 : 1;
         static_assert((1 << H) == EH, "entries per hash thread: a power of two");
-        constexpr int LT = kWsEnc == 512 ? 9 : kWsEnc == 256 ? 8 : 7;  // log2(T): levels between a unit's level-H nodes and its root
-        static_assert((1 << LT) == kWsEnc, "T is a power of two");
-        const size_t lay_stride = (2 * (size_t)cw - 2) * 32;
-        uint32_t npend = 0;
-        // the subtree tops of the `n` pending units, level by level over the whole batch
-        auto tree_tops = [&](uint32_t n) {
-            HashBar::sync();  // the batch's level-H nodes are in `layers` (the group's own stores)
-#pragma unroll 1
-            for (uint32_t sl = 1; sl <= (uint32_t)LT; sl++) {
-                const uint32_t nlog = LT - sl, level = H + sl;  // 2^nlog nodes per unit at this level
-                const size_t off_child = 2 * (size_t)cw - ((2 * (size_t)cw) >> (level - 1));
-                const size_t off = 2 * (size_t)cw - ((2 * (size_t)cw) >> level);
-#pragma unroll 1
-                for (uint32_t i = t; i < (n << nlog); i += T) {
-                    const uint32_t j = i >> nlog, q = i & ((1u << nlog) - 1u);
-                    const uint32_t r = s_pend_row[j], node = ((s_pend_uu[j] * T) >> sl) + q;
-                    uint8_t *lr = layers + (size_t)r * lay_stride;
-                    b3::Digest lft, rgt;
-                    ld_global_v8(lr + (off_child + 2 * (size_t)node) * 32, lft.w);
-                    ld_global_v8(lr + (off_child + 2 * (size_t)node + 1) * 32, rgt.w);
-                    const b3::Digest o = b3::hash_node_call(lft, rgt, one);
-                    if (U == 1 && sl == (uint32_t)LT) {  // the row's root
-                        st_global_v8(roots + (size_t)r * 32, o.w);
-                        if (fan) fan_store_root(fan, fan_step, fan_row_begin + r, o.w);
-                    } else {
-                        st_global_v8(lr + (off + node) * 32, o.w);
-                    }
-                }
-                HashBar::sync();
-            }
-        };
         for (uint32_t it = 0;; it++) {
             const uint32_t buf = it & 1u;
             mbar_wait(&s_full[buf], (it >> 1) & 1u);
@@ -281,29 +240,16 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
                         }
                     }
                 }
-                if (do_tops) {
-                    if (t == 0) {
-                        s_pend_row[npend] = row;
-                        s_pend_uu[npend] = uu;
-                    }
-                    npend++;
-                }
             }
             mbar_arrive(&s_empty[buf]);  // the plane set may be overwritten once all hash threads have said so
-            if (npend >= (uint32_t)kTopBatch) {
-                tree_tops(npend);
-                npend = 0;
-            }
         }
-        if (npend) tree_tops(npend);
     }
-    if (U == 1 && do_tops && fan) fan_finish(fan, fan_step);  // both groups, every CTA: the roots exchange of a sharded commit
 }
 
 namespace {
 
 template <int E, int TENC, int U>
-cudaError_t launch_ws_u(const EncodeArgs &a, uint32_t grid, bool tops) {
+cudaError_t launch_ws_u(const EncodeArgs &a, uint32_t grid) {
     const size_t ws_smem = (2 * 3 * (size_t)(E * TENC) + 64 * 3 + (TENC / 32) * 256) * sizeof(uint32_t);
     auto kern = commit_ws_kernel<E, TENC, U>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem);
@@ -320,11 +266,8 @@ cudaError_t launch_ws_u(const EncodeArgs &a, uint32_t grid, bool tops) {
         const uint32_t units = a.num_rows * U;
         if (grid > units) grid = units;
     }
-    const bool fan = U == 1 && tops && a.fan != nullptr;
     kern<<<grid, 2 * TENC, ws_smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows, a.fuse_layers, 1u,
-                                                row_counter, tops ? 1u : 0u, a.roots, fan ? a.fan : nullptr, a.fan_step,
-                                                a.fan_row_begin);
-    if (fan && a.fan_fused) *a.fan_fused = true;
+                                                row_counter);
     return cudaGetLastError();
 }
 
@@ -339,19 +282,11 @@ cudaError_t launch_ws(const EncodeArgs &a, int *fused_levels) {
     int U = 1;
     if (TENC == 512 && a.num_rows >= 3 * grid && a.num_rows < 6 * grid) U = 2;
     if (const char *env = getenv("ZIPGPU_WS_UNITS")) U = atoi(env) >= 2 ? 2 : 1;
-    // Tree tops inside the launch (then it builds every tree up to the roots of its work units: level depth, or depth - 1
-    // with half-row units) while a CTA gets at most ~8 rows: there the two extra launches of the batched passes cost more
-    // than they save (cw = 4096, 1024 rows: 0.284 -> 0.266 ms; cw = 2048, 1024 rows: 0.156 -> 0.152).  For bigger jobs the
-    // separate passes win -- they run the latency-bound levels at full occupancy (cw = 8192, 4096 rows: 1.921 vs 1.972 ms)
-    // -- and the launch stops at level log2(E / U).  ZIPGPU_WS_TOPS=0/1 forces.
-    bool tops = a.num_rows <= ((E == 8 && TENC == 512) ? 16u : 8u) * grid;  // (cw = 4096 still gains at 14 rows per CTA)
-    if (const char *env = getenv("ZIPGPU_WS_TOPS")) tops = atoi(env) != 0;
-    int depth = 0, h = 0;
-    while ((1u << depth) < (uint32_t)(E * TENC)) depth++;
+    int h = 0;
     while ((1 << h) < E / U) h++;
-    if (fused_levels) *fused_levels = tops ? depth - (U == 2 ? 1 : 0) : h;
-    if (U == 2) return launch_ws_u<E, TENC, 2>(a, grid, tops);
-    return launch_ws_u<E, TENC, 1>(a, grid, tops);
+    if (fused_levels) *fused_levels = h;
+    if (U == 2) return launch_ws_u<E, TENC, 2>(a, grid);
+    return launch_ws_u<E, TENC, 1>(a, grid);
 }
 
 }  // namespace

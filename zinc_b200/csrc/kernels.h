@@ -6,8 +6,6 @@
 
 namespace zipgpu {
 
-struct RootsFanout;  // multi-GPU roots exchange, below
-
 // ---- K1: RAA encoder (raa_encode.cu) ----
 struct EncodeArgs {
     const uint32_t *evals;   // [num_rows][row_len][2*in_limbs]
@@ -22,14 +20,8 @@ struct EncodeArgs {
                                      // (zero-copy over PCIe); every staged row is also written here, in HBM
     uint32_t *row_counter = nullptr; // device word for dynamic row claiming (armed by the launcher); NULL = static rows
     uint8_t *fuse_layers = nullptr;  // non-NULL: the fused commit kernel also writes the lowest Merkle levels
-    int *fused_levels_out = nullptr; // receives the level up to which that launch builds the trees: the warp-specialised
-                                     // kernel goes to the roots of its work units (depth, or depth - 1 with half-row units)
-    uint8_t *roots = nullptr;        // fused commit: where a launch that reaches the roots puts them
-    // row-sharded commit (see MerkleArgs): honoured by a launch that produces the roots itself; *fan_fused reports it
-    const RootsFanout *fan = nullptr;
-    unsigned long long fan_step = 0;
-    uint32_t fan_row_begin = 0;
-    bool *fan_fused = nullptr;
+    int *fused_levels_out = nullptr; // receives the level up to which that launch builds the trees (<= encode_fused_levels():
+                                     // the warp-specialised kernel stops 1 or 2 levels lower when it hashes sub-row units)
     cudaStream_t stream;
 };
 // the warp-specialised commit kernel (commit_ws.cu) for the encoder configuration (E, T) of an exact Int<1> -> Int<4> shape

@@ -823,8 +823,7 @@ struct FanReq {
 };
 
 static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_evals, uint64_t *d_rows, cudaStream_t s,
-                      uint8_t *fuse_layers = nullptr, uint64_t *evals_copy = nullptr, int *fused_levels = nullptr,
-                      uint8_t *d_roots = nullptr, FanReq *fan = nullptr) {
+                      uint8_t *fuse_layers = nullptr, uint64_t *evals_copy = nullptr, int *fused_levels = nullptr) {
     if (num_rows == 0) return ZIPGPU_OK;
     if (num_rows > 0xffffffffull) return fail(ZIPGPU_ERR_UNSUPPORTED, "too many rows");
     int rc;
@@ -896,13 +895,6 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     a.num_sms = code->ctx->num_sms;
     a.fuse_layers = fuse_layers;
     a.fused_levels_out = fused_levels;
-    a.roots = d_roots;
-    if (fan && !fan->fused && fuse_layers) {  // a fused launch that reaches the roots also runs the roots exchange
-        a.fan = fan->pr->d_fan;
-        a.fan_step = fan->pr->step + 1;
-        a.fan_row_begin = (uint32_t)fan->row_begin;
-        a.fan_fused = &fan->fused;
-    }
     a.evals_copy = reinterpret_cast<uint32_t *>(evals_copy);
     if (!getenv("ZIPGPU_STATIC_ROWS")) {
         a.row_counter = code->ctx->d_row_counters + 2 * (code->ctx->row_counter_pos++ % 256);
@@ -911,7 +903,6 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     cudaError_t e = launch_raa_encode(a);
     if (e != cudaSuccess) return cuda_fail(e, "launch_raa_encode");
     code->ctx->launches++;
-    if (a.fan && fan->fused) fan->pr->step++;  // the exchange of this step is in flight
     return ZIPGPU_OK;
 }
 
@@ -1043,8 +1034,7 @@ static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
         return ZIPGPU_OK;
     }
     int fused_levels = code->fused_levels;  // the launch reports how far it really built the trees (sub-row units stop lower)
-    int rc = encode_dev(code, num_rows, d_evals, d_rows, s, fuse ? d_layers : nullptr, evals_copy, &fused_levels, d_roots,
-                        until_level < 0 || until_level >= code->depth ? fan : nullptr);
+    int rc = encode_dev(code, num_rows, d_evals, d_rows, s, fuse ? d_layers : nullptr, evals_copy, &fused_levels);
     if (rc) return rc;
     if (prof) {
         cudaEventRecord(r.e1, s);
