@@ -42,6 +42,27 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 // all bulk groups of this thread are complete (the global writes are done)
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- programmatic dependent launch (sm_90+).  A kernel launched through launch_pdl may be scheduled while its
+// predecessor on the stream is still draining; it must execute pdl_wait() before touching anything the predecessor wrote
+// (a no-op when the kernel was launched the ordinary way).  Hides the ~2-3 us launch gap between the short, dependent
+// kernels of a small commit. ----
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- mbarrier (shared-memory arrive/wait objects, sm_80+): unlike bar.sync, waiters do not synchronise with each
 // other -- every thread (warp) proceeds as soon as the phase it waits for has completed ----
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {

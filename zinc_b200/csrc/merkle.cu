@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(128, MINB)
     merkle_subtree_kernel(const uint32_t *__restrict__ leaves, uint8_t *layers, uint8_t *roots, uint32_t num_rows,
                           TreeGeom g, uint32_t level_in, uint32_t one, const RootsFanout *__restrict__ fan,
                           unsigned long long fan_step, uint32_t fan_row_begin) {
+    pdl_wait();  // (launched with programmatic stream serialisation: the producer of `leaves` / `layers` may still be draining)
     const uint32_t chunks_per_row = (g.cw >> level_in) >> H;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = gid < (size_t)num_rows * chunks_per_row;
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(512)
                            uint32_t level_in, uint32_t S, uint32_t RL, uint32_t one, const RootsFanout *__restrict__ fan,
                            unsigned long long fan_step, uint32_t fan_row_begin) {
     __shared__ __align__(8) uint32_t buf[8][CTA_TREE_BUF];
+    pdl_wait();
     const uint32_t subtrees_per_row = (g.cw >> level_in) >> S;
     const uint32_t row0 = RL ? blockIdx.x << RL : blockIdx.x / subtrees_per_row;
     const uint32_t b = RL ? 0u : blockIdx.x % subtrees_per_row;
@@ -196,6 +198,10 @@ cudaError_t launch_cta_tree(const MerkleArgs &a, const TreeGeom &g, uint32_t lev
     if (grid == 0) return cudaSuccess;
     if (grid > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     const uint32_t half = (1u << (S + RL)) / 2, block = half < 32 ? 32 : half;
+    static const bool pdl = getenv("ZIPGPU_NO_PDL") == nullptr;
+    if (pdl)
+        return launch_pdl(merkle_cta_tree_kernel<LEAF32>, dim3((uint32_t)grid), dim3(block), 0, a.stream, a.leaves, a.layers, a.roots,
+                          a.num_rows, g, level_in, S, RL, 1u, fan ? a.fan : nullptr, a.fan_step, a.fan_row_begin);
     merkle_cta_tree_kernel<LEAF32><<<(uint32_t)grid, block, 0, a.stream>>>(a.leaves, a.layers, a.roots, a.num_rows, g, level_in,
                                                                      S, RL, 1u, fan ? a.fan : nullptr, a.fan_step,
                                                                      a.fan_row_begin);
@@ -211,6 +217,10 @@ cudaError_t launch_pass(const MerkleArgs &a, const TreeGeom &g, uint32_t level_i
     const size_t grid = (threads + block - 1) / block;
     if (grid == 0) return cudaSuccess;
     if (grid > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    static const bool pdl = getenv("ZIPGPU_NO_PDL") == nullptr;
+    if (pdl)
+        return launch_pdl(merkle_subtree_kernel<LEAF32, H, MINB>, dim3((uint32_t)grid), dim3(block), 0, a.stream, a.leaves, a.layers,
+                          a.roots, a.num_rows, g, level_in, 1u, fan ? a.fan : nullptr, a.fan_step, a.fan_row_begin);
     merkle_subtree_kernel<LEAF32, H, MINB><<<(uint32_t)grid, block, 0, a.stream>>>(a.leaves, a.layers, a.roots, a.num_rows,
                                                                            g, level_in, 1u, fan ? a.fan : nullptr,
                                                                            a.fan_step, a.fan_row_begin);
