@@ -26,10 +26,9 @@ __global__ void __launch_bounds__(1024) peer_roots_allgather_kernel(const RootsF
         if (reinterpret_cast<const uint4 *>(dst) == src) continue;  // already in place in the own buffer
         for (size_t i = tid; i < chunks; i += blockDim.x) dst[i] = src[i];
     }
-    __threadfence_system();
+    __threadfence_system();  // every copying thread fences its own stores; the barrier orders them before the publication
     __syncthreads();
     fan_handshake(fan, step, tid);
-    __threadfence_system();
 }
 
 cudaError_t launch_peer_roots_allgather(const RootsFanout *fan, unsigned long long step, const uint8_t *src, size_t offset,

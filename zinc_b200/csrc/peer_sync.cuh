@@ -32,10 +32,11 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 
 // publish + wait, by the threads tid < world of ONE CTA (called by the last CTA of the launch, or by the stand-alone
-// exchange kernel).  Preceded by a system-scope fence of the calling thread.
+// exchange kernel).  The caller's writes to the peers must happen-before this call (a system-scope fence by the calling
+// thread, or by a thread it has synchronised with).  st.release.sys / ld.acquire.sys carry the ordering themselves: no
+// extra fences around them (each system fence costs ~3-7 us on a B200; measured, scripts/fan_probe.py).
 __device__ __forceinline__ void fan_handshake(const RootsFanout *fan, unsigned long long step, uint32_t tid) {
     if (tid < (uint32_t)fan->world) {
-        __threadfence_system();
         st_release_sys_u64(fan->flags[tid] + fan->rank, step);  // flag word [my rank] of peer `tid`
         const unsigned long long *mine = fan->flags[fan->rank] + tid;
         const unsigned long long t0 = global_timer_ns();
@@ -54,36 +55,36 @@ __device__ __forceinline__ void fan_handshake(const RootsFanout *fan, unsigned l
 }
 
 // The thread that holds a finished root stores it into every rank's result buffer (P2P stores through NVLink; the own
-// buffer is one of them) and fences them at system scope right away, while the rest of the grid is still hashing.
+// buffer is one of them) while the rest of the grid is still hashing.  No fence here: the CTA's thread 0 fences once for
+// all of them in fan_finish.
 __device__ __forceinline__ void fan_store_root(const RootsFanout *fan, unsigned long long step, uint32_t global_row,
                                                const uint32_t (&d)[8]) {
     const int par = (int)(step & 1ull);
     for (int p = 0; p < fan->world; p++) st_global_v8(fan->bufs[par][p] + (size_t)global_row * 32, d);
-    __threadfence_system();
 }
 
 // End of a kernel whose threads called fan_store_root.  EVERY thread of EVERY CTA must reach it (it contains barriers).
-// Every CTA counts itself done after its storing threads' system fences; the LAST one runs the handshake.  (Measured
-// against the alternative -- only local stores during the launch, the last CTA copies all roots to the peers, one system
-// fence -- on 8 GPUs at 512 rows each: 0.308 vs 0.318 ms per sharded commit; the spread-out stores overlap the hashing.)
+// Per CTA: barrier (the storing threads' writes happen-before thread 0), ONE system-scope fence by thread 0 (cumulative
+// over them), then the CTA counts itself done with a device-scope atomic.  The CTA that counts last has therefore
+// synchronised with every storing CTA after its system fence, and publishes the flags with release semantics.
+// Cost on one B200 (world = 1, scripts/fan_probe.py): +13 us per commit; the first version (a system fence per stored
+// root, fences around the handshake) cost +24 us.  (Also measured: only local stores during the launch and the last CTA
+// copying all roots to the peers behind one fence -- 0.318 vs 0.308 ms per sharded commit at N = 8.)
 __device__ __forceinline__ void fan_finish(const RootsFanout *fan, unsigned long long step) {
     __shared__ unsigned int s_last;
-    __syncthreads();  // after the storing threads' fences
+    __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();  // cumulative over what the barrier made visible to this thread
+        __threadfence_system();
         const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
         const unsigned int prev = atomicAdd(fan->done, 1u);
         s_last = (prev == total - 1u) ? 1u : 0u;
         if (s_last) {
-            *fan->done = 0u;  // re-armed for the next launch on this stream
-            __threadfence_system();
+            *fan->done = 0u;  // re-armed for the next launch on this stream (ordered by the kernel boundary)
+            __threadfence();  // acquire side of the counter: the other CTAs' fenced stores happen-before the flags below
         }
     }
     __syncthreads();
-    if (s_last) {
-        fan_handshake(fan, step, threadIdx.x);
-        __threadfence_system();
-    }
+    if (s_last) fan_handshake(fan, step, threadIdx.x);
 }
 
 }  // namespace zipgpu
