@@ -195,3 +195,54 @@ def test_zip_linear_code_new_mirrors_reference():
         assert code.a.d == row_len // 2 and code.a.n == cw // 2
     with pytest.raises(AssertionError):
         ZipLinearCode.new(DefaultLinearCodeSpec(), 12, MockTranscript())  # code.rs:105 poly_size.is_power_of_two()
+
+
+def test_multi_gpu_context_has_no_cpu_fallback_either():
+    """zipgpu_mgpu_create (ONE process, n GPUs) refuses to exist without a device, like zipgpu_ctx_create"""
+    from zinc_b200 import MultiContext
+    from zinc_b200 import _native as nat
+
+    cnt = C.c_int(-1)
+    rc = nat.lib().zipgpu_device_count(C.byref(cnt))
+    if rc == 0 and cnt.value > 0:
+        pytest.skip("a GPU is visible here")
+    h = C.c_void_p()
+    assert nat.lib().zipgpu_mgpu_create(None, 0, C.byref(h)) == nat.ERR_NO_DEVICE
+    with pytest.raises(nat.ZipGpuError):
+        MultiContext()
+    # the NULL-argument paths of the sharded entry points answer without touching a device
+    assert nat.lib().zipgpu_commit_resident_sharded(None, None, 0, 0, None, None, None) == nat.ERR_INVALID
+    assert nat.lib().zipgpu_peer_roots_status(None) == nat.ERR_INVALID
+    assert nat.lib().zipgpu_encode_f(None, 0, 1, None, None, None) == nat.ERR_INVALID
+
+
+def test_as_limbs_accepts_signed_limb_arrays():
+    """a 2-D int64 array with limbs > 1 (multi-limb Int<2> inputs given as signed words) used to recurse for
+    ever; it is a reinterpretation of the two's-complement words, while 1-D int64 values are sign-extended"""
+    from zinc_b200.zip import as_limbs
+
+    a = np.array([[1, -1], [-(1 << 63), (1 << 63) - 1]], dtype=np.int64)
+    got = as_limbs(a, 2)
+    assert got.dtype == np.uint64 and got.shape == (2, 2)
+    assert got.tolist() == [[1, 0xFFFFFFFFFFFFFFFF], [1 << 63, (1 << 63) - 1]]
+    assert as_limbs(np.zeros((4, 2), np.int64), 2).shape == (4, 2)
+    ext = as_limbs(np.array([-2, 3], dtype=np.int64), 3)  # values: sign-extended into the upper limbs
+    assert ext.tolist() == [[0xFFFFFFFFFFFFFFFE, 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF], [3, 0, 0]]
+    assert as_limbs(np.array([5, 6], dtype=np.int32), 1).tolist() == [[5], [6]]
+
+
+def test_bench_and_library_agree_on_the_row_partition():
+    """bench.py, dist.py and mgpu.cu (balanced contiguous row ranges) must cut a commitment the same way"""
+    import importlib.util
+
+    from zinc_b200.dist import shard_range
+
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    ns = {}
+    start = src.index("def shard_range")
+    end = src.index("def gen_evals")
+    exec(src[start:end], ns)
+    for n in (0, 1, 3, 512, 4096, 4099):
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                assert ns["shard_range"](n, r, world) == shard_range(n, r, world)
