@@ -43,6 +43,7 @@ struct CachedBuf {
     void *p;
     size_t bytes;
     cudaEvent_t ready;
+    cudaStream_t last = nullptr;  // the stream `ready` was recorded on: a reuse on the same stream needs no wait
 };
 
 struct zipgpu_ctx {
@@ -160,8 +161,10 @@ static cudaError_t dev_alloc(zipgpu_ctx *c, void **out, size_t bytes, cudaStream
     if (best != (size_t)-1) {
         buf = c->cache_free[best];
         c->cache_free.erase(c->cache_free.begin() + best);
-        cudaError_t e = cudaStreamWaitEvent(s, buf.ready, 0);
-        if (e != cudaSuccess) return e;
+        if (buf.last != s) {  // (stream order already covers a reuse on the stream it was released on)
+            cudaError_t e = cudaStreamWaitEvent(s, buf.ready, 0);
+            if (e != cudaSuccess) return e;
+        }
     } else {
         cudaError_t e = cudaMalloc(&buf.p, bytes);
         if (e == cudaErrorMemoryAllocation) {  // drop the cache and retry once
@@ -189,6 +192,7 @@ static cudaError_t dev_free(zipgpu_ctx *c, void *p, cudaStream_t s) {
             CachedBuf buf = c->cache_live[i];
             c->cache_live.erase(c->cache_live.begin() + i);
             cudaError_t e = cudaEventRecord(buf.ready, s);
+            buf.last = s;
             c->cache_free.push_back(buf);
             return e;
         }
@@ -346,6 +350,13 @@ extern "C" int zipgpu_ctx_sync(zipgpu_ctx *c) {
     CU(cudaStreamSynchronize(c->stream2));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaStreamSynchronize(c->d2h));
+    return ZIPGPU_OK;
+}
+
+// after a host job: its copy / second kernel streams have been joined back into the kernel stream, so waiting for that
+// one stream is waiting for the whole job (three fewer driver calls than zipgpu_ctx_sync on the latency path)
+static int sync_job(zipgpu_ctx *c) {
+    CU(cudaStreamSynchronize(c->stream));
     return ZIPGPU_OK;
 }
 
@@ -1381,7 +1392,7 @@ extern "C" int zipgpu_encode_rows(zipgpu_code *code, size_t num_rows, const uint
     CU(cudaSetDevice(code->ctx->device));
     HostJob job{evals, rows_out, nullptr, nullptr, false, nullptr};
     int rc = run_host_job(code, num_rows, job);
-    int rc2 = zipgpu_ctx_sync(code->ctx);
+    int rc2 = sync_job(code->ctx);
     return rc ? rc : rc2;
 }
 
@@ -1557,7 +1568,7 @@ extern "C" int zipgpu_commit(zipgpu_code *code, size_t num_rows, const uint64_t 
     CU(cudaSetDevice(code->ctx->device));
     HostJob job{evals, rows_out, layers_out, roots_out, true, nullptr};
     int rc = run_host_job(code, num_rows, job);
-    int rc2 = zipgpu_ctx_sync(code->ctx);
+    int rc2 = sync_job(code->ctx);
     return rc ? rc : rc2;
 }
 
@@ -1661,7 +1672,7 @@ extern "C" int zipgpu_batch_commit(zipgpu_code *code, size_t num_polys, size_t n
             rc = run_host_job(code, num_rows, job);
         }
     }
-    int rc2 = zipgpu_ctx_sync(code->ctx);
+    int rc2 = sync_job(code->ctx);
     return rc ? rc : rc2;
 }
 
@@ -1675,7 +1686,7 @@ extern "C" int zipgpu_commit_resident(zipgpu_code *code, size_t num_rows, const 
     CU(cudaSetDevice(code->ctx->device));
     HostJob job{evals, nullptr, nullptr, roots_out, true, handle};
     int rc = run_host_job(code, num_rows, job);
-    int rc2 = zipgpu_ctx_sync(code->ctx);
+    int rc2 = sync_job(code->ctx);
     return rc ? rc : rc2;
 }
 
@@ -1736,7 +1747,7 @@ extern "C" int zipgpu_commit_resident_sharded(zipgpu_code *code, zipgpu_peer_roo
     FanReq fan{pr, row_begin};
     HostJob job{evals, nullptr, nullptr, nullptr, true, handle, &fan, roots_all_out};
     rc = run_host_job(code, count, job);
-    int rc2 = zipgpu_ctx_sync(code->ctx);
+    int rc2 = sync_job(code->ctx);
     if (rc == 0 && rc2 == 0) rc = zipgpu_peer_roots_status(pr);
     return rc ? rc : rc2;
 }
