@@ -482,3 +482,29 @@ def test_encode_rows_long_non_power_of_two_codeword(oracle, ctx):
     pp = MultilinearZipParams.new(17, num_rows, code)
     got = MultilinearZip.encode_rows(pp, cw, row_len, evals, ctx)
     assert np.array_equal(got.reshape(-1), rows)
+
+
+@pytest.mark.parametrize("num_rows", [1, 97, 148, 500, 1211])
+def test_cw16384_warp_specialised_commit_kernel(num_rows, oracle, ctx, monkeypatch):
+    """cw = 16384 (nv = 25 / 26) through commit_ws16k_kernel -- one plane set, the ENC group encodes in two half-passes
+    and stores the codeword from registers, the HASH group hashes it back from global memory -- for row counts below,
+    at and above one row per SM and above the dynamic-claiming threshold; against the oracle and the other two paths"""
+    from zinc_b200 import RaaCode, ZipTypes
+
+    row_len, cw = 8192, 16384
+    p1, p2 = oracle.perm_from_seed(cw, KECCAK_SEEDS[0]), oracle.perm_from_seed(cw, KECCAK_SEEDS[1])
+    code = RaaCode.with_permutations(ZipTypes(), row_len, 2, p1, p2)
+    evals = np.random.default_rng(num_rows).integers(0, 1 << 64, size=num_rows * row_len, dtype=np.uint64)
+    if num_rows >= 2:
+        evals[:row_len] = np.uint64((1 << 63) - 1)          # i64::MAX row
+        evals[row_len:2 * row_len] = np.uint64(1 << 63)      # i64::MIN row
+    rc, rows, layers, roots = oracle.commit_mt(evals, num_rows, row_len, 2, 0, 0, p1, p2, threads=16, faithful=False)
+    assert rc == 0
+    monkeypatch.setenv("ZIPGPU_FUSE_MIN_ROWS", "1")
+    for knob in (None, "ZIPGPU_NO_WS", "ZIPGPU_NO_FUSE"):
+        if knob:
+            monkeypatch.setenv(knob, "1")
+        g_rows, g_lay, g_roots = _commit_device(ctx, code, num_rows, cw, evals)
+        assert np.array_equal(g_roots, roots), knob
+        assert np.array_equal(g_rows, rows), knob
+        assert np.array_equal(g_lay, layers), knob

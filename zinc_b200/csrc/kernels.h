@@ -13,6 +13,7 @@ struct EncodeArgs {
     const uint16_t *tab1;    // device tables from build_encode_tables, encode_perm_padded_len(cw) entries each
     const uint16_t *tab2;
     const uint8_t *colw;
+    const uint32_t *perm1_raw = nullptr;  // device u32[cw]: perm1 as uploaded (the cw = 16384 commit kernel gathers through it)
     uint32_t num_rows, row_len, cw, out32;
     int in_limbs;
     int num_sms;
@@ -25,6 +26,10 @@ struct EncodeArgs {
     cudaStream_t stream;
 };
 // the warp-specialised commit kernel (commit_ws.cu) for the encoder configuration (E, T) of an exact Int<1> -> Int<4> shape
+// the cw = 16384 form (commit_ws16k.cu): one plane set, the hash warps read the codeword back from global memory
+bool commit_ws16k_supported(uint32_t row_len, uint32_t cw);
+int commit_ws16k_levels();
+cudaError_t launch_commit_ws16k(const EncodeArgs &a);
 bool commit_ws_supported(int E, int T);
 cudaError_t launch_commit_ws(const EncodeArgs &a, int E, int T, int *fused_levels);
 int encode_fused_levels(int in_limbs, int out_limbs, uint32_t row_len, uint32_t cw);

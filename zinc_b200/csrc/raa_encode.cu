@@ -426,6 +426,11 @@ cudaError_t launch_w(const EncodeArgs &a) {
         // the warp-specialised commit kernel (commit_ws.cu): an encode group and a hash group per CTA, two plane sets
         return launch_commit_ws(a, c.E, c.T, a.fused_levels_out);
     }
+    if (a.fuse_layers && !a.evals_copy && IN32 == 2 && W == 3 && exact && a.out32 == 8 && a.perm1_raw &&
+        commit_ws16k_supported(a.row_len, a.cw) && !getenv("ZIPGPU_NO_WS")) {
+        if (a.fused_levels_out) *a.fused_levels_out = commit_ws16k_levels();
+        return launch_commit_ws16k(a);
+    }
     if (a.fuse_layers && a.fused_levels_out) {
         int h = 0;
         while ((1 << h) < c.E) h++;

@@ -506,6 +506,18 @@ extern "C" int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t rep, i
         delete c;
         return cuda_fail(e, "code tables");
     }
+    if (in_limbs == 1 && out_limbs == 4 && commit_ws16k_supported((uint32_t)row_len, (uint32_t)cw)) {
+        // the cw = 16384 commit kernel gathers pass 1 through the permutation as uploaded
+        if ((e = cudaMalloc(&c->d_perm1, cw * 4)) != cudaSuccess || (e = cudaMalloc(&c->d_perm2, cw * 4)) != cudaSuccess ||
+            (e = cudaMemcpy(c->d_perm1, perm1, cw * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMemcpy(c->d_perm2, perm2, cw * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+            cudaFree(c->d_perm1);
+            cudaFree(c->d_perm2);
+            dev_free(ctx, d_tables, ctx->stream);
+            delete c;
+            return cuda_fail(e, "cudaMalloc/cudaMemcpy(permutations)");
+        }
+    }
     c->d_tables = d_tables;
     c->d_tab1 = reinterpret_cast<uint16_t *>(d_tables);
     c->d_tab2 = reinterpret_cast<uint16_t *>(static_cast<uint8_t *>(d_tables) + padded * 2);
@@ -898,6 +910,7 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     a.tab1 = code->d_tab1;
     a.tab2 = code->d_tab2;
     a.colw = code->d_colw;
+    a.perm1_raw = code->d_perm1;
     a.num_rows = (uint32_t)num_rows;
     a.row_len = (uint32_t)code->row_len;
     a.cw = (uint32_t)code->cw;
@@ -979,6 +992,8 @@ static size_t fuse_min_rows(const zipgpu_ctx *ctx, const zipgpu_code *code) {
     const bool ws = code->in_limbs == 1 && code->out_limbs == 4 &&
                     (code->cw == 1024 || code->cw == 2048 || code->cw == 4096 || code->cw == 8192);
     if (ws) return code->cw == 1024 ? 256 : 128;
+    if (code->in_limbs == 1 && code->out_limbs == 4 && commit_ws16k_supported((uint32_t)code->row_len, (uint32_t)code->cw))
+        return (size_t)ctx->num_sms;  // cw = 16384: from one row per SM
     return (size_t)(code->cw >= 8192 ? 6 : 10) * ctx->num_sms;
 }
 
