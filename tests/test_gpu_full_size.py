@@ -328,6 +328,7 @@ def test_warp_specialised_commit_kernel(row_len, num_rows, oracle, ctx, monkeypa
     rc, rows, layers, roots = oracle.commit_mt(evals, num_rows, row_len, 2, 0, 0, p1, p2, threads=16, faithful=False)
     assert rc == 0
     monkeypatch.setenv("ZIPGPU_FUSE_MIN_ROWS", "1")
+    monkeypatch.setenv("ZIPGPU_WS16K_MIN_ROWS", "1")  # the product uses this kernel from 2048 rows
     for knob in (None, "ZIPGPU_NO_WS", "ZIPGPU_NO_FUSE"):
         if knob:
             monkeypatch.setenv(knob, "1")
@@ -501,6 +502,7 @@ def test_cw16384_warp_specialised_commit_kernel(num_rows, oracle, ctx, monkeypat
     rc, rows, layers, roots = oracle.commit_mt(evals, num_rows, row_len, 2, 0, 0, p1, p2, threads=16, faithful=False)
     assert rc == 0
     monkeypatch.setenv("ZIPGPU_FUSE_MIN_ROWS", "1")
+    monkeypatch.setenv("ZIPGPU_WS16K_MIN_ROWS", "1")  # the product uses this kernel from 2048 rows
     for knob in (None, "ZIPGPU_NO_WS", "ZIPGPU_NO_FUSE"):
         if knob:
             monkeypatch.setenv(knob, "1")

@@ -407,6 +407,16 @@ cudaError_t launch_e(const EncodeArgs &a, const EncodeCfg &c, size_t smem) {
     }
 }
 
+// cw = 16384: rows from which the warp-specialised kernel beats the serial fused kernel (scripts/shard_sweep.py
+// --row-len 8192, round 2: 1024 rows 1.066 vs 1.053 ms, 1536: 1.638 vs 1.631, 2048: 2.068 vs 2.074, 4096: 4.070 vs 4.110,
+// 8192: 8.081 vs 8.178).  The fused launches themselves are level (7.93 vs 7.90 ms at 8192 rows: the serial form hashes
+// with all 32 warps of an SM); the gain is the fifth tree level the 32-leaf hash threads fold in, which halves the
+// latency-bound upper passes (0.28 -> 0.15 ms).
+static uint32_t ws16k_min_rows() {
+    const char *e = getenv("ZIPGPU_WS16K_MIN_ROWS");  // read per launch: the tests switch it
+    return e ? (uint32_t)atol(e) : 2048u;
+}
+
 template <int IN32, int W>
 cudaError_t launch_w(const EncodeArgs &a) {
     const EncodeCfg c = pick_cfg(a.cw);
@@ -427,7 +437,7 @@ cudaError_t launch_w(const EncodeArgs &a) {
         return launch_commit_ws(a, c.E, c.T, a.fused_levels_out);
     }
     if (a.fuse_layers && !a.evals_copy && IN32 == 2 && W == 3 && exact && a.out32 == 8 && a.perm1_raw &&
-        commit_ws16k_supported(a.row_len, a.cw) && !getenv("ZIPGPU_NO_WS")) {
+        commit_ws16k_supported(a.row_len, a.cw) && !getenv("ZIPGPU_NO_WS") && a.num_rows >= ws16k_min_rows()) {
         if (a.fused_levels_out) *a.fused_levels_out = commit_ws16k_levels();
         return launch_commit_ws16k(a);
     }

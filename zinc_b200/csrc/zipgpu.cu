@@ -992,8 +992,6 @@ static size_t fuse_min_rows(const zipgpu_ctx *ctx, const zipgpu_code *code) {
     const bool ws = code->in_limbs == 1 && code->out_limbs == 4 &&
                     (code->cw == 1024 || code->cw == 2048 || code->cw == 4096 || code->cw == 8192);
     if (ws) return code->cw == 1024 ? 256 : 128;
-    if (code->in_limbs == 1 && code->out_limbs == 4 && commit_ws16k_supported((uint32_t)code->row_len, (uint32_t)code->cw))
-        return (size_t)ctx->num_sms;  // cw = 16384: from one row per SM
     return (size_t)(code->cw >= 8192 ? 6 : 10) * ctx->num_sms;
 }
 
