@@ -362,6 +362,40 @@ def test_warp_specialised_commit_kernel_sub_row_units(row_len, num_rows, units, 
     assert np.array_equal(g_lay, layers)
 
 
+@pytest.mark.parametrize("units", [1, 2])
+@pytest.mark.parametrize("row_len,num_rows", [(4096, 1), (4096, 149), (4096, 517), (4096, 1400), (2048, 523), (2048, 2901),
+                                              (1024, 97), (1024, 3000), (512, 611), (256, 59), (256, 5000)])
+def test_warp_specialised_commit_kernel_tree_tops(row_len, num_rows, units, oracle, ctx, monkeypatch):
+    """whole trees in the one launch: the epilogue of the warp-specialised commit kernel that finishes the trees of the
+    units a CTA hashed (4 nodes per thread in registers, then level by level through shared memory; rows whose two
+    units were hashed by two CTAs are joined by whichever arrives second) -- forced for every shape and unit count, at
+    row counts with less than one, one and several batches of 8 units per CTA and split rows at the CTA boundaries;
+    layers, rows and roots against the oracle, twice (the boundary flags re-arm themselves), and ONE launch each"""
+    from zinc_b200 import RaaCode, ZipTypes
+
+    cw = 2 * row_len
+    p1, p2 = oracle.perm_from_seed(cw, KECCAK_SEEDS[0]), oracle.perm_from_seed(cw, KECCAK_SEEDS[1])
+    code = RaaCode.with_permutations(ZipTypes(), row_len, 2, p1, p2)
+    evals = np.random.default_rng(num_rows * 3 + units).integers(0, 1 << 64, size=num_rows * row_len, dtype=np.uint64)
+    rc, rows, layers, roots = oracle.commit_mt(evals, num_rows, row_len, 2, 0, 0, p1, p2, threads=16, faithful=False)
+    assert rc == 0
+    monkeypatch.setenv("ZIPGPU_FUSE_MIN_ROWS", "1")
+    monkeypatch.setenv("ZIPGPU_WS_UNITS", str(units))
+    monkeypatch.setenv("ZIPGPU_WS_TOPS", "1")
+    for rep in range(2):
+        l0 = ctx.launch_count
+        g_rows, g_lay, g_roots = _commit_device(ctx, code, num_rows, cw, evals)
+        assert ctx.launch_count - l0 == 1, "the commit must be one launch"
+        assert np.array_equal(g_roots, roots), rep
+        assert np.array_equal(g_rows, rows), rep
+        assert np.array_equal(g_lay, layers), rep
+    monkeypatch.setenv("ZIPGPU_WS_TOPS", "0")
+    l0 = ctx.launch_count
+    g_rows, g_lay, g_roots = _commit_device(ctx, code, num_rows, cw, evals)
+    assert ctx.launch_count - l0 >= 2
+    assert np.array_equal(g_roots, roots) and np.array_equal(g_lay, layers)
+
+
 def test_peer_roots_allgather_single_rank(ctx):
     """the peer-memory roots exchange degenerates to a copy + self-signal on one GPU (N > 1: scripts/strong_scaling.py
     --p2p and test_peer_roots_two_gpus below); two steps exercise the double buffering"""

@@ -33,7 +33,7 @@ def _device_count():
     return n.value
 
 
-@pytest.mark.parametrize("nv", [6, 8, 12, 16, 20])
+@pytest.mark.parametrize("nv", [6, 8, 12, 16, 20, 21, 22])
 def test_fused_exchange_world1_device(nv, oracle, ctx):
     """zipgpu_commit_device_sharded with a one-rank exchange: the launch that produces the roots also stores them into
     the result buffer and runs the publish/wait handshake with itself; roots == zipgpu_commit_device == oracle"""
@@ -68,6 +68,42 @@ def test_fused_exchange_world1_device(nv, oracle, ctx):
     rc, _, _, roots = oracle.commit_mt(evals, num_rows, row_len, 2, 0, 0, p1, p2, threads=8, faithful=False,
                                        want_rows=False, want_layers=False)
     assert rc == 0 and got.tobytes() == roots.tobytes()
+    peer.close()
+
+
+@pytest.mark.parametrize("units", ["1", "2"])
+def test_fused_exchange_in_the_commit_kernel(units, oracle, ctx, monkeypatch):
+    """a shard whose trees are finished by the warp-specialised commit kernel itself (tops epilogue): that ONE launch also
+    carries the roots exchange, with whole-row units and with half-row units (roots of split rows made by the CTA that
+    arrives second)"""
+    import torch
+
+    from zinc_b200.dist import PeerRoots
+
+    code, row_len, num_rows, cw, p1, p2 = _code(22, KECCAK_SEEDS, oracle)
+    num_rows = 333
+    h = code.native(ctx, 1, 4)
+    evals = np.random.default_rng(5).integers(0, 1 << 64, size=num_rows * row_len, dtype=np.uint64)
+    dev = torch.device("cuda", ctx.device)
+    d_ev = torch.from_numpy(evals.view(np.int64)).to(dev)
+    depth = cw.bit_length() - 1
+    d_rows = torch.empty(num_rows * cw * 4, dtype=torch.int64, device=dev)
+    d_lay = torch.empty(num_rows * ((2 << depth) - 2) * 32, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("ZIPGPU_WS_UNITS", units)
+    monkeypatch.setenv("ZIPGPU_WS_TOPS", "1")
+    total = num_rows + 100  # the local rows are [100, 433) of a larger commitment
+    peer = PeerRoots(ctx, total)
+    rc, _, _, roots = oracle.commit_mt(evals, num_rows, row_len, 2, 0, 0, p1, p2, threads=8, faithful=False,
+                                       want_rows=False, want_layers=False)
+    assert rc == 0
+    for step in range(3):
+        l0 = ctx.launch_count
+        ptr = peer.commit_device(h, 100, num_rows, d_ev.data_ptr(), d_rows.data_ptr(), d_lay.data_ptr())
+        peer.sync()
+        assert ctx.launch_count - l0 == 1
+        got = peer.tensor(ptr).cpu().numpy()
+        assert got[100 * 32:].tobytes() == roots.tobytes(), step
     peer.close()
 
 

@@ -34,21 +34,155 @@
 // units cover.  The fused part then stops one or two tree levels lower (level log2(E / U)).
 #include <cstdlib>
 
+#include "peer_sync.cuh"
 #include "raa_common.cuh"
 
 namespace zipgpu {
 
 constexpr int kBarEnc = 1;  // named barrier of the ENC group
 
+
+// ---- the "tops" epilogue: whole trees in the one launch ----------------------------------------------------------------
+// When the main loops are done both thread groups of the CTA (2T threads, the ENC warps no longer idle) finish the trees
+// of the units this CTA hashed.  A unit left T nodes at level L0 = log2(E / U) in `layers`; eight units at a time:
+//   step A  every thread re-reads 4 consecutive nodes (128 bytes, L2 hits: this CTA wrote them) and reduces them by two
+//           levels in registers -- three quarters of all compressions above L0, at full occupancy and without a barrier;
+//   step B  the remaining log2(T) - 2 levels through a transposed digest buffer in the (now free) plane memory, one
+//           compression of latency and two barriers per level, all eight units side by side.
+// U = 2: a row is two units.  If both are this CTA's, one thread joins them; if the CTA boundary runs through the row,
+// each CTA publishes its half's root (level depth - 1, in `layers`), fences and bumps the boundary's counter -- the
+// one that arrives second finds the other half there and makes the root.
+// Replaces the 2-3 latency-bound passes of merkle.cu that otherwise follow (36 us of a 0.27 ms commit of 512 rows).
+struct WsTops {
+    uint8_t *roots;
+    uint32_t *pair_flags;
+    const RootsFanout *fan;
+    unsigned long long fan_step;
+    uint32_t fan_row_begin;
+};
+
+template <int T, int U>
+__device__ __forceinline__ void ws_tree_tops(uint32_t *sbuf, uint8_t *__restrict__ layers, const WsTops tp, uint32_t cw,
+                                          uint32_t L0, uint32_t depth, uint32_t num_rows, uint32_t u0, uint32_t u1,
+                                          uint32_t one) {
+    constexpr uint32_t Q = T / 4;        // nodes per unit after step A
+    constexpr uint32_t SB = 8 * Q + 8;   // words per digest word in sbuf
+    const uint32_t j = threadIdx.x;
+    const size_t row_stride = (2 * (size_t)cw - 2) * 32;
+    // units of this CTA, numbered q = 0 .. m-1
+    //   U == 1: rows blockIdx.x + q * gridDim.x;  U == 2: units ua + q, ua = u0 rounded down to even (q = 0 may be foreign)
+    const uint32_t ua = U == 1 ? 0u : (u0 & ~1u);
+    const uint32_t m = U == 1 ? (blockIdx.x < num_rows ? (num_rows - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u) : u1 - ua;
+#define UNIT_ROW(q) (U == 1 ? blockIdx.x + (q) * gridDim.x : (ua + (q)) >> 1)
+#define UNIT_HALF(q) (U == 1 ? 0u : (ua + (q)) & 1u)
+#define UNIT_OURS(q) ((q) < m && (U == 1 || ua + (q) >= u0))
+#define LEVEL_OFF(l) (2 * (size_t)cw - ((2 * (size_t)cw) >> (l)))  /* first digest of level l (l >= 1) */
+
+    for (uint32_t q0 = 0; q0 < m; q0 += 8) {
+        {   // ---- step A
+            const uint32_t b = j / Q, i4 = j % Q, q = q0 + b;
+            if (UNIT_OURS(q)) {
+                const uint32_t row = UNIT_ROW(q), half = UNIT_HALF(q);
+                uint8_t *lay_row = layers + (size_t)row * row_stride;
+                const uint32_t idx0 = half * T + 4 * i4;  // within level L0
+                const uint8_t *src = lay_row + (LEVEL_OFF(L0) + idx0) * 32;
+                if (L0 == 0) src = lay_row + (size_t)idx0 * 32;
+                b3::Digest n0, n1, c01, c23;
+                ld_global_v8_sync(src, n0.w);
+                ld_global_v8_sync(src + 32, n1.w);
+                c01 = b3::hash_node_call(n0, n1, one);
+                ld_global_v8_sync(src + 64, n0.w);
+                ld_global_v8_sync(src + 96, n1.w);
+                c23 = b3::hash_node_call(n0, n1, one);
+                uint8_t *d1 = lay_row + (LEVEL_OFF(L0 + 1) + (idx0 >> 1)) * 32;
+                st_global_v8(d1, c01.w);
+                st_global_v8(d1 + 32, c23.w);
+                n0 = b3::hash_node_call(c01, c23, one);
+                st_global_v8(lay_row + (LEVEL_OFF(L0 + 2) + (idx0 >> 2)) * 32, n0.w);
+#pragma unroll
+                for (int w = 0; w < 8; w++) sbuf[w * SB + b * Q + i4] = n0.w[w];
+            }
+        }
+        __syncthreads();
+        // ---- step B: n nodes per unit are produced at level l
+        uint32_t l = L0 + 3;
+        for (uint32_t n = Q / 2; n >= 1; n >>= 1, l++) {
+            const uint32_t b = j / n, i = j % n, q = q0 + b;
+            const bool act = b < 8 && UNIT_OURS(q);
+            b3::Digest o;
+            if (act) {
+                b3::Digest lft, rgt;
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    const uint2 v = *reinterpret_cast<const uint2 *>(&sbuf[w * SB + b * Q + 2 * i]);
+                    lft.w[w] = v.x;
+                    rgt.w[w] = v.y;
+                }
+                o = b3::hash_node_call(lft, rgt, one);
+            }
+            __syncthreads();
+            if (act) {
+                const uint32_t row = UNIT_ROW(q), half = UNIT_HALF(q);
+#pragma unroll
+                for (int w = 0; w < 8; w++) sbuf[w * SB + b * Q + i] = o.w[w];
+                if (l == depth) {  // (U == 1, n == 1) the root
+                    st_global_v8(tp.roots + (size_t)row * 32, o.w);
+                    if (tp.fan) fan_store_root(tp.fan, tp.fan_step, tp.fan_row_begin + row, o.w);
+                } else {
+                    st_global_v8(layers + (size_t)row * row_stride + (LEVEL_OFF(l) + half * n + i) * 32, o.w);
+                }
+            }
+            __syncthreads();
+        }
+        if constexpr (U == 2) {  // ---- the two unit roots of a row (level depth - 1; thread b stored the one of unit b)
+            if (j < 8 && UNIT_OURS(q0 + j)) {
+                const uint32_t q = q0 + j, row = UNIT_ROW(q), half = UNIT_HALF(q);
+                const bool sibling_here = half ? UNIT_OURS(q - 1) : UNIT_OURS(q + 1);  // q0 and ua are even: same batch
+                b3::Digest mine, other, root;
+                bool make = false;
+#pragma unroll
+                for (int w = 0; w < 8; w++) mine.w[w] = sbuf[w * SB + j * Q];
+                if (sibling_here) {
+                    if (half == 0) {
+#pragma unroll
+                        for (int w = 0; w < 8; w++) other.w[w] = sbuf[w * SB + (j + 1) * Q];
+                        make = true;
+                    }
+                } else {
+                    uint32_t *flag = tp.pair_flags + blockIdx.x + (half ? 0u : 1u);  // the boundary this row straddles
+                    __threadfence();  // this thread stored the half's root above
+                    if (atomicAdd(flag, 1u) == 1u) {
+                        __threadfence();
+                        ld_global_cg_v8(layers + (size_t)row * row_stride + (LEVEL_OFF(depth - 1) + (half ^ 1u)) * 32, other.w);
+                        *flag = 0u;  // re-armed for the next launch
+                        make = true;
+                    }
+                }
+                if (make) {
+                    root = half ? b3::hash_node_call(other, mine, one) : b3::hash_node_call(mine, other, one);
+                    st_global_v8(tp.roots + (size_t)row * 32, root.w);
+                    if (tp.fan) fan_store_root(tp.fan, tp.fan_step, tp.fan_row_begin + row, root.w);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tp.fan) fan_finish(tp.fan, tp.fan_step);
+#undef UNIT_ROW
+#undef UNIT_HALF
+#undef UNIT_OURS
+#undef LEVEL_OFF
+}
+
 // E entries per ENC thread, kWsEnc threads per group: (16, 512) = cw 8192, (8, 512) = cw 4096, (8, 256) = cw 2048,
 // (4, 256) = cw 1024, (4, 128) = cw 512 -- the (E, T) of the plain encoder for those shapes, so the same pre-translated
 // tables serve both kernels.  The 512-thread CTAs leave room for two CTAs per SM.
-template <int E, int kWsEnc, int U>
+template <int E, int kWsEnc, int U, bool TOPS>
 __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
     commit_ws_kernel(const uint32_t *__restrict__ evals, uint32_t *__restrict__ rows_out,
                      const uint16_t *__restrict__ tab1, const uint16_t *__restrict__ tab2,
                      const uint8_t *__restrict__ colw, uint32_t num_rows, uint8_t *__restrict__ layers, uint32_t one,
-                     uint32_t *__restrict__ row_counter) {
+                     uint32_t *__restrict__ row_counter, const WsTops tops) {
     constexpr int IN32 = 2, W = 3, OUT32 = 8;
     constexpr uint32_t T = kWsEnc, P = T * E, cw = P, in_words = (P / 2) * IN32;
     constexpr int EH = E / U;                   // entries per hash thread and unit
@@ -244,20 +378,42 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
             mbar_arrive(&s_empty[buf]);  // the plane set may be overwritten once all hash threads have said so
         }
     }
+    if constexpr (TOPS) {
+        __syncthreads();  // every unit of this CTA is hashed and its level-L0 nodes are in `layers`; the planes are free
+        constexpr int L0 = EH >= 16 ? 4 : EH >= 8 ? 3 : EH >= 4 ? 2 : 1;
+        uint32_t depth = 0;
+        while ((1u << depth) < cw) depth++;
+        ws_tree_tops<kWsEnc, U>(planes, layers, tops, cw, (uint32_t)L0, depth, num_rows, u0, u1, one);
+    }
 }
 
 namespace {
 
-template <int E, int TENC, int U>
+// Rows up to which the fused launch also finishes the trees (ZIPGPU_WS_TOPS_MAX_ROWS; ZIPGPU_WS_TOPS=0 disables, =1 forces
+// it for every shape).  Measured on B200 (scripts/shard_sweep.py, ms per commit, tops / separate passes):
+//   cw = 8192: 128 rows 0.093 / 0.096, 256: 0.161 / 0.165, 512: 0.2645 / 0.2742, 1024: 0.497 / 0.510, 2048: 0.971 / 0.977,
+//              3072: 1.447 / 1.450, 4096: 1.936 / 1.927;   cw = 4096: 384 rows 0.124 / 0.130, 1536: 0.399 / 0.404, 3072: equal.
+// A batch of 8 units costs the epilogue ~22 us (15 us of alu work + the latency of the narrow levels), the separate passes
+// ~36 us at 512 rows but, being spread over the whole GPU at full occupancy, no more than the epilogue from ~3000 rows.
+// The two-CTA-per-SM variants (cw <= 2048) have too few units per CTA to fill a batch and measured equal or slower
+// (cw = 2048: 1024 rows 0.164 / 0.152): they keep the separate passes.
+static uint32_t ws_tops_max_rows() {
+    const char *e = getenv("ZIPGPU_WS_TOPS_MAX_ROWS");
+    return e ? (uint32_t)atol(e) : 2048u;
+}
+
+template <int E, int TENC, int U, bool TOPS>
 cudaError_t launch_ws_u(const EncodeArgs &a, uint32_t grid) {
     const size_t ws_smem = (2 * 3 * (size_t)(E * TENC) + 64 * 3 + (TENC / 32) * 256) * sizeof(uint32_t);
-    auto kern = commit_ws_kernel<E, TENC, U>;
+    static_assert(!TOPS || 8 * (8 * (TENC / 4) + 8) <= 2 * 3 * E * TENC, "the digest buffer of the tops fits in the planes");
+    auto kern = commit_ws_kernel<E, TENC, U, TOPS>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem);
     if (err != cudaSuccess) return err;
     uint32_t *row_counter = nullptr;
     if (U == 1) {
         if (grid > a.num_rows) grid = a.num_rows;
-        row_counter = a.num_rows >= 2 * grid ? a.row_counter : nullptr;
+        // (the tops need to know a CTA's rows afterwards: static striding)
+        row_counter = !TOPS && a.num_rows >= 2 * grid ? a.row_counter : nullptr;
         if (row_counter) {
             err = cudaMemsetAsync(row_counter, 0xff, 2 * sizeof(uint32_t), a.stream);
             if (err != cudaSuccess) return err;
@@ -266,8 +422,16 @@ cudaError_t launch_ws_u(const EncodeArgs &a, uint32_t grid) {
         const uint32_t units = a.num_rows * U;
         if (grid > units) grid = units;
     }
+    WsTops tp{};
+    if (TOPS) {
+        tp.roots = a.tops_roots;
+        tp.pair_flags = a.pair_flags;
+        tp.fan = a.fan;
+        tp.fan_step = a.fan_step;
+        tp.fan_row_begin = a.fan_row_begin;
+    }
     kern<<<grid, 2 * TENC, ws_smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows, a.fuse_layers, 1u,
-                                                row_counter);
+                                                row_counter, tp);
     return cudaGetLastError();
 }
 
@@ -282,11 +446,20 @@ cudaError_t launch_ws(const EncodeArgs &a, int *fused_levels) {
     int U = 1;
     if (TENC == 512 && a.num_rows >= 3 * grid && a.num_rows < 6 * grid) U = 2;
     if (const char *env = getenv("ZIPGPU_WS_UNITS")) U = atoi(env) >= 2 ? 2 : 1;
+    // whole trees in this launch: when the caller wants the roots and has a boundary-flag array for split rows
+    const bool tops_ok = a.tops_roots != nullptr && a.pair_flags != nullptr && grid + 1 <= 512;
+    bool tops = tops_ok && TENC == 512 && a.num_rows <= ws_tops_max_rows();
+    if (const char *env = getenv("ZIPGPU_WS_TOPS")) tops = tops_ok && env[0] != '0';
     int h = 0;
     while ((1 << h) < E / U) h++;
+    if (tops) {
+        h = 0;
+        while ((1u << h) < a.cw) h++;
+    }
     if (fused_levels) *fused_levels = h;
-    if (U == 2) return launch_ws_u<E, TENC, 2>(a, grid);
-    return launch_ws_u<E, TENC, 1>(a, grid);
+    if (a.fan_fused) *a.fan_fused = tops && a.fan != nullptr;
+    if (tops) return U == 2 ? launch_ws_u<E, TENC, 2, true>(a, grid) : launch_ws_u<E, TENC, 1, true>(a, grid);
+    return U == 2 ? launch_ws_u<E, TENC, 2, false>(a, grid) : launch_ws_u<E, TENC, 1, false>(a, grid);
 }
 
 }  // namespace

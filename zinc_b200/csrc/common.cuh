@@ -107,6 +107,20 @@ __device__ __forceinline__ void ld_global_v8(const void *p, uint32_t (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "l"(p));
 }
+// ordered forms: not moved across barriers / fences by the compiler.  _sync: data written earlier by this CTA;
+// _cg: data written by another CTA (L2, bypassing the L1 of this SM)
+__device__ __forceinline__ void ld_global_v8_sync(const void *p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_cg_v8(const void *p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p)
+                 : "memory");
+}
 __device__ __forceinline__ void ld_stream_v8(const void *p, uint32_t (&v)[8]) {
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])

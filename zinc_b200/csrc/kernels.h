@@ -6,6 +6,8 @@
 
 namespace zipgpu {
 
+struct RootsFanout;
+
 // ---- K1: RAA encoder (raa_encode.cu) ----
 struct EncodeArgs {
     const uint32_t *evals;   // [num_rows][row_len][2*in_limbs]
@@ -23,6 +25,15 @@ struct EncodeArgs {
     uint8_t *fuse_layers = nullptr;  // non-NULL: the fused commit kernel also writes the lowest Merkle levels
     int *fused_levels_out = nullptr; // receives the level up to which that launch builds the trees (<= encode_fused_levels():
                                      // the warp-specialised kernel stops 1 or 2 levels lower when it hashes sub-row units)
+    // Whole trees in the fused launch (commit_ws.cu, "tops" epilogue): non-NULL tops_roots asks the warp-specialised
+    // kernel to finish the trees of the rows it hashed and write their roots here; if it does, *fused_levels_out = depth.
+    // With `fan` the same launch also carries the multi-GPU roots exchange (see RootsFanout), *fan_fused reports it.
+    uint8_t *tops_roots = nullptr;
+    uint32_t *pair_flags = nullptr;  // zeroed device words, one per CTA boundary (rows hashed as two units by two CTAs)
+    const RootsFanout *fan = nullptr;
+    unsigned long long fan_step = 0;
+    uint32_t fan_row_begin = 0;
+    bool *fan_fused = nullptr;
     cudaStream_t stream;
 };
 // the warp-specialised commit kernel (commit_ws.cu) for the encoder configuration (E, T) of an exact Int<1> -> Int<4> shape

@@ -46,6 +46,8 @@ struct CachedBuf {
     cudaStream_t last = nullptr;  // the stream `ready` was recorded on: a reuse on the same stream needs no wait
 };
 
+constexpr size_t kPairFlagRing = 64, kPairFlagWords = 512;  // one array per fused launch in flight, one word per CTA boundary
+
 struct zipgpu_ctx {
     std::vector<CachedBuf> cache_free;
     std::vector<CachedBuf> cache_live;
@@ -69,6 +71,8 @@ struct zipgpu_ctx {
     uint32_t *d_sink = nullptr;
     uint32_t *d_row_counters = nullptr;  // ring of row-claim counters, one per encoder launch in flight
     size_t row_counter_pos = 0;
+    uint32_t *d_pair_flags = nullptr;    // ring of zeroed boundary-flag arrays for the tops epilogue of commit_ws_kernel
+    size_t pair_flags_pos = 0;
     std::mutex mu;
     // Public entry points serialise on this (recursive: some call each other), so several host threads may share one
     // context; their jobs are then enqueued one after the other on the context's streams.
@@ -309,7 +313,9 @@ extern "C" int zipgpu_ctx_create(int device, zipgpu_ctx **out) {
             return cuda_fail(e, "cudaEventCreate");
         }
     }
-    if ((e = cudaMalloc(&c->d_row_counters, 2 * 256 * sizeof(uint32_t))) != cudaSuccess ||
+    if ((e = cudaMalloc(&c->d_pair_flags, kPairFlagRing * kPairFlagWords * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMemset(c->d_pair_flags, 0, kPairFlagRing * kPairFlagWords * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_row_counters, 2 * 256 * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&c->d_sink, 256)) != cudaSuccess) {
         zipgpu_ctx_destroy(c);
         return cuda_fail(e, "cudaMalloc");
@@ -330,6 +336,7 @@ extern "C" void zipgpu_ctx_destroy(zipgpu_ctx *c) {
     for (auto &b : c->cache_live) { cudaFree(b.p); cudaEventDestroy(b.ready); }
     if (c->d_sink) cudaFree(c->d_sink);
     if (c->d_row_counters) cudaFree(c->d_row_counters);
+    if (c->d_pair_flags) cudaFree(c->d_pair_flags);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream_hi) cudaStreamDestroy(c->stream_hi);
@@ -846,7 +853,8 @@ struct FanReq {
 };
 
 static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_evals, uint64_t *d_rows, cudaStream_t s,
-                      uint8_t *fuse_layers = nullptr, uint64_t *evals_copy = nullptr, int *fused_levels = nullptr) {
+                      uint8_t *fuse_layers = nullptr, uint64_t *evals_copy = nullptr, int *fused_levels = nullptr,
+                      uint8_t *tops_roots = nullptr, FanReq *fan = nullptr) {
     if (num_rows == 0) return ZIPGPU_OK;
     if (num_rows > 0xffffffffull) return fail(ZIPGPU_ERR_UNSUPPORTED, "too many rows");
     int rc;
@@ -923,10 +931,25 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     if (!getenv("ZIPGPU_STATIC_ROWS")) {
         a.row_counter = code->ctx->d_row_counters + 2 * (code->ctx->row_counter_pos++ % 256);
     }
+    bool fan_fused = false;
+    if (tops_roots && fuse_layers) {  // the warp-specialised kernel may finish the trees (and carry the roots exchange)
+        a.tops_roots = tops_roots;
+        a.pair_flags = code->ctx->d_pair_flags + kPairFlagWords * (code->ctx->pair_flags_pos++ % kPairFlagRing);
+        if (fan && !fan->fused) {
+            a.fan = fan->pr->d_fan;
+            a.fan_step = fan->pr->step + 1;
+            a.fan_row_begin = (uint32_t)fan->row_begin;
+            a.fan_fused = &fan_fused;
+        }
+    }
     a.stream = s;
     cudaError_t e = launch_raa_encode(a);
     if (e != cudaSuccess) return cuda_fail(e, "launch_raa_encode");
     code->ctx->launches++;
+    if (fan_fused) {  // the exchange of this step is in flight
+        fan->fused = true;
+        fan->pr->step++;
+    }
     return ZIPGPU_OK;
 }
 
@@ -1058,7 +1081,10 @@ static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
         return ZIPGPU_OK;
     }
     int fused_levels = code->fused_levels;  // the launch reports how far it really built the trees (sub-row units stop lower)
-    int rc = encode_dev(code, num_rows, d_evals, d_rows, s, fuse ? d_layers : nullptr, evals_copy, &fused_levels);
+    // (whole trees in the fused launch only when this call goes all the way to the roots)
+    uint8_t *tops_roots = fuse && d_roots && d_layers && until_level < 0 ? d_roots : nullptr;
+    int rc = encode_dev(code, num_rows, d_evals, d_rows, s, fuse ? d_layers : nullptr, evals_copy, &fused_levels, tops_roots,
+                        fan);
     if (rc) return rc;
     if (prof) {
         cudaEventRecord(r.e1, s);
