@@ -363,8 +363,8 @@ def test_warp_specialised_commit_kernel_sub_row_units(row_len, num_rows, units, 
 
 
 @pytest.mark.parametrize("units", [1, 2])
-@pytest.mark.parametrize("row_len,num_rows", [(4096, 1), (4096, 149), (4096, 517), (4096, 1400), (2048, 523), (2048, 2901),
-                                              (1024, 97), (1024, 3000), (512, 611), (256, 59), (256, 5000)])
+@pytest.mark.parametrize("row_len,num_rows", [(4096, 1), (4096, 149), (4096, 517), (4096, 1400), (2048, 523), (2048, 2300),
+                                              (1024, 97), (1024, 3000), (512, 611), (256, 59), (256, 4500)])
 def test_warp_specialised_commit_kernel_tree_tops(row_len, num_rows, units, oracle, ctx, monkeypatch):
     """whole trees in the one launch: the epilogue of the warp-specialised commit kernel that finishes the trees of the
     units a CTA hashed (4 nodes per thread in registers, then level by level through shared memory; rows whose two

@@ -32,6 +32,7 @@
 // split evenly and statically over the CTAs.  A row whose units fall into two CTAs is encoded by both (encoding is a
 // tenth of the hashing and runs in the otherwise idle ENC warps); each writes out only the part of the codeword its
 // units cover.  The fused part then stops one or two tree levels lower (level log2(E / U)).
+#include <algorithm>
 #include <cstdlib>
 
 #include "peer_sync.cuh"
@@ -61,19 +62,22 @@ struct WsTops {
     uint32_t fan_row_begin;
 };
 
+constexpr uint32_t kTopsMaxRowsPerCta = 64;  // U == 1: rows a CTA may take when it also finishes their trees
+
 template <int T, int U>
 __device__ __forceinline__ void ws_tree_tops(uint32_t *sbuf, uint8_t *__restrict__ layers, const WsTops tp, uint32_t cw,
-                                          uint32_t L0, uint32_t depth, uint32_t num_rows, uint32_t u0, uint32_t u1,
-                                          uint32_t one) {
+                                          uint32_t L0, uint32_t depth, const volatile uint32_t *row_list, uint32_t row_count,
+                                          uint32_t u0, uint32_t u1, uint32_t one) {
     constexpr uint32_t Q = T / 4;        // nodes per unit after step A
     constexpr uint32_t SB = 8 * Q + 8;   // words per digest word in sbuf
     const uint32_t j = threadIdx.x;
     const size_t row_stride = (2 * (size_t)cw - 2) * 32;
     // units of this CTA, numbered q = 0 .. m-1
-    //   U == 1: rows blockIdx.x + q * gridDim.x;  U == 2: units ua + q, ua = u0 rounded down to even (q = 0 may be foreign)
+    //   U == 1: the rows this CTA took, in the order it took them (row_list, written by the ENC group);
+    //   U == 2: units ua + q, ua = u0 rounded down to even (q = 0 may be foreign)
     const uint32_t ua = U == 1 ? 0u : (u0 & ~1u);
-    const uint32_t m = U == 1 ? (blockIdx.x < num_rows ? (num_rows - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u) : u1 - ua;
-#define UNIT_ROW(q) (U == 1 ? blockIdx.x + (q) * gridDim.x : (ua + (q)) >> 1)
+    const uint32_t m = U == 1 ? row_count : u1 - ua;
+#define UNIT_ROW(q) (U == 1 ? row_list[(q)] : (ua + (q)) >> 1)
 #define UNIT_HALF(q) (U == 1 ? 0u : (ua + (q)) & 1u)
 #define UNIT_OURS(q) ((q) < m && (U == 1 || ua + (q) >= u0))
 #define LEVEL_OFF(l) (2 * (size_t)cw - ((2 * (size_t)cw) >> (l)))  /* first digest of level l (l >= 1) */
@@ -197,6 +201,8 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
     __shared__ volatile uint32_t s_row[2];      // row parked in each plane set (0xffffffff: no more rows)
     __shared__ volatile uint32_t s_next;
     __shared__ unsigned long long s_full[2], s_empty[2];  // mbarriers: plane set parked / plane set free again
+    __shared__ volatile uint32_t s_list[TOPS && U == 1 ? kTopsMaxRowsPerCta : 1];  // TOPS: the rows this CTA took
+    __shared__ volatile uint32_t s_count;
     const uint32_t tid = threadIdx.x;
     const uint32_t t = tid & (kWsEnc - 1);      // index within the group
     // U > 1: this CTA's static share of the num_rows * U units
@@ -231,7 +237,17 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
                 EncBar::sync();
             }
             uint32_t early = U == 1 ? row + gridDim.x : row + 1;
-            if (U == 1 && t == 0 && row_counter) early = gridDim.x + atomicAdd(row_counter, 1u) + 1u;
+            if constexpr (TOPS && U == 1) {
+                // the epilogue needs the rows afterwards; a CTA whose list is full takes no more (the others do: the
+                // launcher makes sure the lists of all CTAs together hold every row several times over)
+                if (t == 0) {
+                    s_list[it] = row;
+                    if (it + 1 >= kTopsMaxRowsPerCta) early = 0xffffffffu;
+                    else if (row_counter) early = gridDim.x + atomicAdd(row_counter, 1u) + 1u;
+                }
+            } else {
+                if (U == 1 && t == 0 && row_counter) early = gridDim.x + atomicAdd(row_counter, 1u) + 1u;
+            }
             {
                 WarpStage<IN32, E> ws;
                 ws.load(evals + (size_t)row * in_words, t);
@@ -313,7 +329,10 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
         {   // no more rows: tell the hash warps through the next plane set
             const uint32_t buf = it & 1u;
             if (it >= 2) mbar_wait(&s_empty[buf], ((it >> 1) & 1u) ^ 1u);
-            if (t == 0) s_row[buf] = 0xffffffffu;
+            if (t == 0) {
+                s_row[buf] = 0xffffffffu;
+                if constexpr (TOPS) s_count = it;
+            }
             mbar_arrive(&s_full[buf]);
         }
         if (lane == 0) bulk_wait_all();
@@ -383,7 +402,7 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
         constexpr int L0 = EH >= 16 ? 4 : EH >= 8 ? 3 : EH >= 4 ? 2 : 1;
         uint32_t depth = 0;
         while ((1u << depth) < cw) depth++;
-        ws_tree_tops<kWsEnc, U>(planes, layers, tops, cw, (uint32_t)L0, depth, num_rows, u0, u1, one);
+        ws_tree_tops<kWsEnc, U>(planes, layers, tops, cw, (uint32_t)L0, depth, s_list, s_count, u0, u1, one);
     }
 }
 
@@ -391,12 +410,12 @@ namespace {
 
 // Rows up to which the fused launch also finishes the trees (ZIPGPU_WS_TOPS_MAX_ROWS; ZIPGPU_WS_TOPS=0 disables, =1 forces
 // it for every shape).  Measured on B200 (scripts/shard_sweep.py, ms per commit, tops / separate passes):
-//   cw = 8192: 128 rows 0.093 / 0.096, 256: 0.161 / 0.165, 512: 0.2645 / 0.2742, 1024: 0.497 / 0.510, 2048: 0.971 / 0.977,
-//              3072: 1.447 / 1.450, 4096: 1.936 / 1.927;   cw = 4096: 384 rows 0.124 / 0.130, 1536: 0.399 / 0.404, 3072: equal.
+//   cw = 8192: 256 rows 0.161 / 0.164, 512: 0.263 / 0.273, 1024: 0.4995 / 0.508, 2048: 0.9755 / 0.978, 4096: 1.936 / 1.927
+//   cw = 4096: 256 rows 0.091 / 0.094, 512: 0.144 / 0.154, 1024: 0.260 / 0.269, 2048: 0.504 / 0.505
 // A batch of 8 units costs the epilogue ~22 us (15 us of alu work + the latency of the narrow levels), the separate passes
 // ~36 us at 512 rows but, being spread over the whole GPU at full occupancy, no more than the epilogue from ~3000 rows.
-// The two-CTA-per-SM variants (cw <= 2048) have too few units per CTA to fill a batch and measured equal or slower
-// (cw = 2048: 1024 rows 0.164 / 0.152): they keep the separate passes.
+// The two-CTA-per-SM variants (cw <= 2048) gain 1-2 % up to ~3.5 rows per CTA and lose 5 % at 7 (cw = 2048: 1024 rows
+// 0.149 / 0.151, 2048 rows 0.286 / 0.271): they keep the separate passes.
 static uint32_t ws_tops_max_rows() {
     const char *e = getenv("ZIPGPU_WS_TOPS_MAX_ROWS");
     return e ? (uint32_t)atol(e) : 2048u;
@@ -412,8 +431,7 @@ cudaError_t launch_ws_u(const EncodeArgs &a, uint32_t grid) {
     uint32_t *row_counter = nullptr;
     if (U == 1) {
         if (grid > a.num_rows) grid = a.num_rows;
-        // (the tops need to know a CTA's rows afterwards: static striding)
-        row_counter = !TOPS && a.num_rows >= 2 * grid ? a.row_counter : nullptr;
+        row_counter = a.num_rows >= 2 * grid ? a.row_counter : nullptr;
         if (row_counter) {
             err = cudaMemsetAsync(row_counter, 0xff, 2 * sizeof(uint32_t), a.stream);
             if (err != cudaSuccess) return err;
@@ -447,7 +465,9 @@ cudaError_t launch_ws(const EncodeArgs &a, int *fused_levels) {
     if (TENC == 512 && a.num_rows >= 3 * grid && a.num_rows < 6 * grid) U = 2;
     if (const char *env = getenv("ZIPGPU_WS_UNITS")) U = atoi(env) >= 2 ? 2 : 1;
     // whole trees in this launch: when the caller wants the roots and has a boundary-flag array for split rows
-    const bool tops_ok = a.tops_roots != nullptr && a.pair_flags != nullptr && grid + 1 <= 512;
+    // (U == 1: a CTA lists at most kTopsMaxRowsPerCta rows; keep the total capacity at 4x the rows or more)
+    const bool tops_ok = a.tops_roots != nullptr && a.pair_flags != nullptr && grid + 1 <= 512 &&
+                         (U == 2 || (uint64_t)a.num_rows * 4 <= (uint64_t)std::min(grid, a.num_rows) * kTopsMaxRowsPerCta);
     bool tops = tops_ok && TENC == 512 && a.num_rows <= ws_tops_max_rows();
     if (const char *env = getenv("ZIPGPU_WS_TOPS")) tops = tops_ok && env[0] != '0';
     int h = 0;
