@@ -222,6 +222,27 @@ def run_reference_arm(args, rank: int, world: int):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
+_HOST_BLOCKS = []  # zipgpu_host_alloc blocks stay alive for the life of the process
+
+
+def host_tensor(n, dtype):
+    """a torch CPU tensor of n elements over zipgpu_host_alloc memory: pinned AND backed by 2 MiB pages where the OS
+    grants them.  (torch's pin_memory() blocks were, on some boxes and depending on what the process had allocated
+    before, fed to the GPU at half the PCIe rate: nv = 20 host-to-host 0.55 instead of 0.26 ms.)"""
+    import ctypes as C
+
+    import torch
+
+    from zinc_b200 import _native as nat
+
+    item = torch.empty(0, dtype=dtype).element_size()
+    p = C.c_void_p()
+    nat.check(nat.lib().zipgpu_host_alloc(max(n * item, 1), C.byref(p)))
+    _HOST_BLOCKS.append(p)
+    buf = (C.c_uint8 * max(n * item, 1)).from_address(p.value)
+    return torch.frombuffer(buf, dtype=dtype, count=n)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -293,7 +314,7 @@ def main():
     begin, count = shard_range(num_rows, rank, world)
     evals_h = gen_evals(nv)  # the same MLE on every rank
     my_evals = evals_h[begin * row_len:(begin + count) * row_len]
-    pinned = torch.empty(max(my_evals.size, 1), dtype=torch.int64).pin_memory()
+    pinned = host_tensor(max(my_evals.size, 1), torch.int64)
     pinned.numpy().view(np.uint64)[: my_evals.size] = my_evals
     d_evals = pinned.to(dev, non_blocking=False)
     d_rows = torch.empty(max(count, 1) * cw * 4, dtype=torch.int64, device=dev)
@@ -374,7 +395,7 @@ def main():
 
     # ---- e2e leg: host buffers through the C ABI (pinned H2D of this rank's evaluations + D2H of ALL roots inside the
     #      timed region) ----
-    roots_h = torch.empty(num_rows * 32, dtype=torch.uint8).pin_memory()
+    roots_h = host_tensor(num_rows * 32, torch.uint8)
 
     def step_e2e():
         h = C.c_void_p()
@@ -631,8 +652,9 @@ def single_gpu_extras(args, ctx, L, nat, C, torch, dev, stream, sptr, make_code,
                 sizes[f"nv{snv}"] = o
                 if snv == 20:
                     # BASELINE configs[1]: commit 2^20 on one B200, through the host API as well
-                    ev_pin = torch.from_numpy(gen_evals(snv).view(np.int64)).pin_memory()
-                    roots_pin = torch.empty(snr * 32, dtype=torch.uint8).pin_memory()
+                    ev_pin = host_tensor(1 << snv, torch.int64)
+                    ev_pin.numpy()[:] = gen_evals(snv).view(np.int64)
+                    roots_pin = host_tensor(snr * 32, torch.uint8)
 
                     def host_call():
                         hd = C.c_void_p()
@@ -654,8 +676,10 @@ def single_gpu_extras(args, ctx, L, nat, C, torch, dev, stream, sptr, make_code,
             bnv, npoly = 18, 64
             brl, bnr, bcw = shape_for(bnv)
             _, bhc = make_code(bcw, brl)
-            polys = [torch.from_numpy(gen_evals(bnv, 100 + i).view(np.int64)).pin_memory() for i in range(npoly)]
-            broots = [torch.empty(bnr * 32, dtype=torch.uint8).pin_memory() for _ in range(npoly)]
+            polys = [host_tensor(1 << bnv, torch.int64) for _ in range(npoly)]
+            for i, pt in enumerate(polys):
+                pt.numpy()[:] = gen_evals(bnv, 100 + i).view(np.int64)
+            broots = [host_tensor(bnr * 32, torch.uint8) for _ in range(npoly)]
             ev_arr = (C.c_void_p * npoly)(*[p.data_ptr() for p in polys])
             rt_arr = (C.c_void_p * npoly)(*[r.data_ptr() for r in broots])
             bc = lambda: nat.check(L.zipgpu_batch_commit(bhc, npoly, bnr, ev_arr, None, None, rt_arr))
@@ -681,12 +705,12 @@ def single_gpu_extras(args, ctx, L, nat, C, torch, dev, stream, sptr, make_code,
         # ---- f-1 / f-2: column openings (1000 columns, num_column_opening) and combine_rows on the resident data ----
         try:
             hd = C.c_void_p()
-            roots_tmp = torch.empty(num_rows * 32, dtype=torch.uint8).pin_memory()
+            roots_tmp = host_tensor(num_rows * 32, torch.uint8)
             nat.check(L.zipgpu_commit_resident(hcode, num_rows, pinned.data_ptr(), roots_tmp.data_ptr(), C.byref(hd)))
             ncols = 1000
             cols = np.random.default_rng(1).integers(0, cw, size=ncols, dtype=np.uint32)
             per = int(L.zipgpu_data_open_columns_wire_bytes(hd))
-            wire = torch.empty(ncols * per, dtype=torch.uint8).pin_memory()
+            wire = host_tensor(ncols * per, torch.uint8)
             ow = lambda: nat.check(L.zipgpu_data_open_columns_wire(hd, ncols, nat.ptr(cols), wire.data_ptr()))
             ow_ms = wall_ms(ow, 3, 1, 1)
             configs["open_columns_1000"] = {
@@ -773,7 +797,7 @@ def prover_flow(ctx, args):
             t3 = time.perf_counter()
             cw = code.codeword_len()
             cols = np.random.default_rng(rep).integers(0, cw, size=1000, dtype=np.uint32)
-            wire = data.open_columns_wire(cols)
+            wire = data.open_columns_wire_view(cols)  # proof-stream bytes in the context's pinned stream buffer
             t4 = time.perf_counter()
             co = np.random.default_rng(rep + 1).integers(0, 1 << 64, size=pp.num_rows, dtype=np.uint64)
             data.combine_rows(co, 8)
@@ -842,8 +866,9 @@ def reference_shapes(args, ctx, L, nat, C, torch, dev, stream, sptr, make_code, 
             ref_shapes["EncodeRows"][f"2^{P_}"] = {"gpu_ms": g_enc}
             ref_shapes["Commit"][f"2^{P_}"] = {"gpu_ms": g_com}
             # the call a host makes: pinned host evaluations in, host roots out, prover data resident
-            ev_pin = torch.from_numpy(ev_h.view(np.int64)).pin_memory()
-            roots_pin = torch.empty(nr * 32, dtype=torch.uint8).pin_memory()
+            ev_pin = host_tensor(ev_h.size, torch.int64)
+            ev_pin.numpy()[:] = ev_h.view(np.int64)
+            roots_pin = host_tensor(nr * 32, torch.uint8)
 
             def host_call():
                 hd = C.c_void_p()

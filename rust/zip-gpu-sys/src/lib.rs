@@ -29,6 +29,9 @@ unsafe extern "C" {
     pub fn zipgpu_device_count(count: *mut c_int) -> c_int;
     pub fn zipgpu_ctx_create(device: c_int, out: *mut *mut zipgpu_ctx) -> c_int;
     pub fn zipgpu_ctx_destroy(ctx: *mut zipgpu_ctx);
+    // pinned, huge-page-backed host memory for evaluations / proof streams (include/zipgpu.h)
+    pub fn zipgpu_host_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn zipgpu_host_free(p: *mut c_void) -> c_int;
     pub fn zipgpu_host_register(p: *mut c_void, bytes: usize) -> c_int;
     pub fn zipgpu_host_unregister(p: *mut c_void) -> c_int;
     // RaaCode (code_raa.rs:35-86): per-pp state, permutations uploaded once

@@ -290,6 +290,12 @@ def test_open_columns_wire_format(oracle, ctx):
             expect += depth.to_bytes(8, "big") + paths[ci, r].tobytes()
     got = res.open_columns_wire(cols)
     assert len(got) == len(expect) and got == expect
+    # the same bytes as a view of the context's pinned proof-stream buffer (reused and grown across calls)
+    view = res.open_columns_wire_view(cols[:2])
+    assert view.tobytes() == expect[:len(expect) // 2]
+    view = res.open_columns_wire_view(np.concatenate([cols] * 300))
+    assert view.size == 300 * len(expect) and view[-len(expect):].tobytes() == expect
+    assert res.open_columns_wire_view(np.zeros(0, dtype=np.uint32)).size == 0
     res.free()
 
 

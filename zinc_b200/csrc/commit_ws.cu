@@ -484,6 +484,13 @@ cudaError_t launch_ws(const EncodeArgs &a, int *fused_levels) {
 
 }  // namespace
 
+// the dispatch rule of launch_ws for callers that plan around it (the chunked host pipeline): does a commit of `rows`
+// rows of this shape finish its trees in the fused launch?
+bool commit_ws_whole_trees(uint32_t cw, uint32_t rows) {
+    if (const char *env = getenv("ZIPGPU_WS_TOPS")) return env[0] != '0';
+    return (cw == 4096 || cw == 8192) && rows <= ws_tops_max_rows();
+}
+
 bool commit_ws_supported(int E, int T) {
     return (E == 16 && T == 512) || (E == 8 && T == 512) || (E == 8 && T == 256) || (E == 4 && T == 256) ||
            (E == 4 && T == 128);

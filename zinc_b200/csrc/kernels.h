@@ -42,6 +42,7 @@ bool commit_ws16k_supported(uint32_t row_len, uint32_t cw);
 int commit_ws16k_levels();
 cudaError_t launch_commit_ws16k(const EncodeArgs &a);
 bool commit_ws_supported(int E, int T);
+bool commit_ws_whole_trees(uint32_t cw, uint32_t rows);
 cudaError_t launch_commit_ws(const EncodeArgs &a, int E, int T, int *fused_levels);
 int encode_fused_levels(int in_limbs, int out_limbs, uint32_t row_len, uint32_t cw);
 size_t encode_perm_padded_len(uint32_t cw);

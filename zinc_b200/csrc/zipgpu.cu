@@ -4,6 +4,8 @@
 // Host-pointer entry points split the rows into chunks and run  H2D(chunk k+1) || kernels(chunk k) || D2H(chunk k-1)
 // on three streams, so that the PCIe copies of a commit hide behind the hashing.  Device buffers are recycled by a
 // per-context cache (dev_alloc/dev_free), so steady-state calls never reach cudaMalloc.
+#include <map>
+#include <sys/mman.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -367,13 +369,61 @@ static int sync_job(zipgpu_ctx *c) {
     return ZIPGPU_OK;
 }
 
+// Pinned host memory for evaluations / roots / proof streams.  The DMA rate of a pinned buffer depends on what backs it:
+// measured on the B200 box (a VM behind an IOMMU), an 8 MiB buffer that cudaHostAlloc carved out of a fragmented
+// process (4 KiB pages) fed the GPU at 20-27 GB/s, one backed by 2 MiB pages at 46-55 GB/s -- the nv = 20 host-to-host
+// commit took 0.55 vs 0.26 ms.  So: a 2 MiB-aligned anonymous mapping with transparent huge pages requested,
+// pre-faulted, then page-locked (cudaHostRegister); cudaHostAlloc only as the fallback (ZIPGPU_HOST_ALLOC_PLAIN=1
+// forces it).
+namespace {
+struct HostBlock { void *map; size_t map_len, len; bool registered; };
+std::mutex g_host_mu;
+std::map<void *, HostBlock> g_host_blocks;
+}  // namespace
+
 extern "C" int zipgpu_host_alloc(size_t bytes, void **out) {
     if (!out) return fail(ZIPGPU_ERR_INVALID, "out is NULL");
-    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    *out = nullptr;
+    constexpr size_t kHuge = (size_t)2 << 20;
+    static const bool plain = getenv("ZIPGPU_HOST_ALLOC_PLAIN") != nullptr;
+    if (!plain && bytes >= kHuge) {
+        const size_t len = (bytes + kHuge - 1) & ~(kHuge - 1), map_len = len + kHuge;
+        void *map = mmap(nullptr, map_len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (map != MAP_FAILED) {
+            void *p = (void *)(((uintptr_t)map + kHuge - 1) & ~(uintptr_t)(kHuge - 1));
+            madvise(p, len, MADV_HUGEPAGE);  // advisory: without THP this is an ordinary pre-faulted pinned mapping
+            for (size_t off = 0; off < len; off += 4096) ((volatile char *)p)[off] = 0;
+            if (cudaHostRegister(p, len, cudaHostRegisterPortable) == cudaSuccess) {
+                std::lock_guard<std::mutex> lk(g_host_mu);
+                g_host_blocks[p] = HostBlock{map, map_len, len, true};
+                *out = p;
+                return ZIPGPU_OK;
+            }
+            cudaGetLastError();
+            munmap(map, map_len);
+        }
+    }
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
     if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
     return ZIPGPU_OK;
 }
 extern "C" int zipgpu_host_free(void *p) {
+    if (!p) return ZIPGPU_OK;
+    HostBlock b{};
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        auto it = g_host_blocks.find(p);
+        if (it != g_host_blocks.end()) {
+            b = it->second;
+            g_host_blocks.erase(it);
+        }
+    }
+    if (b.map) {
+        cudaError_t e = cudaHostUnregister(p);
+        munmap(b.map, b.map_len);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaHostUnregister");
+        return ZIPGPU_OK;
+    }
     CU(cudaFreeHost(p));
     return ZIPGPU_OK;
 }
@@ -1303,7 +1353,14 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
     size_t chunk_no = 0;
 
     // Per chunk the trees are taken to the first pass boundary >= level 6 (the wide passes); the rest is deferred.
-    const bool defer_top = merkle && !job.layers_out && sched.size() > 1 && code->depth > 7;
+    // ... unless the fused launch of a chunk finishes its trees anyway (commit_ws_kernel's tops epilogue, cw 4096 / 8192):
+    // then nothing is left after the last chunk but its own launch (nv = 24 e2e 2.70 -> 2.67 ms, nv = 22 0.777 -> 0.753)
+    const bool chunk_whole_trees = code->in_limbs == 1 && code->out_limbs == 4 && !code->sparse && !code->big &&
+                                   fusion_enabled() && chunk >= fuse_min_rows(ctx, code) &&
+                                   commit_ws_whole_trees((uint32_t)code->cw, (uint32_t)chunk);
+    static const bool force_defer = getenv("ZIPGPU_DEFER_TOP") != nullptr;  // A/B knob
+    const bool defer_top = merkle && !job.layers_out && sched.size() > 1 && code->depth > 7 &&
+                           (!chunk_whole_trees || force_defer);
     int split_level = -1, min_split = 1 << 30;  // the deferred top passes start at the LOWEST level any chunk stopped at
     // ZIPGPU_TIMELINE=1: timing events after every copy / chunk, printed relative to the first (diagnostics only)
     static const bool timeline = getenv("ZIPGPU_TIMELINE") != nullptr;
@@ -1394,7 +1451,9 @@ static int run_host_job(zipgpu_code *code, size_t num_rows, const HostJob &job) 
     if ((e = chain(ctx, h2d, s)) != cudaSuccess) return cuda_fail(e, "chain");
     const double t_enq = now();
     if (!job.keep) DEV_FREE(ctx, d_evals, s);
-    if (trace) fprintf(stderr, "[zipgpu] host job: alloc %.3f ms, enqueue %.3f ms\n", t_alloc - t_begin, t_enq - t_alloc);
+    if (trace)
+        fprintf(stderr, "[zipgpu] host job: %zu rows x %zu, %zu chunks: alloc %.3f ms, enqueue %.3f ms\n", num_rows,
+                (size_t)code->row_len, sched.size(), t_alloc - t_begin, t_enq - t_alloc);
     if (job.keep) {
         zipgpu_data *d = new (std::nothrow) zipgpu_data();
         if (!d) return fail(ZIPGPU_ERR_NOMEM, "host allocation failed");
@@ -1941,10 +2000,14 @@ int zipgpu::data_open_columns_wire_strided(const zipgpu_data *d, size_t num_cols
     {
         const size_t vrow = (size_t)d->out_limbs * 8, prow = 8 + (size_t)d->depth * 32;
         const size_t col_local = d->num_rows * (vrow + prow), col_total = total_rows * (vrow + prow);
-        CU(cudaMemcpy2DAsync(stream_out + row_offset * vrow, col_total, d_out, col_local, d->num_rows * vrow, num_cols,
-                             cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpy2DAsync(stream_out + total_rows * vrow + row_offset * prow, col_total, d_out + d->num_rows * vrow,
-                             col_local, d->num_rows * prow, num_cols, cudaMemcpyDeviceToHost, s));
+        if (col_local == col_total) {  // the whole commitment is here: the device buffer IS the stream, one linear copy
+            CU(cudaMemcpyAsync(stream_out, d_out, bytes, cudaMemcpyDeviceToHost, s));
+        } else {
+            CU(cudaMemcpy2DAsync(stream_out + row_offset * vrow, col_total, d_out, col_local, d->num_rows * vrow, num_cols,
+                                 cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpy2DAsync(stream_out + total_rows * vrow + row_offset * prow, col_total, d_out + d->num_rows * vrow,
+                                 col_local, d->num_rows * prow, num_cols, cudaMemcpyDeviceToHost, s));
+        }
     }
     DEV_FREE(ctx, d_cols, s);
     DEV_FREE(ctx, d_out, s);

@@ -66,6 +66,24 @@ class Context:
         self.device = device
         self._codes: dict[tuple[int, int, int], C.c_void_p] = {}   # (code uid, in_limbs, out_limbs) -> zipgpu_code*
         self._live: dict[int, weakref.ref] = {}                    # uid -> weak ref to an object with _release()
+        self._stream_buf = None                                    # (ptr, capacity): pinned proof-stream buffer
+
+    def proof_stream_buffer(self, nbytes: int) -> np.ndarray:
+        """a uint8 view of `nbytes` of this context's PINNED proof-stream buffer (zipgpu_host_alloc; grown on demand, freed
+        with the context).  What `open` appends to the transcript stream (pcs_transcript.rs:115-135,198-211) is tens of
+        MB per proof: into fresh pageable memory the page faults and the staged copy cost 20x the gather + PCIe time.
+        The view is valid until the next call."""
+        self._check_open()
+        if self._stream_buf is None or self._stream_buf[1] < nbytes:
+            if self._stream_buf is not None:
+                nat.lib().zipgpu_host_free(self._stream_buf[0])
+                self._stream_buf = None
+            cap = max(int(nbytes), 1 << 20)
+            p = C.c_void_p()
+            nat.check(nat.lib().zipgpu_host_alloc(cap, C.byref(p)))
+            self._stream_buf = (p, cap)
+        buf = (C.c_uint8 * nbytes).from_address(self._stream_buf[0].value)
+        return np.frombuffer(buf, dtype=np.uint8, count=nbytes)
 
     def _check_open(self) -> None:
         if not self.handle:
@@ -98,6 +116,9 @@ class Context:
             for h in self._codes.values():
                 self._destroy_code(h)
             self._codes.clear()
+            if self._stream_buf is not None:
+                nat.lib().zipgpu_host_free(self._stream_buf[0])
+                self._stream_buf = None
             self._destroy_ctx()
             self.handle = None
 
@@ -135,6 +156,7 @@ class MultiContext(Context):
         self.device = None
         self._codes = {}
         self._live = {}
+        self._stream_buf = None
 
     def sync(self) -> None:
         self._check_open()
@@ -618,13 +640,19 @@ class ResidentZipData:
     def open_columns_wire(self, columns) -> bytes:
         """open_z.rs:124-143 as proof-stream bytes (PcsTranscript::write_integers + write_merkle_proof,
         pcs_transcript.rs:115-135,198-211): what `open` appends to the transcript stream for these columns"""
+        return self.open_columns_wire_view(columns).tobytes()
+
+    def open_columns_wire_view(self, columns) -> np.ndarray:
+        """the same bytes as a uint8 view of the context's pinned proof-stream buffer (no page faults, no staged copy, no
+        extra host copy: the D2H runs at PCIe rate); valid until the next call on this context"""
         cols = np.ascontiguousarray(columns, dtype=np.uint32)
         L = nat.lib()
         per = int((L.zipgpu_mgpu_data_open_columns_wire_bytes if self._multi else L.zipgpu_data_open_columns_wire_bytes)(self._h()))
-        out = np.empty(cols.size * per, dtype=np.uint8)
+        out = self._ctx.proof_stream_buffer(cols.size * per)
         fn = L.zipgpu_mgpu_data_open_columns_wire if self._multi else L.zipgpu_data_open_columns_wire
-        nat.check(fn(self._h(), cols.size, nat.ptr(cols), nat.ptr(out)))
-        return out.tobytes()
+        if cols.size:
+            nat.check(fn(self._h(), cols.size, nat.ptr(cols), out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def combine_rows(self, coeffs, out_limbs: int = 8) -> np.ndarray:
         """open_z.rs:100-113 / zip/utils.rs:94-127: u' = sum_i coeffs[i] * row_i over the unencoded evaluations,
