@@ -402,6 +402,36 @@ def test_warp_specialised_commit_kernel_tree_tops(row_len, num_rows, units, orac
     assert np.array_equal(g_roots, roots) and np.array_equal(g_lay, layers)
 
 
+def test_host_alloc_huge_page_backed_pinned_memory(oracle, ctx):
+    """zipgpu_host_alloc: page-locked memory on 2 MiB pages from 2 MiB up (cudaHostAlloc below); usable as input and
+    output of the host-pointer entry points, freed with zipgpu_host_free (NULL is fine)"""
+    from zinc_b200 import _native as nat
+
+    L = nat.lib()
+    code, row_len, num_rows, cw, p1, p2 = _code(20, KECCAK_SEEDS, oracle)
+    n = num_rows * row_len
+    blocks = []
+    for nbytes in (n * 8, num_rows * 32, (2 << 20) + 4096, 1):
+        p = C.c_void_p()
+        nat.check(L.zipgpu_host_alloc(nbytes, C.byref(p)))
+        assert p.value and p.value % 64 == 0
+        blocks.append(p)
+    assert blocks[0].value % (2 << 20) == 0  # the large block starts on a 2 MiB boundary
+    ev = np.frombuffer((C.c_uint64 * n).from_address(blocks[0].value), dtype=np.uint64)
+    ev[:] = np.random.default_rng(9).integers(0, 1 << 64, size=n, dtype=np.uint64)
+    roots = np.frombuffer((C.c_uint8 * (num_rows * 32)).from_address(blocks[1].value), dtype=np.uint8)
+    hd = C.c_void_p()
+    nat.check(L.zipgpu_commit_resident(code.native(ctx, 1, 4), num_rows, blocks[0], blocks[1], C.byref(hd)))
+    L.zipgpu_data_free(hd)
+    rc, _, _, want = oracle.commit_mt(ev.copy(), num_rows, row_len, 2, 0, 0, p1, p2, threads=8, faithful=False,
+                                      want_rows=False, want_layers=False)
+    assert rc == 0 and roots.tobytes() == want.tobytes()
+    del ev, roots
+    for p in blocks:
+        nat.check(L.zipgpu_host_free(p))
+    nat.check(L.zipgpu_host_free(None))
+
+
 def test_peer_roots_allgather_single_rank(ctx):
     """the peer-memory roots exchange degenerates to a copy + self-signal on one GPU (N > 1: scripts/strong_scaling.py
     --p2p and test_peer_roots_two_gpus below); two steps exercise the double buffering"""
