@@ -142,6 +142,14 @@ int zipgpu_encode_rows_device(zipgpu_code *code, size_t num_rows, const uint64_t
 int zipgpu_encode_f(zipgpu_code *code, size_t num_rows, int limbs, const uint64_t *modulus, const uint64_t *rows,
                     uint64_t *out);
 
+/* ---- encode_wide (code_raa.rs:125-131) for any In = Int<in_limbs>, Out = Int<out_limbs>, 1 <= in <= out <= 8: entries
+ * sign-extended (Out::from(&In), int.rs:194-199), two's-complement adds at the output width.  The verifier runs it on
+ * the combined row of every proximity test with In = Out = M = Int<8> (verify_z.rs:74-78); a latency kernel (one CTA per
+ * row), not the prover's encoder.  Uses the permutations of `code`; its own in/out limbs do not matter.
+ *   rows: num_rows * row_len * in_limbs u64 (host);  out: num_rows * codeword_len * out_limbs u64 (host). */
+int zipgpu_encode_wide(zipgpu_code *code, size_t num_rows, int in_limbs, int out_limbs, const uint64_t *rows,
+                       uint64_t *out);
+
 /* ---- MerkleTree::new batched over rows (pcs/utils.rs:74-118) ----------------------------------------- */
 /* leaves: num_rows * (1<<depth) values of leaf_limbs limbs.  layers_out nullable.  roots_out: num_rows*32. */
 int zipgpu_merkle_rows(zipgpu_ctx *ctx, size_t num_rows, int depth, int leaf_limbs, const uint64_t *leaves,

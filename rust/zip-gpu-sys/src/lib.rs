@@ -84,6 +84,9 @@ unsafe extern "C" {
     // encode_f (code_raa.rs:133-138): the code over field elements (stored residues, `limbs` u64 words each)
     pub fn zipgpu_encode_f(code: *mut zipgpu_code, num_rows: usize, limbs: c_int, modulus: *const u64, rows: *const u64,
                            out: *mut u64) -> c_int;
+    // encode_wide::<In, Out> for any widths (verifier: In = Out = M, verify_z.rs:74-78)
+    pub fn zipgpu_encode_wide(code: *mut zipgpu_code, num_rows: usize, in_limbs: c_int, out_limbs: c_int, rows: *const u64,
+                              out: *mut u64) -> c_int;
     pub fn zipgpu_code_destroy(code: *mut zipgpu_code);
     // encode_rows / commit_no_merkle (commit.rs:104-119,158-183)
     pub fn zipgpu_encode_rows(code: *mut zipgpu_code, num_rows: usize, evals: *const u64, rows_out: *mut u64) -> c_int;

@@ -214,6 +214,7 @@ def test_multi_gpu_context_has_no_cpu_fallback_either():
     assert nat.lib().zipgpu_commit_resident_sharded(None, None, 0, 0, None, None, None) == nat.ERR_INVALID
     assert nat.lib().zipgpu_peer_roots_status(None) == nat.ERR_INVALID
     assert nat.lib().zipgpu_encode_f(None, 0, 1, None, None, None) == nat.ERR_INVALID
+    assert nat.lib().zipgpu_encode_wide(None, 0, 8, 8, None, None) == nat.ERR_INVALID
 
 
 def test_as_limbs_accepts_signed_limb_arrays():

@@ -149,3 +149,60 @@ def test_gpu_outputs_are_wire_bytes(oracle, ctx):
     w2.write_integers(comb)
     assert w2.into_bytes() == comb.astype("<u8").tobytes() and len(w2.into_bytes()) == row_len * 64
     data.free()
+
+
+def _signed_limbs(vals, limbs):
+    return _to_limbs([v & ((1 << (64 * limbs)) - 1) for v in vals], limbs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("row_len", [4, 128, 1000, 4096])
+@pytest.mark.parametrize("in_limbs,out_limbs,bits", [(8, 8, 200), (4, 8, 250), (3, 3, 150), (1, 8, 63), (5, 7, 300), (8, 8, 480)])
+def test_encode_wide_any_widths_matches_oracle(row_len, in_limbs, out_limbs, bits, oracle, ctx):
+    """RaaCode::encode_wide::<In, Out> (code_raa.rs:125-131) at the widths the tiled prover encoder does not carry -- above
+    all the verifier's encode_wide::<M, M> of a combined row (In = Out = Int<8>, verify_z.rs:74-78): signed entries of
+    `bits` bits (sums of coeff x evaluation products are ~140 bits), sign extension on load, against the C oracle's
+    repeat -> permute -> accumulate -> permute -> accumulate at the same widths, and the extremes"""
+    import random
+
+    from zinc_b200 import RaaCode, ZipTypes
+
+    cw = 2 * row_len
+    p1, p2 = oracle.perm_from_seed(cw, KECCAK_SEEDS[0]), oracle.perm_from_seed(cw, KECCAK_SEEDS[1])
+    code = RaaCode.with_permutations(ZipTypes(), row_len, 2, p1, p2)
+    rnd = random.Random(row_len * 131 + in_limbs * 8 + out_limbs)
+    bits = min(bits, 64 * in_limbs - 1)
+    row = [rnd.randrange(-(1 << bits), 1 << bits) for _ in range(row_len)]
+    row[0], row[-1] = (1 << bits) - 1, -(1 << bits)
+    r = _signed_limbs(row, in_limbs)
+    rc, expect = oracle.encode_rows(r.reshape(-1), 1, row_len, 2, p1, p2, in_limbs=in_limbs, out_limbs=out_limbs)
+    got = code.encode_wide(r, in_limbs, out_limbs, ctx)
+    assert np.array_equal(got.reshape(-1), expect)
+    if bits + 2 * cw.bit_length() < 64 * out_limbs:
+        assert rc == 0  # no overflow: the reference's checked adds would not have fired
+
+
+@pytest.mark.gpu
+def test_encode_wide_m_to_m_against_python_bigints(oracle, ctx):
+    """the verifier's shape end to end on a small code: combine_rows on the device (Int<8> combined row), then
+    encode_wide::<M, M> of it, against Python big-int arithmetic (oracle/pyoracle.py) -- and linearity:
+    encode(sum_i c_i row_i) == sum_i c_i encode(row_i), the identity verify_column_testing checks per opened column"""
+    import random
+
+    from oracle import pyoracle as po
+    from zinc_b200 import RaaCode, ZipTypes
+
+    row_len, num_rows = 64, 8
+    cw = 2 * row_len
+    p1, p2 = oracle.perm_from_seed(cw, MOCK_SEEDS[0]), oracle.perm_from_seed(cw, MOCK_SEEDS[1])
+    code = RaaCode.with_permutations(ZipTypes(), row_len, 2, p1, p2)
+    rnd = random.Random(3)
+    evals = [rnd.randrange(-(1 << 63), 1 << 63) for _ in range(num_rows * row_len)]
+    coeffs = [rnd.randrange(-(1 << 63), 1 << 63) for _ in range(num_rows)]
+    combined = [sum(coeffs[i] * evals[i * row_len + c] for i in range(num_rows)) for c in range(row_len)]
+    enc_combined = po.encode_row_perm(combined, 2, p1.tolist(), p2.tolist())
+    got = code.encode_wide(_signed_limbs(combined, 8), 8, 8, ctx)
+    assert np.array_equal(got, _signed_limbs(enc_combined, 8))
+    per_row = [po.encode_row_perm(evals[i * row_len:(i + 1) * row_len], 2, p1.tolist(), p2.tolist()) for i in range(num_rows)]
+    lin = [sum(coeffs[i] * per_row[i][j] for i in range(num_rows)) for j in range(cw)]
+    assert lin == enc_combined

@@ -74,6 +74,7 @@ SIGNATURES = {
     "zipgpu_encode_rows": (i32, [vp, sz, vp, vp]),
     "zipgpu_encode_rows_device": (i32, [vp, sz, vp, vp, vp]),
     "zipgpu_encode_f": (i32, [vp, sz, i32, vp, vp, vp]),
+    "zipgpu_encode_wide": (i32, [vp, sz, i32, i32, vp, vp]),
     "zipgpu_merkle_rows": (i32, [vp, sz, i32, i32, vp, vp, vp]),
     "zipgpu_merkle_rows_device": (i32, [vp, sz, i32, i32, vp, vp, vp, vp]),
     "zipgpu_commit": (i32, [vp, sz, vp, vp, vp, vp]),

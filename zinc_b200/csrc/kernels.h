@@ -74,7 +74,9 @@ struct EncodeFArgs {
     const uint32_t *perm1, *perm2, *modulus;  // device u32[cw], u32[cw], u32[2*limbs]
     uint32_t *scratch;        // device num_rows * cw * 2*limbs words
     uint32_t num_rows, row_len, cw;
-    int limbs;                // u64 limbs per field element (1..6)
+    int limbs;                // u64 limbs per field element (1..6) / per output integer (1..8)
+    int in_limbs = 0;         // > 0: encode_wide instead -- rows_in entries are Int<in_limbs>, sign-extended to Int<limbs>,
+                              // wrap-around adds, `modulus` unused
     cudaStream_t stream;
 };
 cudaError_t launch_encode_f(const EncodeFArgs &a);

@@ -1494,6 +1494,61 @@ extern "C" int zipgpu_encode_rows(zipgpu_code *code, size_t num_rows, const uint
     return rc ? rc : rc2;
 }
 
+// the latency encoder of encode_f.cu on host buffers: in_limbs == 0: field elements of `limbs` limbs modulo `modulus`;
+// in_limbs > 0: Int<in_limbs> entries widened to Int<limbs>, wrap-around adds
+static int encode_rows_generic(zipgpu_code *code, size_t num_rows, int limbs, int in_limbs, const uint64_t *modulus,
+                               const uint64_t *rows, uint64_t *out) {
+    if (num_rows == 0) return ZIPGPU_OK;
+    zipgpu_ctx *ctx = code->ctx;
+    API_LOCK(ctx);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (!code->d_perm1) {  // first use: the gather form of the permutations, as uploaded
+        cudaError_t e;
+        if ((e = cudaMalloc(&code->d_perm1, code->cw * 4)) != cudaSuccess || (e = cudaMalloc(&code->d_perm2, code->cw * 4)) != cudaSuccess ||
+            (e = cudaMemcpy(code->d_perm1, code->h_perm1.data(), code->cw * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMemcpy(code->d_perm2, code->h_perm2.data(), code->cw * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+            cudaFree(code->d_perm1);
+            cudaFree(code->d_perm2);
+            code->d_perm1 = code->d_perm2 = nullptr;
+            return cuda_fail(e, "cudaMalloc/cudaMemcpy(permutations)");
+        }
+    }
+    DevGuard guard(ctx, s);
+    const size_t in_bytes = num_rows * code->row_len * (in_limbs ? in_limbs : limbs) * 8;
+    const size_t out_bytes = num_rows * code->cw * limbs * 8;
+    uint32_t *d_in = nullptr, *d_out = nullptr, *d_scr = nullptr, *d_mod = nullptr;
+    DEV_ALLOC(ctx, &d_in, in_bytes, s);
+    DEV_ALLOC(ctx, &d_out, out_bytes, s);
+    DEV_ALLOC(ctx, &d_scr, out_bytes, s);
+    DEV_ALLOC(ctx, &d_mod, 64, s);
+    CU(cudaMemcpyAsync(d_in, rows, in_bytes, cudaMemcpyHostToDevice, s));
+    if (modulus) CU(cudaMemcpyAsync(d_mod, modulus, (size_t)limbs * 8, cudaMemcpyHostToDevice, s));
+    EncodeFArgs a;
+    a.rows_in = d_in;
+    a.out = d_out;
+    a.perm1 = code->d_perm1;
+    a.perm2 = code->d_perm2;
+    a.modulus = d_mod;
+    a.scratch = d_scr;
+    a.num_rows = (uint32_t)num_rows;
+    a.row_len = (uint32_t)code->row_len;
+    a.cw = (uint32_t)code->cw;
+    a.limbs = limbs;
+    a.in_limbs = in_limbs;
+    a.stream = s;
+    cudaError_t e = launch_encode_f(a);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_encode_f");
+    ctx->launches++;
+    CU(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    DEV_FREE(ctx, d_in, s);
+    DEV_FREE(ctx, d_out, s);
+    DEV_FREE(ctx, d_scr, s);
+    DEV_FREE(ctx, d_mod, s);
+    CU(cudaStreamSynchronize(s));
+    return ZIPGPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // encode_f (code_raa.rs:133-138): the RAA code over field elements
 // ------------------------------------------------------------------------------------------------------
@@ -1514,53 +1569,19 @@ extern "C" int zipgpu_encode_f(zipgpu_code *code, size_t num_rows, int limbs, co
             cmp = rows[i * limbs + l] < modulus[l] ? -1 : rows[i * limbs + l] > modulus[l] ? 1 : 0;
         if (cmp >= 0) return fail(ZIPGPU_ERR_INVALID, "encode_f: element " + std::to_string(i) + " is not reduced modulo the field modulus");
     }
-    if (num_rows == 0) return ZIPGPU_OK;
-    zipgpu_ctx *ctx = code->ctx;
-    API_LOCK(ctx);
-    CU(cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
-    if (!code->d_perm1) {  // first use: the gather form of the permutations, as uploaded
-        cudaError_t e;
-        if ((e = cudaMalloc(&code->d_perm1, code->cw * 4)) != cudaSuccess || (e = cudaMalloc(&code->d_perm2, code->cw * 4)) != cudaSuccess ||
-            (e = cudaMemcpy(code->d_perm1, code->h_perm1.data(), code->cw * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
-            (e = cudaMemcpy(code->d_perm2, code->h_perm2.data(), code->cw * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
-            cudaFree(code->d_perm1);
-            cudaFree(code->d_perm2);
-            code->d_perm1 = code->d_perm2 = nullptr;
-            return cuda_fail(e, "cudaMalloc/cudaMemcpy(permutations)");
-        }
-    }
-    DevGuard guard(ctx, s);
-    const size_t in_bytes = num_rows * code->row_len * limbs * 8, out_bytes = num_rows * code->cw * limbs * 8;
-    uint32_t *d_in = nullptr, *d_out = nullptr, *d_scr = nullptr, *d_mod = nullptr;
-    DEV_ALLOC(ctx, &d_in, in_bytes, s);
-    DEV_ALLOC(ctx, &d_out, out_bytes, s);
-    DEV_ALLOC(ctx, &d_scr, out_bytes, s);
-    DEV_ALLOC(ctx, &d_mod, 64, s);
-    CU(cudaMemcpyAsync(d_in, rows, in_bytes, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(d_mod, modulus, (size_t)limbs * 8, cudaMemcpyHostToDevice, s));
-    EncodeFArgs a;
-    a.rows_in = d_in;
-    a.out = d_out;
-    a.perm1 = code->d_perm1;
-    a.perm2 = code->d_perm2;
-    a.modulus = d_mod;
-    a.scratch = d_scr;
-    a.num_rows = (uint32_t)num_rows;
-    a.row_len = (uint32_t)code->row_len;
-    a.cw = (uint32_t)code->cw;
-    a.limbs = limbs;
-    a.stream = s;
-    cudaError_t e = launch_encode_f(a);
-    if (e != cudaSuccess) return cuda_fail(e, "launch_encode_f");
-    ctx->launches++;
-    CU(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
-    DEV_FREE(ctx, d_in, s);
-    DEV_FREE(ctx, d_out, s);
-    DEV_FREE(ctx, d_scr, s);
-    DEV_FREE(ctx, d_mod, s);
-    CU(cudaStreamSynchronize(s));
-    return ZIPGPU_OK;
+    return encode_rows_generic(code, num_rows, limbs, 0, modulus, rows, out);
+}
+
+// encode_wide (code_raa.rs:125-131) for any In = Int<in_limbs>, Out = Int<out_limbs>: what the verifier runs on the
+// combined row of a proximity test with In = Out = M (verify_z.rs:74-78)
+extern "C" int zipgpu_encode_wide(zipgpu_code *code, size_t num_rows, int in_limbs, int out_limbs, const uint64_t *rows,
+                                  uint64_t *out) {
+    if (!code || (num_rows && (!rows || !out))) return fail(ZIPGPU_ERR_INVALID, "NULL argument");
+    if (code->sparse) return fail(ZIPGPU_ERR_UNSUPPORTED, "encode_wide is implemented for the RAA code");
+    if (in_limbs < 1 || out_limbs < in_limbs || out_limbs > 8)
+        return fail(ZIPGPU_ERR_INVALID, "need 1 <= in_limbs <= out_limbs <= 8");
+    if (num_rows > 0x7fffffffull) return fail(ZIPGPU_ERR_UNSUPPORTED, "too many rows");
+    return encode_rows_generic(code, num_rows, out_limbs, in_limbs, nullptr, rows, out);
 }
 
 // ------------------------------------------------------------------------------------------------------

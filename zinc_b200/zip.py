@@ -365,6 +365,14 @@ class RaaCode:
         assert r.shape[0] == self._row_len, "Row length must match the code's row length"  # code_raa.rs:93-97
         ctx = ctx or default_context()
         out = np.empty((self.codeword_len(), out_limbs), dtype=np.uint64)
+        if in_limbs > 2:
+            # wider inputs than the prover's evaluations: the verifier's encode_wide::<M, M> of a combined row
+            # (verify_z.rs:74-78) -- the latency encoder, permutations of the same code
+            if ctx.multi:
+                raise Error("encode_wide of Int<%d> rows runs on one GPU: pass a Context" % in_limbs)
+            nat.check(nat.lib().zipgpu_encode_wide(self.native(ctx, self.zt.N, self.zt.K), 1, in_limbs, out_limbs, nat.ptr(r),
+                                                   nat.ptr(out)))
+            return out
         enc = nat.lib().zipgpu_mgpu_encode_rows if ctx.multi else nat.lib().zipgpu_encode_rows
         nat.check(enc(self.native(ctx, in_limbs, out_limbs), 1, nat.ptr(r), nat.ptr(out)))
         return out
