@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kCols)
     if (col >= row_len) return;
     Acc192 a{0, 0, 0};
     const long long *p = evals + (size_t)r0 * row_len + col;
-#pragma unroll 8
+#pragma unroll 16  // 16 independent 8-byte loads in flight per thread
     for (uint32_t i = 0; i < nr; i++) acc_mul_add(a, c[i], __ldg(p + (size_t)i * row_len));
     unsigned long long *o = partial + ((size_t)blockIdx.y * row_len + col) * 3;
     o[0] = a.w0;
@@ -58,12 +58,14 @@ __global__ void __launch_bounds__(kCols)
     o[2] = a.w2;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32)
     combine_rows_final_kernel(const unsigned long long *__restrict__ partial, unsigned long long *__restrict__ out,
                               uint32_t slices, uint32_t row_len, uint32_t out_limbs) {
+    pdl_wait();  // launched with programmatic stream serialisation behind the partial sums
     const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= row_len) return;
     Acc192 a{0, 0, 0};
+#pragma unroll 8  // (not unrolled, the 3 x slices dependent-looking loads of a thread went out one slice at a time: ~20 us)
     for (uint32_t s = 0; s < slices; s++) {
         const unsigned long long *p = partial + ((size_t)s * row_len + col) * 3;
         Acc192 b{p[0], p[1], p[2]};
@@ -92,11 +94,10 @@ cudaError_t launch_combine_rows(const CombineArgs &a, int *launches) {
                                                                a.num_rows, a.row_len);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    combine_rows_final_kernel<<<(a.row_len + 127) / 128, 128, 0, a.stream>>>(
-        reinterpret_cast<const unsigned long long *>(a.scratch), reinterpret_cast<unsigned long long *>(a.out), slices,
-        a.row_len, a.out_limbs);
     if (launches) *launches = 2;
-    return cudaGetLastError();
+    return launch_pdl(combine_rows_final_kernel, dim3((a.row_len + 31) / 32), dim3(32), 0, a.stream,
+                      reinterpret_cast<const unsigned long long *>(a.scratch), reinterpret_cast<unsigned long long *>(a.out),
+                      slices, a.row_len, a.out_limbs);
 }
 
 }  // namespace zipgpu
