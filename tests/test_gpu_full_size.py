@@ -344,6 +344,33 @@ def test_warp_specialised_commit_kernel(row_len, num_rows, oracle, ctx, monkeypa
         assert np.array_equal(g_lay, layers), knob
 
 
+@pytest.mark.parametrize("num_rows", [1, 2, 73, 74, 75, 149, 500, 1211])
+def test_cw16384_cluster_commit_kernel(num_rows, oracle, ctx, monkeypatch):
+    """cw = 16384 (nv = 25 / 26) through the opt-in commit_wsc_kernel -- a 2-CTA cluster per row, the two plane sets split over the
+    shared memories of the SM pair, the encoder's gathers and scan totals crossing over through distributed shared
+    memory -- for row counts below, at and above one row per cluster and with dynamic claiming; rows, layers and roots
+    against the oracle, twice"""
+    from zinc_b200 import RaaCode, ZipTypes
+
+    row_len, cw = 8192, 16384
+    p1, p2 = oracle.perm_from_seed(cw, KECCAK_SEEDS[0]), oracle.perm_from_seed(cw, KECCAK_SEEDS[1])
+    code = RaaCode.with_permutations(ZipTypes(), row_len, 2, p1, p2)
+    evals = np.random.default_rng(num_rows + 7).integers(0, 1 << 64, size=num_rows * row_len, dtype=np.uint64)
+    if num_rows >= 2:
+        evals[:row_len] = np.uint64((1 << 63) - 1)          # i64::MAX row
+        evals[row_len:2 * row_len] = np.uint64(1 << 63)      # i64::MIN row
+    rc, rows, layers, roots = oracle.commit_mt(evals, num_rows, row_len, 2, 0, 0, p1, p2, threads=16, faithful=False)
+    assert rc == 0
+    monkeypatch.setenv("ZIPGPU_FUSE_MIN_ROWS", "1")
+    monkeypatch.setenv("ZIPGPU_WSC", "1")  # opt-in: measured slower than the single-SM forms (DESIGN.md section 3)
+    monkeypatch.setenv("ZIPGPU_WSC_MIN_ROWS", "1")
+    for rep in range(2):
+        g_rows, g_lay, g_roots = _commit_device(ctx, code, num_rows, cw, evals)
+        assert np.array_equal(g_rows, rows), rep
+        assert np.array_equal(g_lay, layers), rep
+        assert np.array_equal(g_roots, roots), rep
+
+
 @pytest.mark.parametrize("units", [1, 2])
 @pytest.mark.parametrize("row_len,num_rows", [(4096, 37), (4096, 391), (2048, 523), (1024, 97), (1024, 1500), (512, 611),
                                               (256, 59), (256, 1777)])

@@ -21,7 +21,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr",
            "-I", INCLUDE]
-SOURCES = ["raa_encode.cu", "commit_ws.cu", "commit_ws16k.cu", "raa_big.cu", "encode_f.cu", "merkle.cu", "open_columns.cu", "combine_rows.cu", "sparse_encode.cu", "sparse_umma.cu", "peer_roots.cu", "microbench.cu", "zipgpu.cu", "mgpu.cu", "rand_compat.cpp"]
+SOURCES = ["raa_encode.cu", "commit_ws.cu", "commit_ws16k.cu", "commit_wsc.cu", "raa_big.cu", "encode_f.cu", "merkle.cu", "open_columns.cu", "combine_rows.cu", "sparse_encode.cu", "sparse_umma.cu", "peer_roots.cu", "microbench.cu", "zipgpu.cu", "mgpu.cu", "rand_compat.cpp"]
 
 
 def _deps():

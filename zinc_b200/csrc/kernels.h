@@ -38,6 +38,10 @@ struct EncodeArgs {
 };
 // the warp-specialised commit kernel (commit_ws.cu) for the encoder configuration (E, T) of an exact Int<1> -> Int<4> shape
 // the cw = 16384 form (commit_ws16k.cu): one plane set, the hash warps read the codeword back from global memory
+// the cw = 16384 form as a 2-CTA cluster (commit_wsc.cu): two plane sets split over the shared memories of an SM pair
+bool commit_wsc_supported(uint32_t row_len, uint32_t cw);
+int commit_wsc_levels();
+cudaError_t launch_commit_wsc(const EncodeArgs &a);
 bool commit_ws16k_supported(uint32_t row_len, uint32_t cw);
 int commit_ws16k_levels();
 cudaError_t launch_commit_ws16k(const EncodeArgs &a);

@@ -412,6 +412,18 @@ cudaError_t launch_e(const EncodeArgs &a, const EncodeCfg &c, size_t smem) {
 // 8192: 8.081 vs 8.178).  The fused launches themselves are level (7.93 vs 7.90 ms at 8192 rows: the serial form hashes
 // with all 32 warps of an SM); the gain is the fifth tree level the 32-leaf hash threads fold in, which halves the
 // latency-bound upper passes (0.28 -> 0.15 ms).
+// cw = 16384: the 2-CTA-cluster kernel (commit_wsc.cu) is OPT-IN (ZIPGPU_WSC=1, from ZIPGPU_WSC_MIN_ROWS rows): correct,
+// but measured slower than the single-SM forms -- 8192 rows: fused launch 8.14 ms against 7.94 (commit_ws16k) and 7.90
+// (serial fused kernel); its encoder alone needs 38 us per row (15 us for the same work inside one SM): the two gathers
+// are ~33 K four- and eight-byte distributed-shared-memory transactions per row and CTA, and four cluster meetings.
+static bool wsc_enabled() {
+    const char *e = getenv("ZIPGPU_WSC");
+    return e && e[0] == '1';
+}
+static uint32_t wsc_min_rows() {
+    const char *e = getenv("ZIPGPU_WSC_MIN_ROWS");
+    return e ? (uint32_t)atol(e) : 1024u;
+}
 static uint32_t ws16k_min_rows() {
     const char *e = getenv("ZIPGPU_WS16K_MIN_ROWS");  // read per launch: the tests switch it
     return e ? (uint32_t)atol(e) : 2048u;
@@ -435,6 +447,11 @@ cudaError_t launch_w(const EncodeArgs &a) {
         commit_ws_supported(c.E, c.T)) {
         // the warp-specialised commit kernel (commit_ws.cu): an encode group and a hash group per CTA, two plane sets
         return launch_commit_ws(a, c.E, c.T, a.fused_levels_out);
+    }
+    if (a.fuse_layers && !a.evals_copy && IN32 == 2 && W == 3 && exact && a.out32 == 8 &&
+        commit_wsc_supported(a.row_len, a.cw) && wsc_enabled() && !getenv("ZIPGPU_NO_WS") && a.num_rows >= wsc_min_rows()) {
+        if (a.fused_levels_out) *a.fused_levels_out = commit_wsc_levels();
+        return launch_commit_wsc(a);
     }
     if (a.fuse_layers && !a.evals_copy && IN32 == 2 && W == 3 && exact && a.out32 == 8 && a.perm1_raw &&
         commit_ws16k_supported(a.row_len, a.cw) && !getenv("ZIPGPU_NO_WS") && a.num_rows >= ws16k_min_rows()) {
