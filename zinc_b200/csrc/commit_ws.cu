@@ -3,9 +3,10 @@
 //
 // Replaces commit.rs:69-74 (encode_rows, then MerkleTree::new per row) up to tree level log2(E / U); the batched passes of
 // merkle.cu finish the trees.  Two thread groups per CTA, two plane sets in shared memory:
-//   warps 0..n-1  (ENC)  : stage -> gather -> scan -> gather -> scan -> park s2 in plane set `buf` -> write the codeword
-//                          out (record tiles + bulk stores), then straight on to the next row in the other plane set
-//   warps n..2n-1 (HASH) : BLAKE3 leaves and the lowest tree levels of the row parked in `buf`, straight from the planes
+//   warps 0..n-1  (ENC)  : stage -> gather -> scan -> gather -> scan -> park s2 in plane set `buf`, then straight on to
+//                          the next row in the other plane set
+//   warps n..2n-1 (HASH) : the row parked in `buf`, straight from the planes: every entry is stored to `rows_out` (the
+//                          codeword) and hashed (BLAKE3 leaf), the lowest tree levels follow in registers
 // Two mbarriers per plane set hand it back and forth (full: ENC arrives / HASH waits; empty: HASH arrives / ENC waits).
 // (Round 1 used named barriers, bar.arrive / bar.sync: a bar.sync only completes when ALL waiters have arrived, which put
 // the 16 hash warps in lockstep at every row boundary -- the fast ones idled until the slowest was done.  With mbarriers
@@ -197,7 +198,6 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *planes = smem;                    // [2][W][P]
     uint32_t *aux = smem + 2 * W * P;           // scan scratch of the ENC group
-    uint32_t *tiles = aux + 64 * W;             // one 1 KiB record tile per ENC warp
     __shared__ volatile uint32_t s_row[2];      // row parked in each plane set (0xffffffff: no more rows)
     __shared__ volatile uint32_t s_next;
     __shared__ unsigned long long s_full[2], s_empty[2];  // mbarriers: plane set parked / plane set free again
@@ -225,8 +225,6 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
         uint32_t c1[T16::NR], c2[T16::NR], cc[T8::NR];
         T16::load(tab1, t, T, c1);
         const uint32_t wbase = (t >> 5) * (E * 32);
-        uint32_t *tile = tiles + (t >> 5) * 256;
-        const uint32_t lane = t & 31u, ha = (lane >> 2) & 1u;
         uint32_t row = U == 1 ? blockIdx.x : u0 / U, it = 0;
         const uint32_t row_end = U == 1 ? num_rows : (u1 + U - 1) / U;  // U > 1: rows [u0 / U, ceil(u1 / U))
         for (; row < row_end; it++) {
@@ -296,34 +294,7 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
             if (t == 0) s_row[buf] = row;
             mbar_arrive(&s_full[buf]);  // hand the row to the hash warps (every thread's arrive releases its own writes)
             __syncwarp();
-            T16::load(tab1, t, T, c1);   // for the next row; in flight during the write-out
-            // write-out of this warp's 32E positions: 32-byte records into the warp's tile, one bulk store per KiB.
-            // U > 1: only the part of the codeword this CTA's units cover (the CTA that owns the other units of a
-            // shared row writes the rest); a warp's positions lie inside one unit.
-            bool mine = true;
-            if constexpr (U > 1) {
-                const uint32_t unit = row * U + ((t >> 5) * U) / (T >> 5);
-                mine = unit >= u0 && unit < u1;
-            }
-            if (mine) {
-                uint8_t *dst_w = reinterpret_cast<uint8_t *>(rows_out) + ((size_t)row * cw + (size_t)(t >> 5) * (32 * E)) * 32;
-#pragma unroll
-                for (int j = 0; j < E; j++) {
-                    const uint32_t i = (t >> 5) * (32 * E) + j * 32 + lane;
-                    const uint32_t s = slot_of<E>(i / E, i % E, T);
-                    const uint32_t a0 = pl[s], a1 = pl[P + s], a2 = pl[2 * P + s];
-                    const uint32_t sign = (uint32_t)((int32_t)a2 >> 31);
-                    const uint4 lo = make_uint4(a0, a1, a2, sign), hi = make_uint4(sign, sign, sign, sign);
-                    if (lane == 0) bulk_wait_read_all();
-                    __syncwarp();
-                    uint4 *rec = reinterpret_cast<uint4 *>(tile) + lane * 2;
-                    rec[ha] = ha ? hi : lo;
-                    rec[ha ^ 1u] = ha ? lo : hi;
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) bulk_store_s2g(dst_w + (size_t)j * 1024, tile, 1024);
-                }
-            }
+            T16::load(tab1, t, T, c1);   // for the next row
             row = s_next;  // published before this iteration's ENC barriers
         }
         {   // no more rows: tell the hash warps through the next plane set
@@ -335,7 +306,6 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
             }
             mbar_arrive(&s_full[buf]);
         }
-        if (lane == 0) bulk_wait_all();
     } else {
         // ============================== HASH ==============================
         constexpr int H = EH >= 16 ? 4 : EH >= 8 ? 3 : EH >= 4 ? 2 : 1;
@@ -347,6 +317,12 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
             if (row == 0xffffffffu) break;
             const uint32_t *pl = planes + buf * (W * P);
             uint8_t *lay_row = layers + (size_t)row * (2 * (size_t)cw - 2) * 32;
+#ifdef WS_NO_HASH  // A/B builds: the encoder alone
+            if (one == 1u) {
+                mbar_arrive(&s_empty[buf]);
+                continue;
+            }
+#endif
             // the units of this row that are ours (U == 1: the whole row)
             uint32_t uu = 0, uu_end = 1;
             if constexpr (U > 1) {
@@ -369,6 +345,10 @@ __global__ void __launch_bounds__(2 * kWsEnc, kWsEnc == 512 ? 1 : 2)
                     const uint32_t sign = (uint32_t)((int32_t)x[W - 1] >> 31);
 #pragma unroll
                     for (int w = W; w < OUT32; w++) x[w] = sign;
+                    // the codeword entry itself: x IS the 32-byte Int<4> record (round 2: the ENC group used to write the
+                    // codeword out through record tiles and bulk stores -- 3 % of the kernel, on the same issue slots;
+                    // one streaming store here: fused kernel 1.836 -> 1.803 ms)
+                    st_stream_v8(reinterpret_cast<uint8_t *>(rows_out) + ((size_t)row * cw + idx) * 32, x);
                     b3::Digest d;
                     b3::hash_leaf<OUT32>(x, d.w, one);
                     st_global_v8(lay_row + (size_t)idx * 32, d.w);
@@ -423,7 +403,7 @@ static uint32_t ws_tops_max_rows() {
 
 template <int E, int TENC, int U, bool TOPS>
 cudaError_t launch_ws_u(const EncodeArgs &a, uint32_t grid) {
-    const size_t ws_smem = (2 * 3 * (size_t)(E * TENC) + 64 * 3 + (TENC / 32) * 256) * sizeof(uint32_t);
+    const size_t ws_smem = (2 * 3 * (size_t)(E * TENC) + 64 * 3) * sizeof(uint32_t);
     static_assert(!TOPS || 8 * (8 * (TENC / 4) + 8) <= 2 * 3 * E * TENC, "the digest buffer of the tops fits in the planes");
     auto kern = commit_ws_kernel<E, TENC, U, TOPS>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem);

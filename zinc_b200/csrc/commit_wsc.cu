@@ -1,38 +1,36 @@
-// zinc_b200/csrc/commit_wsc.cu -- the warp-specialised commit kernel for cw = 16384 (nv = 25 / 26) as a 2-CTA CLUSTER:
-// commit_ws.cu's arrangement (ENC warps encode row r + 1 into one plane set while HASH warps hash row r straight from
-// the other) for the codeword length whose two plane sets (2 x 192 KiB) do not fit one SM -- they are split over the
-// shared memories of the two SMs of a cluster (distributed shared memory).
+// zinc_b200/csrc/commit_wsc.cu -- the warp-specialised commit kernel for cw = 16384 (nv = 25 / 26) as a 2-CTA CLUSTER
+// (opt-in: ZIPGPU_WSC=1).
 //
-// Same job: RAA encode (code_raa.rs:89-105) + BLAKE3 leaves + tree levels 1..4 (pcs/utils.rs:87-118) of every row in
-// one launch, Int<1> -> Int<4>.  The per-pp tables are those of the (E = 16, T = 1024) encoder layout; CTA c of a
-// cluster runs virtual threads 512 c .. 512 c + 511 of it:
-//   * a plane in the [k][t] layout (staged row, finished entries s2: slot k * 1024 + t') is split by COLUMN -- CTA c
-//     holds the columns of its own threads as a [16][512] half-plane -- and a plane in the [warp][k * 32 + colour] layout
-//     (parked s1) by WARP.  Either way everything a thread WRITES is in its own CTA's shared memory, the hash warps read
-//     only local memory (the leaves of columns 512 c .. are exactly the 8192 leaves 8192 c ..), and the code for staging,
-//     parking, write-out and hashing is the (E = 16, T = 512) code of commit_ws.cu on the half-plane;
-//   * only the two GATHERS of the encoder cross over: through tab1 from the staged row, through tab2 from s1 -- half of
-//     them land in the peer's shared memory (ld.shared::cluster; ~215 cycles instead of ~30, 16 independent loads per
-//     thread, and the ENC warps have three quarters of a row time to spare);
-//   * the two prefix sums are CTA-local scans plus the total of CTA 0 handed to CTA 1 (one remote store);
-//   * the ENC groups of the two CTAs meet four times per row (staged / gather 1 done + totals / s1 parked / gather 2
-//     done + totals) through a 2-arrival mbarrier in each CTA: local named barrier, one thread arrives on its own and
-//     (mbarrier.arrive.release.cluster on the mapa'd address) on the peer's barrier, one warp waits with acquire.cluster,
-//     named barrier again.  The HASH groups never take part: barrier.cluster would stall them.
+// commit_ws.cu's arrangement -- ENC warps encode row r + 1 while HASH warps hash row r straight from shared memory --
+// for the codeword length whose two plane sets (2 x 192 KiB) do not fit one SM: the two CTAs of a cluster take one row
+// together, CTA c owning positions 8192 c .. 8192 c + 8191 (virtual threads 512 c .. of a 1024-thread layout, 16
+// consecutive positions each).  Same job: RAA encode (code_raa.rs:89-105) + BLAKE3 leaves + tree levels 1..4
+// (pcs/utils.rs:87-118) of every row in one launch, Int<1> -> Int<4>.
+//   * shared memory holds ONLY the finished entries s2 of a CTA's half of two rows ([16][512] half-planes; the
+//     (E = 16, T = 512) parking and hash code of commit_ws.cu) -- the hash warps read local memory only, store each
+//     entry to `rows_out` and hash it;
+//   * pass 1 gathers row[perm1[i] mod row_len] straight from global memory (the 64 KiB row is L2 / L1 resident), scans
+//     inside the CTA's half and stores s1 as 16-byte records to an L2-resident scratch (two rows per cluster);
+//   * the ENC groups of the two CTAs meet ONCE per row (s1 of the whole row is in the scratch, CTA 0's total of the first
+//     prefix sum in both CTAs): named barrier, one thread arrives (mbarrier.arrive.release.cluster on mapa'd addresses)
+//     on its own and the peer's 2-arrival mbarrier, one warp waits with acquire.cluster, named barrier;
+//   * pass 2 gathers s1[perm2[i]] from the scratch (one 16-byte ld.global.cg per entry; entries of CTA 1's half get CTA
+//     0's total added), scans, and CTA 1 alone waits for CTA 0's total of the second prefix sum (remote store + remote
+//     arrive; CTA 0 does not wait).  The HASH groups never take part in any of this (barrier.cluster would stall them).
 // Rows are claimed per cluster (CTA 0 claims and stores the row into the peer's s_next).
 //
-// Why: the single-SM form for this shape (commit_ws16k.cu) keeps s1 only and lets the hash warps re-read the codeword
-// from L2 -- they reach 0.83 of the alu-pipe peak, the shared-memory-fed hash loop 0.87-0.88.
-//
-// RESULT (B200, nv = 26, 8192 rows): bit-exact, but the fused launch takes 8.14 ms against 7.94 ms for commit_ws16k.cu and
-// 7.90 ms for the serial fused kernel -- 73.5 us per row and CTA where the hash loop alone needs 65.5.  The encoder is the
-// critical path: alone (hashing compiled out) it needs 38 us per row, against ~15 us for the same 8192 positions inside
-// one SM.  Its two gathers are 8192 eight-byte and 24576 four-byte scattered shared::cluster loads per row and CTA, half
-// of them remote -- the SM-to-SM network moves ~20 B/clk in wide accesses but far less in 4-byte ones -- and the four
-// meetings cost a named barrier, a remote mbarrier round trip and another named barrier each.  With 16 hash warps
-// taking four of five issue slots the 38 us stretch past the 65 us budget.  (A random permutation over the whole row
-// means half of every intermediate vector must cross between the two CTAs; in bulk that would be 2.6 us per row, but
-// there is no room for a receive buffer next to two plane sets.)  The kernel therefore stays OPT-IN (ZIPGPU_WSC=1).
+// History and RESULT (B200, nv = 26, 8192 rows; commit_ws16k.cu: fused launch 7.93 ms + 0.15 ms upper passes):
+//   v1  both plane sets split over the two SMs' shared memories, the encoder's two gathers through distributed shared
+//       memory (ld.shared::cluster), four meetings per row: bit-exact on the first run, fused launch 8.14 ms -- the
+//       encoder alone needed 38 us per row (8192 eight-byte + 24576 four-byte scattered DSMEM loads per row and CTA, half
+//       remote) and, competing with 16 hash warps, became the critical path;
+//   v2  s1 through the L2 scratch instead (this file): encoder alone 41 us -- the record-tile / bulk-store write-out
+//       of the codeword, not the gathers, was the expensive part;
+//   v3  the hash threads store the codeword (as in commit_ws.cu now): encoder alone 22 us, fused launch 7.88 ms.
+// That is 0.7 % better than commit_ws16k.cu per launch, but this kernel stops at tree level 4 (16 leaves per hash thread)
+// where ws16k folds in a fifth, so the commit is 8.16 vs 8.08 ms.  All forms of this shape end within 3 % of each other
+// (serial: hash at 0.95 of the alu peak plus a serial encode; ws16k: hidden encode, L2-fed hash at 0.83; cluster:
+// shared-memory-fed hash, but twice the encoder work per hash warp of the cw = 8192 kernel).
 #include <cstdlib>
 
 #include "raa_common.cuh"
@@ -89,23 +87,25 @@ __device__ __forceinline__ void cluster_barrier_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ uint4 ld_global_cg_v4(const void *p) {
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(2 * kT, 1)
     commit_wsc_kernel(const uint32_t *__restrict__ evals, uint32_t *__restrict__ rows_out,
-                      const uint16_t *__restrict__ tab1, const uint16_t *__restrict__ tab2,
-                      const uint8_t *__restrict__ colw, uint32_t num_rows, uint8_t *__restrict__ layers, uint32_t one,
-                      uint32_t *__restrict__ row_counter) {
-    using T16 = Tab16<kE>;
-    using T8 = Tab8<kE>;
+                      const uint32_t *__restrict__ perm1, const uint32_t *__restrict__ perm2, uint4 *scratch,
+                      uint32_t num_rows, uint8_t *__restrict__ layers, uint32_t one, uint32_t *__restrict__ row_counter) {
     using EncBar = NamedBarrier<kBarEncC, kT>;
-    constexpr uint32_t in_words_half = (kRowLen / 2) * kIn32;  // words of the input row a CTA stages
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *planes = smem;                   // [2][W][kPL]: this CTA's halves of the two plane sets
+    uint32_t *planes = smem;                   // [2][W][kPL]: this CTA's halves of two rows' finished entries (s2)
     uint32_t *aux = smem + 2 * kW * kPL;       // scan scratch of the ENC group
-    uint32_t *tiles = aux + 64 * kW;           // one 1 KiB record tile per ENC warp
     __shared__ volatile uint32_t s_row[2];     // row parked in each plane set (0xffffffff: no more rows)
     __shared__ volatile uint32_t s_next;       // written by CTA 0's claimer (locally and into the peer)
-    __shared__ volatile uint32_t s_xtot[kW];   // CTA 1: the scan total of CTA 0
-    __shared__ unsigned long long s_full[2], s_empty[2], s_cs;
+    __shared__ volatile uint32_t s_tot1[2][kW];  // total of CTA 0's half of the first prefix sum, by row parity (both CTAs)
+    __shared__ volatile uint32_t s_tot2[kW];     // CTA 1: total of CTA 0's half of the second prefix sum
+    __shared__ unsigned long long s_full[2], s_empty[2], s_cs, s_cs2;
     const uint32_t tid = threadIdx.x;
     const uint32_t t = tid & (kT - 1);         // index within the group
     const uint32_t crank = cluster_ctarank(), peer = crank ^ 1u;
@@ -117,22 +117,69 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(2 * kT, 1)
         mbar_init(&s_empty[0], kT);
         mbar_init(&s_empty[1], kT);
         mbar_init(&s_cs, 2);
+        mbar_init(&s_cs2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     cluster_barrier_all();  // both CTAs are resident and their barriers initialised before anyone touches the peer
 
     if (tid < kT) {
         // ============================== ENC ==============================
-        const uint32_t vt = crank * kT + t;    // virtual thread of the 1024-thread table layout
-        const uint32_t planes_sa = (uint32_t)__cvta_generic_to_shared(planes);
-        const uint32_t base_c[2] = {mapa_shared(planes_sa, 0), mapa_shared(planes_sa, 1)};
+        const uint32_t vt = crank * kT + t;    // virtual thread: positions 16 vt .. 16 vt + 15 of the row
         const uint32_t cs_own = mapa_shared((uint32_t)__cvta_generic_to_shared(&s_cs), crank);
         const uint32_t cs_peer = mapa_shared((uint32_t)__cvta_generic_to_shared(&s_cs), peer);
+        const uint32_t cs2_peer = mapa_shared((uint32_t)__cvta_generic_to_shared(&s_cs2), peer);
         const uint32_t next_peer = mapa_shared((uint32_t)__cvta_generic_to_shared(const_cast<uint32_t *>(&s_next)), peer);
-        const uint32_t xtot_peer = mapa_shared((uint32_t)__cvta_generic_to_shared(const_cast<uint32_t *>(&s_xtot[0])), peer);
-        uint32_t cs_phase = 0;
-        // the ENC groups of both CTAs meet: everything either wrote to its own shared memory before is visible to the other
-        auto enc_cluster_sync = [&]() {
+        const uint32_t tot1_peer = mapa_shared((uint32_t)__cvta_generic_to_shared(const_cast<uint32_t *>(&s_tot1[0][0])), peer);
+        const uint32_t tot2_peer = mapa_shared((uint32_t)__cvta_generic_to_shared(const_cast<uint32_t *>(&s_tot2[0])), peer);
+        uint32_t cs_phase = 0, cs2_phase = 0;
+        const uint4 *p1v = reinterpret_cast<const uint4 *>(perm1 + (size_t)vt * kE);
+        const uint4 *p2v = reinterpret_cast<const uint4 *>(perm2 + (size_t)vt * kE);
+        uint32_t row = cluster_id, it = 0;
+        for (; row < num_rows; it++) {
+            const uint32_t buf = it & 1u;
+            uint32_t *pl = planes + buf * (kW * kPL);
+            uint4 *s1g = scratch + ((size_t)cluster_id * 2 + buf) * kCw;  // this row's s1 (16-byte records), L2-resident
+            uint32_t early = row + num_clusters;
+            if (crank == 0 && t == 0 && row_counter) early = num_clusters + atomicAdd(row_counter, 1u) + 1u;
+            // ---- pass 1: y1 = widen(row[perm1[i] mod row_len]) straight from global memory (the 64 KiB row is L2 / L1
+            // resident), prefix sum inside this CTA's half
+            const uint32_t *erow = evals + (size_t)row * (kRowLen * kIn32);
+            uint32_t v[kE][kW];
+#pragma unroll
+            for (int q = 0; q < kE / 4; q++) {
+                const uint4 pi = __ldg(p1v + q);
+                const uint32_t src[4] = {pi.x, pi.y, pi.z, pi.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint2 x = __ldg(reinterpret_cast<const uint2 *>(erow) + (src[j] & (kRowLen - 1)));
+                    v[4 * q + j][0] = x.x;
+                    v[4 * q + j][1] = x.y;
+                    v[4 * q + j][2] = (uint32_t)((int32_t)x.y >> 31);
+                }
+            }
+            uint32_t pre[kW];
+            block_scan<kW, kE, EncBar>(v, pre, aux, t, kT >> 5);
+            if (crank == 0 && t == kT - 1) {  // the total of CTA 0's half: to both CTAs (entries of CTA 1's half lack it)
+                uint32_t tot[kW];
+#pragma unroll
+                for (int w = 0; w < kW; w++) tot[w] = v[kE - 1][w];
+                add_limbs<kW>(tot, pre);
+#pragma unroll
+                for (int w = 0; w < kW; w++) {
+                    s_tot1[buf][w] = tot[w];
+                    st_cluster_u32(tot1_peer + 4u * (buf * kW + w), tot[w]);
+                }
+            }
+            {   // s1 of this thread's 16 consecutive positions (prefix within the CTA's half) -> the row's scratch
+                uint4 *dst = s1g + (size_t)vt * kE;
+#pragma unroll
+                for (int k = 0; k < kE; k++) {
+                    add_limbs<kW>(v[k], pre);
+                    dst[k] = make_uint4(v[k][0], v[k][1], v[k][2], 0u);
+                }
+            }
+            __threadfence();     // the records are in L2 before this thread meets the others
+            // the ENC groups of both CTAs meet: s1 of the whole row is in the scratch, CTA 0's total in both CTAs
             EncBar::sync();
             if (t == 0) {
                 mbar_arrive_cluster(cs_own);
@@ -141,94 +188,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(2 * kT, 1)
             if (t < 32) mbar_wait_cluster(&s_cs, cs_phase);
             EncBar::sync();
             cs_phase ^= 1u;
-        };
-        // CTA 1 adds the scan total of CTA 0 (handed over before the meeting that precedes this call)
-        auto add_peer_total = [&](uint32_t (&pre)[kW]) {
-            if (crank == 1) {
-                uint32_t x[kW];
-#pragma unroll
-                for (int w = 0; w < kW; w++) x[w] = s_xtot[w];
-                add_limbs<kW>(pre, x);
-            }
-        };
-
-        uint32_t c1[T16::NR], c2[T16::NR], cc[T8::NR];
-        T16::load(tab1, vt, kVT, c1);
-        const uint32_t wbase = (t >> 5) * (kE * 32);
-        uint32_t *tile = tiles + (t >> 5) * 256;
-        const uint32_t lane = t & 31u, ha = (lane >> 2) & 1u;
-        uint32_t row = cluster_id, it = 0;
-        for (; row < num_rows; it++) {
-            const uint32_t buf = it & 1u;
-            uint32_t *pl = planes + buf * (kW * kPL);
-            const uint32_t set_off = buf * (kW * kPL) * 4u;  // byte offset of the plane set inside a CTA's planes
-            if (it >= 2) {  // this CTA's hash warps are done with its half of the plane set
-                if (t < 32) mbar_wait(&s_empty[buf], ((it >> 1) & 1u) ^ 1u);
-                EncBar::sync();
-            }
-            uint32_t early = row + num_clusters;
-            if (crank == 0 && t == 0 && row_counter) early = num_clusters + atomicAdd(row_counter, 1u) + 1u;
-            {   // this CTA's half of the input row into its own slots ([k][512] layout of plane 0)
-                WarpStage<kIn32, kE> ws;
-                ws.load(evals + (size_t)row * (kRowLen * kIn32) + (size_t)crank * in_words_half, t);
-                ws.store(pl, kPL, kT, t);
-            }
-            enc_cluster_sync();  // (1) the whole row is staged
-            uint32_t v[kE][kW];
-#pragma unroll
-            for (int k = 0; k < kE; k++) {
-                const uint32_t so = T16::get(c1, k) * kIn32;  // word k' * 1024 + column of the [16][1024] staged layout
-                const uint32_t col = so & 1023u, loc = ((so >> 10) << 9) | (col & 511u);
-                const uint2 x = ld_cluster_v2(base_c[col >> 9] + set_off + loc * 4u);
-                v[k][0] = x.x;
-                v[k][1] = x.y;
-                v[k][2] = (uint32_t)((int32_t)x.y >> 31);
-            }
-            if (crank == 0 && t == 0) {
+            if (crank == 0 && t == 0) {  // (the peer read the previous claim before it came to this meeting)
                 if (early < num_rows) prefetch_l2_bulk(evals + (size_t)early * (kRowLen * kIn32), kRowLen * kIn32 * 4u);
                 s_next = early;
                 st_cluster_u32(next_peer, early);
             }
-            uint32_t pre[kW];
-            T8::load(colw, vt, kVT, cc);
-            block_scan<kW, kE, EncBar>(v, pre, aux, t, kT >> 5);
-            if (crank == 0 && t == kT - 1) {  // the total of CTA 0 -> CTA 1
-                uint32_t tot[kW];
+            // ---- pass 2: y2 = s1[perm2[i]] from the scratch (one 16-byte L2 read per entry), second prefix sum
+            {
+                uint32_t t1[kW];
 #pragma unroll
-                for (int w = 0; w < kW; w++) tot[w] = v[kE - 1][w];
-                add_limbs<kW>(tot, pre);
+                for (int w = 0; w < kW; w++) t1[w] = s_tot1[buf][w];
 #pragma unroll
-                for (int w = 0; w < kW; w++) st_cluster_u32(xtot_peer + 4u * w, tot[w]);
-            }
-            enc_cluster_sync();  // (2) every gather from the staged row is done; the total has arrived
-            add_peer_total(pre);
+                for (int q = 0; q < kE / 4; q++) {
+                    const uint4 pi = __ldg(p2v + q);
+                    const uint32_t src[4] = {pi.x, pi.y, pi.z, pi.w};
 #pragma unroll
-            for (int k = 0; k < kE; k++) {
-                add_limbs<kW>(v[k], pre);
-                const uint32_t s1 = wbase + k * 32 + T8::get(cc, k);
+                    for (int j = 0; j < 4; j++) {
+                        const uint4 r = ld_global_cg_v4(s1g + src[j]);
+                        const uint32_t m = src[j] >= kCw / 2 ? 0xffffffffu : 0u;  // an entry of CTA 1's half: + CTA 0's total
+                        uint32_t add[kW];
 #pragma unroll
-                for (int w = 0; w < kW; w++) pl[w * kPL + s1] = v[k][w];
-            }
-            T16::load(tab2, vt, kVT, c2);
-            enc_cluster_sync();  // (3) s1 is parked
-#pragma unroll
-            for (int k = 0; k < kE; k++) {
-                const uint32_t sl = T16::get(c2, k);  // s1 address of the [32 warps][512] layout
-                const uint32_t a = base_c[sl >> 13] + set_off + (sl & 8191u) * 4u;
-#pragma unroll
-                for (int w = 0; w < kW; w++) v[k][w] = ld_cluster_u32(a + (uint32_t)w * (kPL * 4u));
+                        for (int w = 0; w < kW; w++) add[w] = t1[w] & m;
+                        v[4 * q + j][0] = r.x;
+                        v[4 * q + j][1] = r.y;
+                        v[4 * q + j][2] = r.z;
+                        add_limbs<kW>(v[4 * q + j], add);
+                    }
+                }
             }
             block_scan<kW, kE, EncBar>(v, pre, aux, t, kT >> 5);
-            if (crank == 0 && t == kT - 1) {
-                uint32_t tot[kW];
+            if (crank == 0) {
+                if (t == kT - 1) {  // CTA 0's total -> CTA 1, which alone waits for it
+                    uint32_t tot[kW];
 #pragma unroll
-                for (int w = 0; w < kW; w++) tot[w] = v[kE - 1][w];
-                add_limbs<kW>(tot, pre);
+                    for (int w = 0; w < kW; w++) tot[w] = v[kE - 1][w];
+                    add_limbs<kW>(tot, pre);
 #pragma unroll
-                for (int w = 0; w < kW; w++) st_cluster_u32(xtot_peer + 4u * w, tot[w]);
+                    for (int w = 0; w < kW; w++) st_cluster_u32(tot2_peer + 4u * w, tot[w]);
+                    mbar_arrive_cluster(cs2_peer);
+                }
+            } else {
+                if (t < 32) mbar_wait_cluster(&s_cs2, cs2_phase);
+                EncBar::sync();
+                cs2_phase ^= 1u;
+                uint32_t x[kW];
+#pragma unroll
+                for (int w = 0; w < kW; w++) x[w] = s_tot2[w];
+                add_limbs<kW>(pre, x);
             }
-            enc_cluster_sync();  // (4) every gather from s1 is done; the total has arrived
-            add_peer_total(pre);
+            if (it >= 2) {  // this CTA's hash warps are done with the plane set (the encoder ran ahead of them until here)
+                if (t < 32) mbar_wait(&s_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                EncBar::sync();
+            }
 #pragma unroll
             for (int k = 0; k < kE; k++) {
                 add_limbs<kW>(v[k], pre);
@@ -238,29 +249,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(2 * kT, 1)
             }
             if (t == 0) s_row[buf] = row;
             mbar_arrive(&s_full[buf]);  // this CTA's half of the row to its hash warps
-            __syncwarp();
-            T16::load(tab1, vt, kVT, c1);  // for the next row; in flight during the write-out
-            {   // write-out of this warp's 512 positions (32-byte records into the warp's tile, one bulk store per KiB)
-                uint8_t *dst_w = reinterpret_cast<uint8_t *>(rows_out) +
-                                 ((size_t)row * kCw + (size_t)crank * (kCw / 2) + (size_t)(t >> 5) * (32 * kE)) * 32;
-#pragma unroll
-                for (int j = 0; j < kE; j++) {
-                    const uint32_t i = (t >> 5) * (32 * kE) + j * 32 + lane;
-                    const uint32_t s = slot_of<kE>(i / kE, i % kE, kT);
-                    const uint32_t a0 = pl[s], a1 = pl[kPL + s], a2 = pl[2 * kPL + s];
-                    const uint32_t sign = (uint32_t)((int32_t)a2 >> 31);
-                    const uint4 lo = make_uint4(a0, a1, a2, sign), hi = make_uint4(sign, sign, sign, sign);
-                    if (lane == 0) bulk_wait_read_all();
-                    __syncwarp();
-                    uint4 *rec = reinterpret_cast<uint4 *>(tile) + lane * 2;
-                    rec[ha] = ha ? hi : lo;
-                    rec[ha ^ 1u] = ha ? lo : hi;
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) bulk_store_s2g(dst_w + (size_t)j * 1024, tile, 1024);
-                }
-            }
-            row = s_next;  // published before meeting (2) of this iteration
+            row = s_next;  // published after this iteration's meeting
         }
         {   // no more rows: tell the hash warps through the next plane set
             const uint32_t buf = it & 1u;
@@ -268,7 +257,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(2 * kT, 1)
             if (t == 0) s_row[buf] = 0xffffffffu;
             mbar_arrive(&s_full[buf]);
         }
-        if (lane == 0) bulk_wait_all();
     } else {
         // ============================== HASH ==============================
         // the (E = 16, T = 512) hash loop of commit_ws.cu on this CTA's half-planes: leaves 8192 * crank ...
@@ -298,6 +286,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(2 * kT, 1)
                 const uint32_t sign = (uint32_t)((int32_t)x[kW - 1] >> 31);
 #pragma unroll
                 for (int w = kW; w < kOut32; w++) x[w] = sign;
+                st_stream_v8(reinterpret_cast<uint8_t *>(rows_out) + ((size_t)row * kCw + idx) * 32, x);  // the codeword entry
                 b3::Digest d;
                 b3::hash_leaf<kOut32>(x, d.w, one);
                 st_global_v8(lay_row + (size_t)idx * 32, d.w);
@@ -326,8 +315,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(2 * kT, 1)
 bool commit_wsc_supported(uint32_t row_len, uint32_t cw) { return cw == kCw && row_len == kRowLen; }
 int commit_wsc_levels() { return 4; }
 
+size_t commit_wsc_scratch_bytes(int num_sms) { return (size_t)(num_sms / 2) * 2 * kCw * sizeof(uint4); }
+
 cudaError_t launch_commit_wsc(const EncodeArgs &a) {
-    const size_t smem = ((size_t)2 * kW * kPL + 64 * kW + (kT / 32) * 256) * sizeof(uint32_t);
+    if (!a.perm1_raw || !a.perm2_raw || !a.wsc_scratch) return cudaErrorInvalidValue;
+    const size_t smem = ((size_t)2 * kW * kPL + 64 * kW) * sizeof(uint32_t);
     cudaError_t err = cudaFuncSetAttribute(commit_wsc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     uint32_t clusters = (uint32_t)a.num_sms / 2;
@@ -338,7 +330,8 @@ cudaError_t launch_commit_wsc(const EncodeArgs &a) {
         err = cudaMemsetAsync(row_counter, 0xff, 2 * sizeof(uint32_t), a.stream);
         if (err != cudaSuccess) return err;
     }
-    commit_wsc_kernel<<<2 * clusters, 2 * kT, smem, a.stream>>>(a.evals, a.rows_out, a.tab1, a.tab2, a.colw, a.num_rows,
+    commit_wsc_kernel<<<2 * clusters, 2 * kT, smem, a.stream>>>(a.evals, a.rows_out, a.perm1_raw, a.perm2_raw,
+                                                                reinterpret_cast<uint4 *>(a.wsc_scratch), a.num_rows,
                                                                 a.fuse_layers, 1u, row_counter);
     return cudaGetLastError();
 }

@@ -15,7 +15,9 @@ struct EncodeArgs {
     const uint16_t *tab1;    // device tables from build_encode_tables, encode_perm_padded_len(cw) entries each
     const uint16_t *tab2;
     const uint8_t *colw;
-    const uint32_t *perm1_raw = nullptr;  // device u32[cw]: perm1 as uploaded (the cw = 16384 commit kernel gathers through it)
+    const uint32_t *perm1_raw = nullptr;  // device u32[cw]: perm1 as uploaded (the cw = 16384 commit kernels gather through it)
+    const uint32_t *perm2_raw = nullptr;  // device u32[cw]: perm2 as uploaded (commit_wsc.cu)
+    void *wsc_scratch = nullptr;          // commit_wsc_scratch_bytes(num_sms) of device memory (commit_wsc.cu: s1 of the rows in flight)
     uint32_t num_rows, row_len, cw, out32;
     int in_limbs;
     int num_sms;
@@ -41,6 +43,7 @@ struct EncodeArgs {
 // the cw = 16384 form as a 2-CTA cluster (commit_wsc.cu): two plane sets split over the shared memories of an SM pair
 bool commit_wsc_supported(uint32_t row_len, uint32_t cw);
 int commit_wsc_levels();
+size_t commit_wsc_scratch_bytes(int num_sms);
 cudaError_t launch_commit_wsc(const EncodeArgs &a);
 bool commit_ws16k_supported(uint32_t row_len, uint32_t cw);
 int commit_ws16k_levels();

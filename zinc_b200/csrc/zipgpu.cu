@@ -969,6 +969,15 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     a.tab2 = code->d_tab2;
     a.colw = code->d_colw;
     a.perm1_raw = code->d_perm1;
+    a.perm2_raw = code->d_perm2;
+    void *wsc_scratch = nullptr;
+    if (fuse_layers && code->d_perm2 && code->in_limbs == 1 && code->out_limbs == 4 &&
+        commit_wsc_supported((uint32_t)code->row_len, (uint32_t)code->cw)) {
+        // the cluster commit kernel of this shape keeps s1 of the rows in flight in an L2-resident scratch
+        cudaError_t ea = dev_alloc(code->ctx, &wsc_scratch, commit_wsc_scratch_bytes(code->ctx->num_sms), s);
+        if (ea != cudaSuccess) return cuda_fail(ea, "dev_alloc(wsc scratch)");
+        a.wsc_scratch = wsc_scratch;
+    }
     a.num_rows = (uint32_t)num_rows;
     a.row_len = (uint32_t)code->row_len;
     a.cw = (uint32_t)code->cw;
@@ -994,6 +1003,7 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     }
     a.stream = s;
     cudaError_t e = launch_raa_encode(a);
+    if (wsc_scratch) dev_free(code->ctx, wsc_scratch, s);
     if (e != cudaSuccess) return cuda_fail(e, "launch_raa_encode");
     code->ctx->launches++;
     if (fan_fused) {  // the exchange of this step is in flight
