@@ -186,6 +186,8 @@ __global__ void __launch_bounds__(MAXT, MINB)
         //         codeword entries back (conflict-free by the XOR swizzle) and each 32-byte Int<4> leaves as ONE
         //         256-bit store, so a warp request covers 1 KiB of contiguous output (8 full 128-byte lines). ----
         uint32_t *dst_row = rows_out + (size_t)row * cw * out32;
+        // (FUSE: no write-out phase -- the hash phase below stores each entry as it loads it for the leaf hash)
+        if constexpr (!FUSE) {
         if constexpr (BULK) {
             // warp w writes out positions [w*32E, (w+1)*32E), 32 consecutive ones (1 KiB of output) per step: the three
             // limbs come back from the planes, the sign-extended 32-byte records go into the warp's tile (lane L puts
@@ -263,6 +265,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
             }
         }
         }
+        }
         // ---- 5b. FUSE: leaf hashes and the lowest log2(E) tree levels of the entries this thread owns ----
         if constexpr (FUSE) {
             constexpr int H = E >= 16 ? 4 : E >= 8 ? 3 : E >= 4 ? 2 : E >= 2 ? 1 : 0;
@@ -279,6 +282,16 @@ __global__ void __launch_bounds__(MAXT, MINB)
 #pragma unroll
                 for (int w = W; w < OUT32; w++) x[w] = sign;
                 const uint32_t idx = t * E + k;  // leaf index within the row
+                {   // the codeword entry itself: x IS the sign-extended record
+                    static_assert(OUT32 % 8 == 0, "fused commit: whole 32-byte vectors per entry");
+                    uint8_t *rec = reinterpret_cast<uint8_t *>(dst_row) + (size_t)idx * (OUT32 * 4);
+#pragma unroll
+                    for (int q = 0; q < OUT32 / 8; q++) {
+                        const uint32_t o[8] = {x[8 * q], x[8 * q + 1], x[8 * q + 2], x[8 * q + 3],
+                                               x[8 * q + 4], x[8 * q + 5], x[8 * q + 6], x[8 * q + 7]};
+                        st_stream_v8(rec + 32 * q, o);
+                    }
+                }
                 b3::Digest d;
                 b3::hash_leaf<OUT32>(x, d.w, one);
                 st_global_v8(lay_row + (size_t)idx * 32, d.w);
@@ -407,26 +420,14 @@ cudaError_t launch_e(const EncodeArgs &a, const EncodeCfg &c, size_t smem) {
     }
 }
 
-// cw = 16384: rows from which the warp-specialised kernel beats the serial fused kernel (scripts/shard_sweep.py
-// --row-len 8192, round 2: 1024 rows 1.066 vs 1.053 ms, 1536: 1.638 vs 1.631, 2048: 2.068 vs 2.074, 4096: 4.070 vs 4.110,
-// 8192: 8.081 vs 8.178).  The fused launches themselves are level (7.93 vs 7.90 ms at 8192 rows: the serial form hashes
-// with all 32 warps of an SM); the gain is the fifth tree level the 32-leaf hash threads fold in, which halves the
-// latency-bound upper passes (0.28 -> 0.15 ms).
-// cw = 16384: the 2-CTA-cluster kernel (commit_wsc.cu) is OPT-IN (ZIPGPU_WSC=1, from ZIPGPU_WSC_MIN_ROWS rows): correct,
-// but measured slower than the single-SM forms -- 8192 rows: fused launch 8.14 ms against 7.94 (commit_ws16k) and 7.90
-// (serial fused kernel); its encoder alone needs 38 us per row (15 us for the same work inside one SM): the two gathers
-// are ~33 K four- and eight-byte distributed-shared-memory transactions per row and CTA, and four cluster meetings.
-static bool wsc_enabled() {
-    const char *e = getenv("ZIPGPU_WSC");
-    return e && e[0] == '1';
-}
-static uint32_t wsc_min_rows() {
-    const char *e = getenv("ZIPGPU_WSC_MIN_ROWS");
-    return e ? (uint32_t)atol(e) : 1024u;
-}
+// cw = 16384: the single-SM warp-specialised kernel (commit_ws16k.cu) is OPT-IN (ZIPGPU_WS16K_MIN_ROWS=<rows>).  While the
+// serial fused kernel had its own write-out phase, ws16k won from 2048 rows (8192 rows: 8.081 vs 8.178 ms, the gain
+// being the fifth tree level its 32-leaf hash threads fold in).  Since the serial kernel stores each entry in the hash
+// phase (no write-out phase at all) it is faster at every row count (scripts/shard_sweep.py --row-len 8192, ms per
+// commit, serial / ws16k): 1024 rows 1.000 / 1.064, 2048: 1.966 / 2.069, 4096: 3.899 / 4.071, 8192: 7.760 / 8.081.
 static uint32_t ws16k_min_rows() {
     const char *e = getenv("ZIPGPU_WS16K_MIN_ROWS");  // read per launch: the tests switch it
-    return e ? (uint32_t)atol(e) : 2048u;
+    return e ? (uint32_t)atol(e) : 0xffffffffu;
 }
 
 template <int IN32, int W>
