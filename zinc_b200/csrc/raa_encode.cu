@@ -425,6 +425,16 @@ cudaError_t launch_e(const EncodeArgs &a, const EncodeCfg &c, size_t smem) {
 // being the fifth tree level its 32-leaf hash threads fold in).  Since the serial kernel stores each entry in the hash
 // phase (no write-out phase at all) it is faster at every row count (scripts/shard_sweep.py --row-len 8192, ms per
 // commit, serial / ws16k): 1024 rows 1.000 / 1.064, 2048: 1.966 / 2.069, 4096: 3.899 / 4.071, 8192: 7.760 / 8.081.
+// cw = 16384: the 2-CTA-cluster kernel (commit_wsc.cu) is OPT-IN too (ZIPGPU_WSC=1, from ZIPGPU_WSC_MIN_ROWS rows): three
+// variants measured, the best 8.16 ms per nv = 26 commit (commit_wsc.cu has the history).
+static bool wsc_enabled() {
+    const char *e = getenv("ZIPGPU_WSC");
+    return e && e[0] == '1';
+}
+static uint32_t wsc_min_rows() {
+    const char *e = getenv("ZIPGPU_WSC_MIN_ROWS");
+    return e ? (uint32_t)atol(e) : 1024u;
+}
 static uint32_t ws16k_min_rows() {
     const char *e = getenv("ZIPGPU_WS16K_MIN_ROWS");  // read per launch: the tests switch it
     return e ? (uint32_t)atol(e) : 0xffffffffu;
