@@ -971,7 +971,8 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     a.perm1_raw = code->d_perm1;
     a.perm2_raw = code->d_perm2;
     void *wsc_scratch = nullptr;
-    if (fuse_layers && code->d_perm2 && code->in_limbs == 1 && code->out_limbs == 4 &&
+    const char *wsc_env = getenv("ZIPGPU_WSC");  // the cluster kernel is opt-in (read per call: the tests switch it)
+    if (wsc_env && wsc_env[0] == '1' && fuse_layers && code->d_perm2 && code->in_limbs == 1 && code->out_limbs == 4 &&
         commit_wsc_supported((uint32_t)code->row_len, (uint32_t)code->cw)) {
         // the cluster commit kernel of this shape keeps s1 of the rows in flight in an L2-resident scratch
         cudaError_t ea = dev_alloc(code->ctx, &wsc_scratch, commit_wsc_scratch_bytes(code->ctx->num_sms), s);
