@@ -68,6 +68,8 @@ struct BigEncodeArgs {
     uint32_t *scratch;        // raa_big_plan() bytes
     uint32_t num_rows, row_len, cw, out32, batch_rows;
     int in_limbs;
+    int num_sms = 0;          // > 0 allows the row-per-CTA form (one persistent CTA per SM)
+    size_t scratch_bytes = 0; // size of `scratch`
     cudaStream_t stream;
 };
 bool raa_big_supported(int in_limbs, uint32_t cw);

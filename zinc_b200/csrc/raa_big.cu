@@ -13,6 +13,7 @@
 // gathers); at these sizes the BLAKE3 passes that follow take 4x longer than this encoder, so the commit is still
 // alu-bound.  The permutations are used as uploaded (u32[cw]); no per-pp table translation.
 #include <algorithm>
+#include <cstdlib>
 
 #include "raa_common.cuh"
 
@@ -149,6 +150,193 @@ __global__ void __launch_bounds__(kBigT)
     }
 }
 
+// ---- the row-per-CTA form (Int<1> inputs, W <= 4, cw a multiple of 16384) ------------------------------------------
+// One persistent 1024-thread CTA per SM takes whole rows, a row in segments of 16384 positions (16 consecutive positions per
+// thread and segment, the running total carried from segment to segment):
+//   pass 1: y1[i] = widen(row[perm1[i] mod row_len]) straight from global memory (the row is L2 / L1 resident), prefix
+//           sum, s1 as 16-byte records into THIS CTA's slice of the scratch -- cw * 16 bytes, written and re-read by the
+//           same SM, so it never leaves L2;
+//   pass 2: y2[i] = s1[perm2[i]] (one ld.global.cg per entry: the slice is rewritten for every row, so L1 must be
+//           bypassed), prefix sum, the finished entry stored sign-extended with one streaming 256-bit store.
+// No chunk totals, no third pass, no intermediate vector in DRAM: the compulsory traffic only (8 B in, out32 * 4 B out per
+// position) in principle -- measured (ncu, 2048 rows of cw = 32768): the 78 MB of scratch slices do not all stay in L2 under
+// the 2 GiB of streaming output (DRAM 2.1 GB read + 4.9 GB written for 2.4 GB compulsory), and the random 8- and 16-byte
+// gathers keep the load/store unit's queue full.  nv = 27 (8192 rows): encode 7.78 ms (three chunked launches) -> 6.28 ms,
+// commit 22.5 -> 21.0 ms; the BLAKE3 passes that follow take 14.7 ms.  ZIPGPU_BIG_CHUNKED=1 selects the chunked form.
+constexpr int kRowT = 1024, kRowE = 16, kRowSeg = kRowT * kRowE;
+
+template <int W>
+__global__ void __launch_bounds__(kRowT, 1)
+    raa_big_row_kernel(const uint32_t *__restrict__ evals, const uint32_t *__restrict__ perm1, const uint32_t *__restrict__ perm2,
+                       uint4 *scratch, uint32_t *__restrict__ rows_out, uint32_t num_rows, uint32_t row_len, uint32_t cw,
+                       uint32_t out32) {
+    constexpr int IN32 = 2;
+    // W == 3: a warp's 512 entries go through a [3][16][32] tile of its own (the XOR swizzle of slot_of<16>: lane-major
+    // writes and position-major reads are both conflict free) so that every global store instruction of a warp covers
+    // 32 CONSECUTIVE positions -- 512 contiguous bytes of s1 records, 1 KiB of output.  (Stored straight from the
+    // registers that hold 16 consecutive positions per lane, each instruction touched 32 different lines: ncu showed the
+    // load/store unit's queue as the limiter, lg_throttle 27 of 77 stalled warps per issue.)
+    constexpr bool TILE = W == 3;
+    extern __shared__ __align__(16) uint32_t tiles[];  // TILE: [32 warps][3][512] words
+    __shared__ uint32_t aux[64 * W];
+    __shared__ uint32_t s_tot[W];
+    const uint32_t t = threadIdx.x;
+    const uint32_t lane = t & 31u;
+    uint32_t *tile = tiles + (TILE ? (t >> 5) * (3 * 512) : 0);
+    uint4 *s1 = scratch + (size_t)blockIdx.x * cw;
+    const uint32_t nseg = cw / kRowSeg;
+    const bool pow2 = (row_len & (row_len - 1)) == 0;
+    for (uint32_t row = blockIdx.x; row < num_rows; row += gridDim.x) {
+        const uint2 *erow = reinterpret_cast<const uint2 *>(evals + (size_t)row * row_len * IN32);
+        uint32_t carry[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) carry[w] = 0u;
+        // ---- pass 1 ----
+#pragma unroll 1
+        for (uint32_t seg = 0; seg < nseg; seg++) {
+            const uint32_t i0 = seg * kRowSeg + t * kRowE;
+            const uint4 *p4 = reinterpret_cast<const uint4 *>(perm1 + i0);
+            uint32_t v[kRowE][W];
+#pragma unroll
+            for (int q = 0; q < kRowE / 4; q++) {
+                const uint4 pi = __ldg(p4 + q);
+                const uint32_t src[4] = {pi.x, pi.y, pi.z, pi.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t e = pow2 ? (src[j] & (row_len - 1)) : (src[j] % row_len);
+                    const uint2 x = __ldg(erow + e);
+                    v[4 * q + j][0] = x.x;
+                    v[4 * q + j][1] = x.y;
+                    const uint32_t sign = (uint32_t)((int32_t)x.y >> 31);
+#pragma unroll
+                    for (int w = IN32; w < W; w++) v[4 * q + j][w] = sign;
+                }
+            }
+            uint32_t pre[W];
+            block_scan<W, kRowE>(v, pre, aux, t, kRowT / 32);
+            add_limbs<W>(pre, carry);
+            if constexpr (TILE) {
+#pragma unroll
+                for (int k = 0; k < kRowE; k++) {
+                    add_limbs<W>(v[k], pre);
+                    const uint32_t sl = slot_of<kRowE>(lane, k, 32);
+#pragma unroll
+                    for (int w = 0; w < W; w++) tile[w * 512 + sl] = v[k][w];
+                }
+                __syncwarp();
+                uint4 *dst = s1 + seg * kRowSeg + (t >> 5) * 512;  // this warp's 512 consecutive positions
+#pragma unroll
+                for (int j = 0; j < kRowE; j++) {
+                    const uint32_t p = j * 32 + lane, sl = slot_of<kRowE>(p / kRowE, p % kRowE, 32);
+                    dst[p] = make_uint4(tile[sl], tile[512 + sl], tile[1024 + sl], 0u);
+                }
+                __syncwarp();
+            } else {
+#pragma unroll
+                for (int k = 0; k < kRowE; k++) {
+                    add_limbs<W>(v[k], pre);
+                    s1[i0 + k] = make_uint4(v[k][0], v[k][1], v[k][2], W > 3 ? v[k][W > 3 ? 3 : 0] : 0u);
+                }
+            }
+            if (t == kRowT - 1) {
+#pragma unroll
+                for (int w = 0; w < W; w++) s_tot[w] = v[kRowE - 1][w];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < W; w++) carry[w] = s_tot[w];
+            __syncthreads();  // (s_tot and aux are reused by the next segment)
+        }
+        // every s1 record of the row is written (the barriers above order the CTA's own global writes for its own reads)
+#pragma unroll
+        for (int w = 0; w < W; w++) carry[w] = 0u;
+        uint32_t *orow = rows_out + (size_t)row * cw * out32;
+        // ---- pass 2 ----
+#pragma unroll 1
+        for (uint32_t seg = 0; seg < nseg; seg++) {
+            const uint32_t i0 = seg * kRowSeg + t * kRowE;
+            const uint4 *p4 = reinterpret_cast<const uint4 *>(perm2 + i0);
+            uint32_t v[kRowE][W];
+#pragma unroll
+            for (int q = 0; q < kRowE / 4; q++) {
+                const uint4 pi = __ldg(p4 + q);
+                const uint32_t src[4] = {pi.x, pi.y, pi.z, pi.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint4 r;
+                    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                                 : "l"(s1 + src[j]));
+                    v[4 * q + j][0] = r.x;
+                    v[4 * q + j][1] = r.y;
+                    v[4 * q + j][2] = r.z;
+                    if constexpr (W > 3) v[4 * q + j][3] = r.w;
+                }
+            }
+            uint32_t pre[W];
+            block_scan<W, kRowE>(v, pre, aux, t, kRowT / 32);
+            add_limbs<W>(pre, carry);
+            if constexpr (TILE) {
+#pragma unroll
+                for (int k = 0; k < kRowE; k++) {
+                    add_limbs<W>(v[k], pre);
+                    const uint32_t sl = slot_of<kRowE>(lane, k, 32);
+#pragma unroll
+                    for (int w = 0; w < W; w++) tile[w * 512 + sl] = v[k][w];
+                }
+                __syncwarp();
+                uint32_t *dw = orow + (size_t)(seg * kRowSeg + (t >> 5) * 512) * out32;
+#pragma unroll
+                for (int j = 0; j < kRowE; j++) {
+                    const uint32_t p = j * 32 + lane, sl = slot_of<kRowE>(p / kRowE, p % kRowE, 32);
+                    const uint32_t a0 = tile[sl], a1 = tile[512 + sl], a2 = tile[1024 + sl];
+                    const uint32_t sign = (uint32_t)((int32_t)a2 >> 31);
+                    uint32_t *d = dw + (size_t)p * out32;
+                    const uint32_t rec0[8] = {a0, a1, a2, sign, sign, sign, sign, sign};
+                    st_stream_v8(d, rec0);
+                    const uint32_t recs[8] = {sign, sign, sign, sign, sign, sign, sign, sign};
+                    for (uint32_t o = 8; o < out32; o += 8) st_stream_v8(d + o, recs);
+                }
+                __syncwarp();
+            } else {
+#pragma unroll
+                for (int k = 0; k < kRowE; k++) {
+                    add_limbs<W>(v[k], pre);
+                    const uint32_t sign = (uint32_t)((int32_t)v[k][W - 1] >> 31);
+                    uint32_t *d = orow + (size_t)(i0 + k) * out32;
+                    for (uint32_t o = 0; o < out32; o += 8) {
+                        uint32_t rec[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) rec[j] = (o + j < (uint32_t)W) ? v[k][(o + j < (uint32_t)W) ? o + j : 0] : sign;
+                        st_stream_v8(d + o, rec);
+                    }
+                }
+            }
+            if (t == kRowT - 1) {
+#pragma unroll
+                for (int w = 0; w < W; w++) s_tot[w] = v[kRowE - 1][w];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < W; w++) carry[w] = s_tot[w];
+            __syncthreads();
+        }
+        // (the next row's pass 1 overwrites s1: every gather of this row is done -- the barriers of the last segment)
+    }
+}
+
+template <int W>
+cudaError_t launch_big_rows(const BigEncodeArgs &a, uint32_t grid) {
+    const size_t smem = W == 3 ? (size_t)(kRowT / 32) * 3 * 512 * sizeof(uint32_t) : 0;  // the warps' transposition tiles
+    if (smem) {
+        cudaError_t e = cudaFuncSetAttribute(raa_big_row_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    raa_big_row_kernel<W><<<grid, kRowT, smem, a.stream>>>(a.evals, a.perm1, a.perm2, reinterpret_cast<uint4 *>(a.scratch), a.rows_out,
+                                                        a.num_rows, a.row_len, a.cw, a.out32);
+    return cudaGetLastError();
+}
+
 template <int IN32, int W>
 cudaError_t launch_big_w(const BigEncodeArgs &a) {
     constexpr int SW = W <= 4 ? 4 : 8;
@@ -194,6 +382,16 @@ bool raa_big_supported(int in_limbs, uint32_t cw) {
 
 cudaError_t launch_raa_encode_big(const BigEncodeArgs &a, int *launches) {
     const int W = encode_compute_limbs(a.in_limbs, a.cw);
+    // the row-per-CTA form: Int<1> inputs, whole segments, 32-byte-vector output records, scratch for one row per CTA
+    if (a.in_limbs == 1 && W <= 4 && a.cw % kRowSeg == 0 && (a.out32 & 7u) == 0 && a.num_sms > 0 && !getenv("ZIPGPU_BIG_CHUNKED")) {
+        uint32_t grid = std::min<uint32_t>((uint32_t)a.num_sms, a.num_rows);
+        const size_t per_cta = (size_t)a.cw * sizeof(uint4);
+        if (a.scratch_bytes >= per_cta) {
+            grid = (uint32_t)std::min<size_t>(grid, a.scratch_bytes / per_cta);
+            if (launches) *launches = 1;
+            return W <= 3 ? launch_big_rows<3>(a, grid) : launch_big_rows<4>(a, grid);
+        }
+    }
     if (launches) *launches = 3 * (int)((a.num_rows + a.batch_rows - 1) / a.batch_rows);
     if (a.in_limbs == 1 && W <= 3) return launch_big_w<2, 3>(a);
     if (a.in_limbs == 1 && W == 4) return launch_big_w<2, 4>(a);

@@ -953,6 +953,8 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
         b.stream = s;
         size_t scratch_bytes = 0;
         raa_big_plan(code->in_limbs, b.cw, b.num_rows, &b.batch_rows, &scratch_bytes);
+        b.num_sms = ctx->num_sms;
+        b.scratch_bytes = scratch_bytes;
         DevGuard guard(ctx, s);
         DEV_ALLOC(ctx, &b.scratch, scratch_bytes, s);
         int n = 0;
