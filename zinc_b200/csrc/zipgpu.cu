@@ -1919,7 +1919,7 @@ extern "C" int zipgpu_data_read_layers(const zipgpu_data *d, size_t row_begin, s
     API_LOCK(d->ctx);
     CU(cudaSetDevice(d->ctx->device));
     const size_t lb = layers_per_row(d->depth) * 32;
-    if (lb * row_count) {
+    if (lb != 0 && row_count != 0) {
         CU(cudaMemcpyAsync(layers_out, d->d_layers + row_begin * lb, row_count * lb, cudaMemcpyDeviceToHost,
                            d->ctx->stream));
         CU(cudaStreamSynchronize(d->ctx->stream));
