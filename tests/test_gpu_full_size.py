@@ -541,7 +541,7 @@ def test_peer_roots_two_gpus():
     assert res == [(0, True), (1, True)], res
 
 
-@pytest.mark.parametrize("chunked", [False, True])
+@pytest.mark.parametrize("chunked", [False, True, "fused"])
 @pytest.mark.parametrize("row_len,num_rows,limbs", [(16384, 37, 1), (16384, 301, 1), (32768, 5, 1), (65536, 3, 1), (16384, 6, 2)])
 def test_codewords_longer_than_shared_memory(row_len, num_rows, limbs, chunked, oracle, ctx, monkeypatch):
     """cw = 32768 / 65536 / 131072 (nv = 27 ... 34 row shapes; code_raa.rs:42-43 and structs.rs:79-90 put no bound on nv):
@@ -550,7 +550,9 @@ def test_codewords_longer_than_shared_memory(row_len, num_rows, limbs, chunked, 
     rows = more than one row per CTA) and the three chunked launches (forced, and what Int<2> inputs use) -- codewords,
     every Merkle layer and the roots of a row sample against the oracle; cw = 131072 needs 98-bit entries (4-limb scans),
     Int<2> inputs 5-limb scans"""
-    if chunked:
+    if chunked == "fused":  # the commit form of the row-per-CTA encoder (leaves + tree levels 1..4 in the same launch;
+        monkeypatch.setenv("ZIPGPU_FUSE_MIN_ROWS", "1")  # taken from 888 rows by default), where the shape has one
+    elif chunked:
         monkeypatch.setenv("ZIPGPU_BIG_CHUNKED", "1")
     from zinc_b200 import DenseMultilinearExtension, MultilinearZip, MultilinearZipParams, RaaCode, RandomFieldZipTypes
 

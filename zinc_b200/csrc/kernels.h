@@ -68,11 +68,13 @@ struct BigEncodeArgs {
     uint32_t *scratch;        // raa_big_plan() bytes
     uint32_t num_rows, row_len, cw, out32, batch_rows;
     int in_limbs;
+    uint8_t *fuse_layers = nullptr;  // non-NULL: the fused commit form (leaves + tree levels 1..raa_big_fused_levels())
     int num_sms = 0;          // > 0 allows the row-per-CTA form (one persistent CTA per SM)
     size_t scratch_bytes = 0; // size of `scratch`
     cudaStream_t stream;
 };
 bool raa_big_supported(int in_limbs, uint32_t cw);
+int raa_big_fused_levels(int in_limbs, int out_limbs, uint32_t cw);
 void raa_big_plan(int in_limbs, uint32_t cw, uint32_t num_rows, uint32_t *batch_rows, size_t *scratch_bytes);
 cudaError_t launch_raa_encode_big(const BigEncodeArgs &a, int *launches);
 

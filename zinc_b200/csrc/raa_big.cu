@@ -165,11 +165,16 @@ __global__ void __launch_bounds__(kBigT)
 // commit 22.5 -> 21.0 ms; the BLAKE3 passes that follow take 14.7 ms.  ZIPGPU_BIG_CHUNKED=1 selects the chunked form.
 constexpr int kRowT = 1024, kRowE = 16, kRowSeg = kRowT * kRowE;
 
-template <int W>
+// FUSE (W == 3, Int<4> entries): the commit form -- after the second prefix sum of a segment every thread also hashes the
+// 16 entries it owns (BLAKE3 leaves + tree levels 1..4, read back from its warp's tile) and stores entry, leaf digest and
+// nodes itself, like the serial fused kernel of raa_encode.cu: the leaf pass that would re-read the whole codeword from
+// HBM (8 GiB at nv = 27) disappears.
+template <int W, bool FUSE>
 __global__ void __launch_bounds__(kRowT, 1)
     raa_big_row_kernel(const uint32_t *__restrict__ evals, const uint32_t *__restrict__ perm1, const uint32_t *__restrict__ perm2,
                        uint4 *scratch, uint32_t *__restrict__ rows_out, uint32_t num_rows, uint32_t row_len, uint32_t cw,
-                       uint32_t out32) {
+                       uint32_t out32, uint8_t *__restrict__ layers, uint32_t one) {
+    static_assert(!FUSE || W == 3, "the fused form hashes from the 3-limb tiles");
     constexpr int IN32 = 2;
     // W == 3: a warp's 512 entries go through a [3][16][32] tile of its own (the XOR swizzle of slot_of<16>: lane-major
     // writes and position-major reads are both conflict free) so that every global store instruction of a warp covers
@@ -285,6 +290,37 @@ __global__ void __launch_bounds__(kRowT, 1)
                     for (int w = 0; w < W; w++) tile[w * 512 + sl] = v[k][w];
                 }
                 __syncwarp();
+                if constexpr (FUSE) {
+                    uint8_t *lay_row = layers + (size_t)row * (2 * (size_t)cw - 2) * 32;
+                    b3::Digest stack[4];
+#pragma unroll 1
+                    for (uint32_t k = 0; k < (uint32_t)kRowE; k++) {
+                        const uint32_t sl = slot_of<kRowE>(lane, k, 32);
+                        uint32_t x[8];
+                        x[0] = tile[sl];
+                        x[1] = tile[512 + sl];
+                        x[2] = tile[1024 + sl];
+                        const uint32_t sign = (uint32_t)((int32_t)x[2] >> 31);
+#pragma unroll
+                        for (int w = 3; w < 8; w++) x[w] = sign;
+                        const uint32_t idx = i0 + k;  // leaf index within the row
+                        st_stream_v8(orow + (size_t)idx * 8, x);
+                        b3::Digest d;
+                        b3::hash_leaf<8>(x, d.w, one);
+                        st_global_v8(lay_row + (size_t)idx * 32, d.w);
+#pragma unroll 1
+                        for (int l = 0; l < 4; l++) {
+                            if ((k >> l) & 1u) {
+                                d = b3::hash_node_call(stack[l], d, one);
+                                const size_t off = 2 * (size_t)cw - ((2 * (size_t)cw) >> (l + 1));
+                                st_global_v8(lay_row + (off + (idx >> (l + 1))) * 32, d.w);
+                            } else {
+                                stack[l] = d;
+                                break;
+                            }
+                        }
+                    }
+                } else {
                 uint32_t *dw = orow + (size_t)(seg * kRowSeg + (t >> 5) * 512) * out32;
 #pragma unroll
                 for (int j = 0; j < kRowE; j++) {
@@ -296,6 +332,7 @@ __global__ void __launch_bounds__(kRowT, 1)
                     st_stream_v8(d, rec0);
                     const uint32_t recs[8] = {sign, sign, sign, sign, sign, sign, sign, sign};
                     for (uint32_t o = 8; o < out32; o += 8) st_stream_v8(d + o, recs);
+                }
                 }
                 __syncwarp();
             } else {
@@ -325,15 +362,15 @@ __global__ void __launch_bounds__(kRowT, 1)
     }
 }
 
-template <int W>
+template <int W, bool FUSE>
 cudaError_t launch_big_rows(const BigEncodeArgs &a, uint32_t grid) {
     const size_t smem = W == 3 ? (size_t)(kRowT / 32) * 3 * 512 * sizeof(uint32_t) : 0;  // the warps' transposition tiles
     if (smem) {
-        cudaError_t e = cudaFuncSetAttribute(raa_big_row_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(raa_big_row_kernel<W, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    raa_big_row_kernel<W><<<grid, kRowT, smem, a.stream>>>(a.evals, a.perm1, a.perm2, reinterpret_cast<uint4 *>(a.scratch), a.rows_out,
-                                                        a.num_rows, a.row_len, a.cw, a.out32);
+    raa_big_row_kernel<W, FUSE><<<grid, kRowT, smem, a.stream>>>(a.evals, a.perm1, a.perm2, reinterpret_cast<uint4 *>(a.scratch),
+                                                              a.rows_out, a.num_rows, a.row_len, a.cw, a.out32, a.fuse_layers, 1u);
     return cudaGetLastError();
 }
 
@@ -375,6 +412,13 @@ void raa_big_plan(int in_limbs, uint32_t cw, uint32_t num_rows, uint32_t *batch_
     *scratch_bytes = rows * per_row + 256;
 }
 
+// tree levels the fused commit form of the row-per-CTA encoder builds (0: no fused form for this shape)
+int raa_big_fused_levels(int in_limbs, int out_limbs, uint32_t cw) {
+    if (getenv("ZIPGPU_BIG_CHUNKED") || getenv("ZIPGPU_BIG_NO_FUSE")) return 0;
+    if (in_limbs != 1 || out_limbs != 4 || cw % kRowSeg != 0 || (cw & (cw - 1)) != 0) return 0;
+    return encode_compute_limbs(in_limbs, cw) <= 3 ? 4 : 0;
+}
+
 bool raa_big_supported(int in_limbs, uint32_t cw) {
     const int W = encode_compute_limbs(in_limbs, cw);
     return cw <= (1u << 24) && ((in_limbs == 1 && (W == 3 || W == 4)) || (in_limbs == 2 && (W == 5 || W == 6)));
@@ -389,9 +433,14 @@ cudaError_t launch_raa_encode_big(const BigEncodeArgs &a, int *launches) {
         if (a.scratch_bytes >= per_cta) {
             grid = (uint32_t)std::min<size_t>(grid, a.scratch_bytes / per_cta);
             if (launches) *launches = 1;
-            return W <= 3 ? launch_big_rows<3>(a, grid) : launch_big_rows<4>(a, grid);
+            if (a.fuse_layers) {
+                if (W > 3 || a.out32 != 8) return cudaErrorInvalidConfiguration;
+                return launch_big_rows<3, true>(a, grid);
+            }
+            return W <= 3 ? launch_big_rows<3, false>(a, grid) : launch_big_rows<4, false>(a, grid);
         }
     }
+    if (a.fuse_layers) return cudaErrorInvalidConfiguration;  // (raa_big_fused_levels() says where the fused form exists)
     if (launches) *launches = 3 * (int)((a.num_rows + a.batch_rows - 1) / a.batch_rows);
     if (a.in_limbs == 1 && W <= 3) return launch_big_w<2, 3>(a);
     if (a.in_limbs == 1 && W == 4) return launch_big_w<2, 4>(a);

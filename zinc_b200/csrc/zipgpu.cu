@@ -536,7 +536,7 @@ extern "C" int zipgpu_code_create(zipgpu_ctx *ctx, size_t row_len, size_t rep, i
     cudaError_t e;
     if (big) {  // the chunked encoder reads the permutations as they are
         c->big = true;
-        c->fused_levels = 0;
+        c->fused_levels = c->depth > 0 && merkle_supported(out_limbs * 2) ? raa_big_fused_levels(in_limbs, out_limbs, (uint32_t)cw) : 0;
         if ((e = cudaMalloc(&c->d_perm1, cw * 4)) != cudaSuccess || (e = cudaMalloc(&c->d_perm2, cw * 4)) != cudaSuccess ||
             (e = cudaMemcpy(c->d_perm1, perm1, cw * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
             (e = cudaMemcpy(c->d_perm2, perm2, cw * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
@@ -938,9 +938,12 @@ static int encode_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
         return ZIPGPU_OK;
     }
     if (code->big) {
-        if (fuse_layers || evals_copy) return fail(ZIPGPU_ERR_INVALID, "no fused commit kernel for codewords > 16384");
+        if (evals_copy || (fuse_layers && code->fused_levels <= 0))
+            return fail(ZIPGPU_ERR_INVALID, "no fused commit kernel for this codeword length");
         zipgpu_ctx *ctx = code->ctx;
         BigEncodeArgs b;
+        b.fuse_layers = fuse_layers;
+        if (fuse_layers && fused_levels) *fused_levels = code->fused_levels;
         b.evals = reinterpret_cast<const uint32_t *>(d_evals);
         b.rows_out = reinterpret_cast<uint32_t *>(d_rows);
         b.perm1 = code->d_perm1;
