@@ -1097,8 +1097,17 @@ static int commit_dev(zipgpu_code *code, size_t num_rows, const uint64_t *d_eval
     // The fused kernel is one persistent CTA pair per SM: it needs a few rows per CTA for one CTA's encode phases to
     // run under the other's hashing; below that the two-kernel path, whose hash passes balance at subtree granularity,
     // is faster.
-    const bool fuse = d_roots && d_layers && code->fused_levels > 0 && code->fused_levels <= code->depth &&
-                      num_rows >= fuse_min_rows(ctx, code) && fusion_enabled();
+    bool rows_ok = num_rows >= fuse_min_rows(ctx, code);
+    if (!rows_ok && !getenv("ZIPGPU_FUSE_MIN_ROWS") && !code->big && !code->sparse && code->in_limbs == 1 && code->out_limbs == 4 &&
+        commit_ws16k_supported((uint32_t)code->row_len, (uint32_t)code->cw)) {
+        // cw = 16384: one 1024-thread CTA per SM takes a row at a time, so below the threshold the serial fused kernel
+        // still wins whenever the rows fill whole waves (296 rows: 0.309 vs 0.340 ms, 740: 0.723 vs 0.798; but 512 rows =
+        // 3.46 waves: 0.584 vs 0.576)
+        const size_t sms = (size_t)ctx->num_sms, waves = (num_rows + sms - 1) / sms;
+        rows_ok = waves * sms * 100 <= num_rows * 112;
+    }
+    const bool fuse = d_roots && d_layers && code->fused_levels > 0 && code->fused_levels <= code->depth && rows_ok &&
+                      fusion_enabled();
     if (evals_copy && !fuse) return fail(ZIPGPU_ERR_INVALID, "zero-copy input needs the fused commit kernel");
     // Sparse code on the tensor cores: the GEMM (TMA + tcgen05, 6 warps per SM, hardly any INT32 work) and the BLAKE3
     // passes (INT32-alu-bound, no shared memory) use different parts of an SM.  Row chunks are encoded back to back on
